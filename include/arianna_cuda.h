@@ -1,0 +1,193 @@
+/*
+ * arianna_cuda.h -- C ABI of libarianna_cuda.so, the B200 (sm_100a) multi-chain Metropolis engine that
+ * drops in behind Arianna.jl's `Metropolis` / `StoreCallbacks` / `StoreTrajectories` /
+ * `PolicyGradientEstimator` for `particle_1d`-type systems.
+ *
+ * Arianna has no FFI of its own (it is pure Julia); the "reference interface" each entry point replaces is
+ * the Julia method it stands in for, cited as path:line under the reference tree.  INTEGRATION.md shows the
+ * `ccall` bindings of the Julia shim.
+ *
+ * Conventions
+ *   - every function returns an int32 status (ARIANNA_OK == 0); nothing throws or aborts across the ABI;
+ *   - arianna_last_error(h) returns a NUL-terminated message owned by the handle (h may be NULL for errors
+ *     raised by arianna_create itself: thread-local storage);
+ *   - host pointers are borrowed for the duration of the call only;  all calls on one handle must come from
+ *     one host thread at a time;
+ *   - kernels are enqueued asynchronously on the handle's stream; every function that returns numbers to the
+ *     host synchronises that stream first;
+ *   - one handle == one GPU == one contiguous shard [chain_offset, chain_offset + n_chains) of the global
+ *     ensemble.  Multi-GPU = one process (or handle) per GPU; per-chain results do not depend on the sharding
+ *     because the RNG stream of a chain is keyed by its GLOBAL index.
+ */
+#ifndef ARIANNA_CUDA_H
+#define ARIANNA_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARIANNA_ABI_VERSION 1
+#if defined(__GNUC__)
+#define ARIANNA_API __attribute__((visibility("default")))
+#else
+#define ARIANNA_API
+#endif
+#define ARIANNA_MAX_MOVES 16
+
+typedef struct arianna_handle arianna_handle;
+
+enum arianna_status {
+    ARIANNA_OK = 0,
+    ARIANNA_ERR_INVALID = 1,     /* bad argument (the Julia shim throws ArgumentError)                   */
+    ARIANNA_ERR_CUDA = 2,        /* a CUDA runtime call failed; message holds cudaGetErrorString          */
+    ARIANNA_ERR_NOMEM = 3,       /* device or host allocation failed                                      */
+    ARIANNA_ERR_UNSUPPORTED = 4, /* valid request this build cannot serve (e.g. replay with XOSHIRO rng)  */
+    ARIANNA_ERR_NO_DEVICE = 5    /* no CUDA device: there is NO CPU fallback                              */
+};
+
+/* potential(x): the script-level global of the examples (MC_harmonic_oscillator.jl:4, test/runtests). */
+enum arianna_potential {
+    ARIANNA_POT_HARMONIC = 0,    /* x^2                                                                   */
+    ARIANNA_POT_QUARTIC = 1,     /* x^4                                                                   */
+    ARIANNA_POT_DOUBLE_WELL = 2  /* (x^2 - 1)^2                                                           */
+};
+
+enum arianna_rng_mode {
+    ARIANNA_RNG_PHILOX = 0,      /* in-register counter-based Philox4x32-10 + Box-Muller (native mode)     */
+    ARIANNA_RNG_XOSHIRO = 1      /* per-chain xoshiro256++ state + ziggurat randn, the reference's generator
+                                    family (Random.Xoshiro [EXT]); states uploaded with arianna_set_rng_state */
+};
+
+enum arianna_arith_mode {
+    ARIANNA_ARITH_EXACT = 0,     /* the reference's exact binary64 operation order, no FMA contraction
+                                                                                   */
+    ARIANNA_ARITH_FAST = 1       /* algebraically equal, symmetric-proposal cancellation, exact restore on
+                                    reject                                                                 */
+};
+
+/* Flags of arianna_sweep */
+#define ARIANNA_SWEEP_REDUCE 1u  /* fuse the callback reductions (energy / acceptance sums) into the sweep  */
+
+typedef struct arianna_config {
+    uint32_t struct_size;        /* = sizeof(arianna_config); ABI guard                                    */
+    int32_t device;              /* CUDA device ordinal; -1 = the calling thread's current device          */
+    int64_t n_chains;            /* chains held by THIS handle (local shard), >= 1                         */
+    int64_t chain_offset;        /* global 0-based index of the first local chain                          */
+    int64_t n_chains_total;      /* global ensemble size (denominator of the callback means); 0 = n_chains */
+    int64_t seed;                /* `seed` of Metropolis(chains; seed=...) (metropolis.jl:288): chain c
+                                    (1-based, global) owns stream  seed + c - 1  (metropolis.jl:262)        */
+    double beta;                 /* Particle.β (particle_1d.jl:11), shared by all chains unless
+                                    arianna_set_betas is called                                            */
+    int32_t potential;           /* enum arianna_potential                                                 */
+    int32_t n_moves;             /* pool size, 1 .. ARIANNA_MAX_MOVES                                      */
+    double sigma[ARIANNA_MAX_MOVES];  /* Move.parameters.σ per move (ComponentArray(σ=...))                */
+    double weight[ARIANNA_MAX_MOVES]; /* Move.weight per move; must sum to 1 (Categorical validates [EXT]) */
+    int32_t rng_mode;            /* enum arianna_rng_mode                                                  */
+    int32_t arith_mode;          /* enum arianna_arith_mode                                                */
+    void *stream;                /* optional cudaStream_t to run on; NULL = the handle creates its own     */
+} arianna_config;
+
+/* Summed GradientData record of one learnable move (gradients.jl:41-47), P = 1 parameter (σ). */
+typedef struct arianna_gradient_data {
+    double j;                    /* Σ objective r·α                                                        */
+    double dj;                   /* Σ ∇j                                                                   */
+    double dlogq_forward;        /* Σ ∇logq_forward                                                        */
+    double g;                    /* Σ ∇logq_f · ∇logq_fᵀ                                                   */
+    double n;                    /* sample count (exact integer in binary64)                               */
+} arianna_gradient_data;
+
+ARIANNA_API uint32_t arianna_abi_version(void);
+ARIANNA_API const char *arianna_last_error(const arianna_handle *h);
+
+/* Lifecycle.  Replaces Metropolis(chains; pool, seed, ...) (metropolis.jl:240-291) + the per-chain heap
+ * objects of `chains::Vector{Particle}` (particle_1d.jl:9-16): chains live only in HBM. */
+ARIANNA_API int32_t arianna_create(const arianna_config *cfg, arianna_handle **out);
+ARIANNA_API int32_t arianna_destroy(arianna_handle *h);
+
+/* Chain state.  set: `[System(x, β) for ...]` (MC_harmonic_oscillator.jl:13); e = potential(x) is derived.
+ * init_synthetic: x0 = 4u - 2 from the engine's counter-based stream (same expression, :13).
+ * get: what store_trajectory / callback_energy read, `system.x`, `system.e` (particle_1d.jl:63-70);
+ * either pointer may be NULL.  Resets nothing. */
+ARIANNA_API int32_t arianna_set_state(arianna_handle *h, const double *x);
+ARIANNA_API int32_t arianna_init_synthetic(arianna_handle *h, int64_t seed);
+ARIANNA_API int32_t arianna_get_state(arianna_handle *h, double *x, double *e);
+/* Asynchronous variant for StoreTrajectories at scale (algorithms.jl:198-203): enqueues the D2H copy of x
+ * into caller-pinned memory and returns; arianna_synchronize() completes it. */
+ARIANNA_API int32_t arianna_get_state_async(arianna_handle *h, double *x_pinned);
+ARIANNA_API int32_t arianna_set_beta(arianna_handle *h, double beta);
+ARIANNA_API int32_t arianna_set_betas(arianna_handle *h, const double *betas); /* per-chain β, [n_chains] host */
+
+/* Policy parameters θ = (σ) of move `move_id` (0-based): the shared `parameters` array every chain's Move
+ * aliases (metropolis.jl:253-260), mutated in place by learning_step! (learning.jl:33).  P must be 1.
+ * log_norm (optional, may be NULL) lets the host pass its own binary64 value of log(2π·σ²)/2
+ * (particle_1d.jl:53) so that replay is bit-exact with the host language's `log`. */
+ARIANNA_API int32_t arianna_set_params(arianna_handle *h, int32_t move_id, const double *theta, int32_t P,
+                           const double *log_norm);
+ARIANNA_API int32_t arianna_get_params(arianna_handle *h, int32_t move_id, double *theta, int32_t P);
+
+/* K fused Metropolis steps for every local chain, native RNG (cfg.rng_mode).  Replaces K consecutive
+ * make_step!(sim, ::Metropolis) calls with sweepstep = 1 (metropolis.jl:302-309 -> mc_sweep! :203-212 ->
+ * mc_step! :176-190).  Asynchronous. */
+ARIANNA_API int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags);
+
+/* Replay mode: the same K steps consuming caller-supplied draws instead of the native RNG, always in EXACT
+ * arithmetic.  u_cat / z / u_acc are step-major [K][n_chains] (u_cat may be NULL when n_moves == 1);
+ * `on_device` != 0 means the three pointers (and decisions_out) are device pointers.  decisions_out
+ * (optional) receives mc_step!'s return value (metropolis.jl:185,188) per step and chain. */
+ARIANNA_API int32_t arianna_sweep_replay(arianna_handle *h, int64_t K, const double *u_cat, const double *z,
+                             const double *u_acc, uint8_t *decisions_out, int32_t on_device);
+
+/* XOSHIRO mode: per-chain generator states [n_chains][4] uint64 (Xoshiro.s0..s3 [EXT]); tables: the
+ * 256-entry ziggurat tables ki/wi/fi of the host's randn [EXT] (NULL = engine-generated). */
+ARIANNA_API int32_t arianna_set_rng_state(arianna_handle *h, const uint64_t *states);
+ARIANNA_API int32_t arianna_get_rng_state(arianna_handle *h, uint64_t *states);
+ARIANNA_API int32_t arianna_set_ziggurat_tables(arianna_handle *h, const uint64_t *ki, const double *wi, const double *fi);
+
+/* Callbacks.  callback_energy (particle_1d.jl:68-70) and callback_acceptance (metropolis.jl:319-321: per
+ * move, the mean over chains of accepted_calls/total_calls, NaN while some chain never tried the move).
+ * arianna_callbacks returns the means over THIS handle's chains (the local shard); multi-GPU hosts use the
+ * *_sums variants and combine across shards:
+ *   sums[0] = Σ e,  sums[1 + k] = Σ_c acc_ck / tot_ck,  sums[1 + n_moves] = local chain count.
+ * arianna_callback_sums_device exposes the device buffer holding those 2 + n_moves doubles (valid until the
+ * next sweep) for an NCCL all-reduce without a host round trip; the host finishes the division. */
+ARIANNA_API int32_t arianna_callbacks(arianna_handle *h, double *mean_energy, double *acc_per_move);
+ARIANNA_API int32_t arianna_callback_sums(arianna_handle *h, double *sums);
+ARIANNA_API int32_t arianna_callback_sums_device(arianna_handle *h, double **dptr, int32_t *n);
+
+/* Move counters summed over the local chains (what a single-ensemble host `Move` would hold), and the raw
+ * per-chain counters [n_moves][n_chains]. */
+ARIANNA_API int32_t arianna_get_counters(arianna_handle *h, int64_t *accepted, int64_t *total);
+ARIANNA_API int32_t arianna_get_chain_counters(arianna_handle *h, uint32_t *accepted, uint32_t *total);
+
+/* PGMC.  One make_step!(sim, ::PolicyGradientEstimator) (estimator.jl:111-134): for each learnable move
+ * (0-based ids, in order) and each chain, q_batch samples of sample_gradient_data/pgmc_estimate
+ * (gradients.jl:93-121) with the analytic ∂σ log q = δ²/σ³ − 1/σ, summed into the per-move accumulators
+ * gradients_data[k] (estimator.jl:130).  Asynchronous.
+ * arianna_pgmc_read returns the accumulated SUMS (local shard); arianna_pgmc_reset zeroes them
+ * (update.jl:55).  arianna_pgmc_sums_device exposes the [n_learn][5] device buffer for an all-reduce. */
+ARIANNA_API int32_t arianna_pgmc_estimate(arianna_handle *h, int32_t q_batch, const int32_t *learn_ids, int32_t n_learn);
+ARIANNA_API int32_t arianna_pgmc_estimate_replay(arianna_handle *h, int32_t q_batch, const int32_t *learn_ids,
+                                     int32_t n_learn, const double *z /* [n_learn][q_batch][n_chains] */,
+                                     int32_t on_device);
+ARIANNA_API int32_t arianna_pgmc_read(arianna_handle *h, arianna_gradient_data *out, int32_t n_learn);
+ARIANNA_API int32_t arianna_pgmc_reset(arianna_handle *h);
+ARIANNA_API int32_t arianna_pgmc_sums_device(arianna_handle *h, double **dptr, int32_t *n);
+
+/* Plumbing. */
+ARIANNA_API int32_t arianna_get_stream(arianna_handle *h, void **stream);
+ARIANNA_API int32_t arianna_synchronize(arianna_handle *h);
+ARIANNA_API int32_t arianna_launch_count(arianna_handle *h, int64_t *n_launches);
+ARIANNA_API int32_t arianna_steps_done(arianna_handle *h, int64_t *steps);
+ARIANNA_API int32_t arianna_device_info(arianna_handle *h, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor,
+                            int64_t *hbm_bytes);
+
+/* FP64 pipe peak of the handle's device by a dependent-chain-free DFMA microbenchmark (flop/s); used as the
+ * FP64 roofline denominator because MEASURED_PEAKS.json holds none. */
+ARIANNA_API int32_t arianna_measure_fp64_peak(arianna_handle *h, double *flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARIANNA_CUDA_H */

@@ -1,0 +1,785 @@
+// arianna_cuda.cu -- C ABI of libarianna_cuda.so (declared in include/arianna_cuda.h).
+//
+// Host side of the engine: owns the HBM-resident ensemble, picks the kernel instantiation, keeps the draw
+// indices (steps_done / estimator samples) and hands out device pointers of the small reduction buffers for
+// the per-store NCCL all-reduce.  There is NO CPU fallback anywhere in this file: without a CUDA device
+// arianna_create fails with ARIANNA_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/arianna_cuda.h"
+#include "kernels.cuh"
+
+using namespace arianna;
+
+static_assert(ARIANNA_MAX_MOVES == kMaxMoves, "header / kernel pool size mismatch");
+static_assert(sizeof(arianna_gradient_data) == 5 * sizeof(double), "gradient record layout");
+
+struct arianna_handle {
+    arianna_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t hbm_bytes = 0;
+    int grid = 0;  // persistent grid: resident CTAs per SM x SM count
+
+    int64_t M = 0;
+    double *d_x = nullptr;
+    uint32_t *d_acc = nullptr, *d_tot = nullptr;
+    double *d_betas = nullptr;
+    uint64_t *d_rng = nullptr;
+    uint64_t *d_ki = nullptr;
+    double *d_wi = nullptr, *d_fi = nullptr;
+    double *d_partials = nullptr;
+    unsigned int *d_ticket = nullptr;
+    double *d_sums = nullptr;       // [kMaxOut]
+    double *d_gd = nullptr;         // [kMaxMoves][5]
+    unsigned long long *d_csum = nullptr;  // [2 * kMaxMoves]
+    double *d_scratch = nullptr;    // e[] staging for get_state / dfma out
+    size_t scratch_bytes = 0;
+
+    PoolParams pool{};
+    int64_t steps_done = 0;         // MC steps done per chain == draw index base == total_calls (single move)
+    int64_t pgmc_samples = 0;       // estimator samples drawn per chain
+    int64_t launches = 0;
+    bool sums_valid = false;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int32_t fail(arianna_handle *h, int32_t code, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+
+#define CU_TRY(h, expr)                                                                                       \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return fail((h), _e == cudaErrorMemoryAllocation ? ARIANNA_ERR_NOMEM : ARIANNA_ERR_CUDA,          \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                                  \
+    } while (0)
+
+#define REQUIRE(h, cond, msg)                                                                                 \
+    do {                                                                                                      \
+        if (!(cond)) return fail((h), ARIANNA_ERR_INVALID, (msg));                                            \
+    } while (0)
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+double host_lognorm(double sigma)
+{
+    // log((2π)*(σ*σ))/2 with 2π = 6.283185307179586 (particle_1d.jl:53)
+    const double s2 = sigma * sigma;
+    return std::log(6.283185307179586 * s2) / 2.0;
+}
+
+int grid_for(const arianna_handle *h, int64_t M, int ctas_per_sm)
+{
+    int64_t need = (M + kBlock - 1) / kBlock;
+    int64_t cap = (int64_t)h->sm_count * ctas_per_sm;
+    return (int)(need < cap ? need : cap);
+}
+
+size_t ensure_scratch(arianna_handle *h, size_t bytes)
+{
+    if (h->scratch_bytes >= bytes) return bytes;
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    h->d_scratch = nullptr;
+    h->scratch_bytes = 0;
+    if (cudaMalloc(&h->d_scratch, bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+    h->scratch_bytes = bytes;
+    return bytes;
+}
+
+// Ziggurat tables of the "Julia-like" randn (generated exactly as oracle/arianna_oracle.c:zig_init does, which
+// restates randmtzig's create_ziggurat_tables [EXT]); the host may override them (arianna_set_ziggurat_tables).
+void make_zig_tables(uint64_t *ki, double *wi, double *fi)
+{
+    const double R = 3.6541528853610088, AREA = 0.00492867323399, NM = 2251799813685248.0;
+    double x1 = R, xx;
+    wi[255] = x1 / NM;
+    fi[255] = std::exp(-0.5 * x1 * x1);
+    ki[0] = (uint64_t)(x1 * fi[255] / AREA * NM);
+    wi[0] = AREA / fi[255] / NM;
+    fi[0] = 1.0;
+    for (int i = 254; i > 0; --i) {
+        xx = std::sqrt(-2.0 * std::log(AREA / x1 + fi[i + 1]));
+        ki[i + 1] = (uint64_t)(xx / x1 * NM);
+        wi[i] = xx / NM;
+        fi[i] = std::exp(-0.5 * xx * xx);
+        x1 = xx;
+    }
+    ki[1] = 0;
+}
+
+template <typename F>
+int32_t dispatch_pot(int pot, F &&f)
+{
+    switch (pot) {
+    case POT_HARMONIC: return f(std::integral_constant<int, POT_HARMONIC>{});
+    case POT_QUARTIC: return f(std::integral_constant<int, POT_QUARTIC>{});
+    default: return f(std::integral_constant<int, POT_DOUBLE_WELL>{});
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t arianna_abi_version(void) { return ARIANNA_ABI_VERSION; }
+
+const char *arianna_last_error(const arianna_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int32_t arianna_create(const arianna_config *cfg, arianna_handle **out)
+{
+    if (!cfg || !out) return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: NULL argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(arianna_config))
+        return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: struct_size does not match this ABI");
+    if (cfg->n_chains < 1) return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: n_chains must be >= 1");
+    if (cfg->n_moves < 1 || cfg->n_moves > ARIANNA_MAX_MOVES)
+        return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: n_moves must be in 1..ARIANNA_MAX_MOVES");
+    if (cfg->potential < 0 || cfg->potential > ARIANNA_POT_DOUBLE_WELL)
+        return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: unknown potential");
+    if (cfg->rng_mode != ARIANNA_RNG_PHILOX && cfg->rng_mode != ARIANNA_RNG_XOSHIRO)
+        return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: unknown rng_mode");
+    if (cfg->arith_mode != ARIANNA_ARITH_EXACT && cfg->arith_mode != ARIANNA_ARITH_FAST)
+        return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: unknown arith_mode");
+    double wsum = 0.0;
+    for (int k = 0; k < cfg->n_moves; ++k) {
+        if (!(cfg->sigma[k] > 0.0) || !std::isfinite(cfg->sigma[k]))
+            return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: sigma must be finite and > 0");
+        if (!(cfg->weight[k] >= 0.0))
+            return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: weights must be >= 0");
+        wsum += cfg->weight[k];
+    }
+    // Distributions.Categorical rejects probability vectors that do not sum to one [EXT] (metropolis.jl:206)
+    if (std::fabs(wsum - 1.0) > 1e-10 * std::sqrt((double)cfg->n_moves))
+        return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: move weights must sum to 1 (Categorical)");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, ARIANNA_ERR_NO_DEVICE,
+                    "arianna_create: no CUDA device visible; libarianna_cuda has no CPU fallback");
+    }
+    int dev = cfg->device;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, ARIANNA_ERR_CUDA, "cudaGetDevice failed");
+    }
+    if (dev >= ndev) return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: device ordinal out of range");
+
+    arianna_handle *h = new (std::nothrow) arianna_handle();
+    if (!h) return fail(nullptr, ARIANNA_ERR_NOMEM, "arianna_create: host allocation failed");
+    h->cfg = *cfg;
+    if (h->cfg.n_chains_total <= 0) h->cfg.n_chains_total = cfg->n_chains;
+    h->device = dev;
+    h->M = cfg->n_chains;
+    DeviceGuard guard(dev);
+
+    auto bail = [&](int32_t code, const std::string &msg) {
+        g_create_err = msg;
+        arianna_destroy(h);
+        return code;
+    };
+#define CU_CREATE(expr)                                                                                       \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return bail(_e == cudaErrorMemoryAllocation ? ARIANNA_ERR_NOMEM : ARIANNA_ERR_CUDA,               \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                                  \
+    } while (0)
+
+    cudaDeviceProp prop{};
+    CU_CREATE(cudaGetDeviceProperties(&prop, dev));
+    h->sm_count = prop.multiProcessorCount;
+    h->cc_major = prop.major;
+    h->cc_minor = prop.minor;
+    h->hbm_bytes = prop.totalGlobalMem;
+    if (prop.major != 10)
+        return bail(ARIANNA_ERR_UNSUPPORTED, "arianna_create: this library is built for sm_100a (B200) only");
+    // persistent-style grid: 8 resident CTAs of 256 threads per SM cover the 64-warp SM limit
+    h->grid = grid_for(h, h->M, 8);
+
+    if (cfg->stream) {
+        h->stream = (cudaStream_t)cfg->stream;
+    } else {
+        CU_CREATE(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+
+    const int nm = cfg->n_moves;
+    h->pool.n_moves = nm;
+    for (int k = 0; k < kMaxMoves; ++k) {
+        h->pool.sigma[k] = k < nm ? cfg->sigma[k] : 1.0;
+        h->pool.weight[k] = k < nm ? cfg->weight[k] : 0.0;
+        h->pool.lognorm[k] = host_lognorm(h->pool.sigma[k]);
+    }
+
+    CU_CREATE(cudaMalloc(&h->d_x, sizeof(double) * h->M));
+    CU_CREATE(cudaMalloc(&h->d_acc, sizeof(uint32_t) * h->M * nm));
+    CU_CREATE(cudaMemsetAsync(h->d_acc, 0, sizeof(uint32_t) * h->M * nm, h->stream));
+    if (nm > 1) {
+        CU_CREATE(cudaMalloc(&h->d_tot, sizeof(uint32_t) * h->M * nm));
+        CU_CREATE(cudaMemsetAsync(h->d_tot, 0, sizeof(uint32_t) * h->M * nm, h->stream));
+    }
+    CU_CREATE(cudaMemsetAsync(h->d_x, 0, sizeof(double) * h->M, h->stream));
+    const int max_grid = h->sm_count * 8;
+    CU_CREATE(cudaMalloc(&h->d_partials, sizeof(double) * (size_t)max_grid * kMaxOut));
+    CU_CREATE(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
+    CU_CREATE(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
+    CU_CREATE(cudaMalloc(&h->d_sums, sizeof(double) * kMaxOut));
+    CU_CREATE(cudaMemsetAsync(h->d_sums, 0, sizeof(double) * kMaxOut, h->stream));
+    CU_CREATE(cudaMalloc(&h->d_gd, sizeof(double) * kMaxMoves * 5));
+    CU_CREATE(cudaMemsetAsync(h->d_gd, 0, sizeof(double) * kMaxMoves * 5, h->stream));
+    CU_CREATE(cudaMalloc(&h->d_csum, sizeof(unsigned long long) * 2 * kMaxMoves));
+
+    if (cfg->rng_mode == ARIANNA_RNG_XOSHIRO) {
+        CU_CREATE(cudaMalloc(&h->d_rng, sizeof(uint64_t) * 4 * h->M));
+        CU_CREATE(cudaMemsetAsync(h->d_rng, 0, sizeof(uint64_t) * 4 * h->M, h->stream));
+        CU_CREATE(cudaMalloc(&h->d_ki, sizeof(uint64_t) * 256));
+        CU_CREATE(cudaMalloc(&h->d_wi, sizeof(double) * 256));
+        CU_CREATE(cudaMalloc(&h->d_fi, sizeof(double) * 256));
+        uint64_t ki[256];
+        double wi[256], fi[256];
+        make_zig_tables(ki, wi, fi);
+        CU_CREATE(cudaMemcpyAsync(h->d_ki, ki, sizeof ki, cudaMemcpyHostToDevice, h->stream));
+        CU_CREATE(cudaMemcpyAsync(h->d_wi, wi, sizeof wi, cudaMemcpyHostToDevice, h->stream));
+        CU_CREATE(cudaMemcpyAsync(h->d_fi, fi, sizeof fi, cudaMemcpyHostToDevice, h->stream));
+        CU_CREATE(cudaStreamSynchronize(h->stream));  // stack tables must outlive the copies
+    }
+    // opt in to large dynamic shared memory for the multi-move kernels (2 * n_moves * 256 * 4 B <= 32 KB: default ok)
+    CU_CREATE(cudaStreamSynchronize(h->stream));
+#undef CU_CREATE
+    *out = h;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_destroy(arianna_handle *h)
+{
+    if (!h) return ARIANNA_OK;
+    DeviceGuard guard(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_x); cudaFree(h->d_acc); cudaFree(h->d_tot); cudaFree(h->d_betas); cudaFree(h->d_rng);
+    cudaFree(h->d_ki); cudaFree(h->d_wi); cudaFree(h->d_fi); cudaFree(h->d_partials); cudaFree(h->d_ticket);
+    cudaFree(h->d_sums); cudaFree(h->d_gd); cudaFree(h->d_csum); cudaFree(h->d_scratch);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_set_state(arianna_handle *h, const double *x)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, x != nullptr, "arianna_set_state: x is NULL");
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->M, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->sums_valid = false;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_init_synthetic(arianna_handle *h, int64_t seed)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    init_kernel<<<h->grid, kBlock, 0, h->stream>>>(h->d_x, h->M, (uint64_t)(seed + h->cfg.chain_offset));
+    CU_TRY(h, cudaGetLastError());
+    ++h->launches;
+    h->sums_valid = false;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_get_state(arianna_handle *h, double *x, double *e)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (x) CU_TRY(h, cudaMemcpyAsync(x, h->d_x, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->stream));
+    if (e) {
+        if (!ensure_scratch(h, sizeof(double) * h->M))
+            return fail(h, ARIANNA_ERR_NOMEM, "arianna_get_state: scratch allocation failed");
+        energy_kernel<<<h->grid, kBlock, 0, h->stream>>>(h->d_x, h->d_scratch, h->M, h->cfg.potential);
+        CU_TRY(h, cudaGetLastError());
+        ++h->launches;
+        CU_TRY(h, cudaMemcpyAsync(e, h->d_scratch, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_get_state_async(arianna_handle *h, double *x_pinned)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, x_pinned != nullptr, "arianna_get_state_async: destination is NULL");
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaMemcpyAsync(x_pinned, h->d_x, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_set_beta(arianna_handle *h, double beta)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    h->cfg.beta = beta;
+    if (h->d_betas) { cudaStreamSynchronize(h->stream); cudaFree(h->d_betas); h->d_betas = nullptr; }
+    return ARIANNA_OK;
+}
+
+int32_t arianna_set_betas(arianna_handle *h, const double *betas)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, betas != nullptr, "arianna_set_betas: betas is NULL");
+    DeviceGuard guard(h->device);
+    if (!h->d_betas) CU_TRY(h, cudaMalloc(&h->d_betas, sizeof(double) * h->M));
+    CU_TRY(h, cudaMemcpyAsync(h->d_betas, betas, sizeof(double) * h->M, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_set_params(arianna_handle *h, int32_t move_id, const double *theta, int32_t P,
+                           const double *log_norm)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, move_id >= 0 && move_id < h->pool.n_moves, "arianna_set_params: move_id out of range");
+    REQUIRE(h, theta != nullptr && P == 1, "arianna_set_params: StandardGaussian has exactly one parameter (σ)");
+    REQUIRE(h, std::isfinite(theta[0]) && theta[0] > 0.0, "arianna_set_params: σ must be finite and > 0 (Normal(0, σ))");
+    // kernel parameters are passed by value at launch: updating the host copy is all that is needed
+    h->pool.sigma[move_id] = theta[0];
+    h->pool.lognorm[move_id] = log_norm ? *log_norm : host_lognorm(theta[0]);
+    return ARIANNA_OK;
+}
+
+int32_t arianna_get_params(arianna_handle *h, int32_t move_id, double *theta, int32_t P)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, move_id >= 0 && move_id < h->pool.n_moves, "arianna_get_params: move_id out of range");
+    REQUIRE(h, theta != nullptr && P == 1, "arianna_get_params: StandardGaussian has exactly one parameter (σ)");
+    theta[0] = h->pool.sigma[move_id];
+    return ARIANNA_OK;
+}
+
+static int32_t launch_callback_reduce(arianna_handle *h)
+{
+    ReduceParams rp{h->d_x, h->d_acc, h->d_tot, h->M, h->steps_done, h->pool.n_moves, h->cfg.potential,
+                    h->d_partials, h->d_ticket, h->d_sums};
+    callback_reduce_kernel<<<h->grid, kBlock, 0, h->stream>>>(rp);
+    CU_TRY(h, cudaGetLastError());
+    ++h->launches;
+    h->sums_valid = true;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, K >= 0, "arianna_sweep: K must be >= 0");
+    REQUIRE(h, h->steps_done + K <= 0xFFFFFFFFll, "arianna_sweep: per-chain counters are 32-bit (2^32-1 steps max)");
+    DeviceGuard guard(h->device);
+    const bool multi = h->pool.n_moves > 1;
+    const bool want_reduce = (flags & ARIANNA_SWEEP_REDUCE) != 0;
+    if (K == 0) return want_reduce ? launch_callback_reduce(h) : ARIANNA_OK;
+    const size_t smem = multi ? sizeof(uint32_t) * 2 * h->pool.n_moves * kBlock : 0;
+    const bool exact = h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
+
+    if (h->cfg.rng_mode == ARIANNA_RNG_PHILOX) {
+        SweepParams sp{};
+        sp.x = h->d_x; sp.acc = h->d_acc; sp.tot = h->d_tot; sp.betas = h->d_betas; sp.beta = h->cfg.beta;
+        sp.M = h->M; sp.K = K; sp.t0 = h->steps_done;
+        sp.sid0 = (uint64_t)(h->cfg.seed + h->cfg.chain_offset);
+        sp.reduce = (want_reduce && !multi) ? 1 : 0;
+        sp.partials = h->d_partials; sp.ticket = h->d_ticket; sp.sums = h->d_sums;
+        sp.pool = h->pool;
+        dispatch_pot(h->cfg.potential, [&](auto pot) {
+            constexpr int POT = decltype(pot)::value;
+            if (exact) {
+                if (multi) sweep_philox_kernel<POT, ARITH_EXACT, true><<<h->grid, kBlock, smem, h->stream>>>(sp);
+                else sweep_philox_kernel<POT, ARITH_EXACT, false><<<h->grid, kBlock, 0, h->stream>>>(sp);
+            } else {
+                if (multi) sweep_philox_kernel<POT, ARITH_FAST, true><<<h->grid, kBlock, smem, h->stream>>>(sp);
+                else sweep_philox_kernel<POT, ARITH_FAST, false><<<h->grid, kBlock, 0, h->stream>>>(sp);
+            }
+            return 0;
+        });
+    } else {
+        XoshiroParams xp{};
+        xp.x = h->d_x; xp.acc = h->d_acc; xp.tot = h->d_tot; xp.betas = h->d_betas; xp.beta = h->cfg.beta;
+        xp.M = h->M; xp.K = K; xp.rng = h->d_rng; xp.ki = h->d_ki; xp.wi = h->d_wi; xp.fi = h->d_fi;
+        xp.pool = h->pool;
+        dispatch_pot(h->cfg.potential, [&](auto pot) {
+            constexpr int POT = decltype(pot)::value;
+            if (exact) {
+                if (multi) sweep_xoshiro_kernel<POT, ARITH_EXACT, true><<<h->grid, kBlock, smem, h->stream>>>(xp);
+                else sweep_xoshiro_kernel<POT, ARITH_EXACT, false><<<h->grid, kBlock, 0, h->stream>>>(xp);
+            } else {
+                if (multi) sweep_xoshiro_kernel<POT, ARITH_FAST, true><<<h->grid, kBlock, smem, h->stream>>>(xp);
+                else sweep_xoshiro_kernel<POT, ARITH_FAST, false><<<h->grid, kBlock, 0, h->stream>>>(xp);
+            }
+            return 0;
+        });
+    }
+    CU_TRY(h, cudaGetLastError());
+    ++h->launches;
+    h->steps_done += K;
+    h->sums_valid = false;
+    if (want_reduce) {
+        if (!multi && h->cfg.rng_mode == ARIANNA_RNG_PHILOX) h->sums_valid = true;  // fused at the sweep's tail
+        else return launch_callback_reduce(h);
+    }
+    return ARIANNA_OK;
+}
+
+int32_t arianna_sweep_replay(arianna_handle *h, int64_t K, const double *u_cat, const double *z,
+                             const double *u_acc, uint8_t *decisions_out, int32_t on_device)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, K >= 0, "arianna_sweep_replay: K must be >= 0");
+    REQUIRE(h, z != nullptr && u_acc != nullptr, "arianna_sweep_replay: z and u_acc are required");
+    const bool multi = h->pool.n_moves > 1;
+    REQUIRE(h, !multi || u_cat != nullptr, "arianna_sweep_replay: u_cat is required for multi-move pools");
+    REQUIRE(h, h->steps_done + K <= 0xFFFFFFFFll, "arianna_sweep_replay: per-chain counters are 32-bit");
+    if (K == 0) return ARIANNA_OK;
+    DeviceGuard guard(h->device);
+    const size_t smem = multi ? sizeof(uint32_t) * 2 * h->pool.n_moves * kBlock : 0;
+
+    auto launch = [&](int64_t k, const double *duc, const double *dz, const double *dua, uint8_t *ddec) -> int32_t {
+        ReplayParams rp{};
+        rp.x = h->d_x; rp.acc = h->d_acc; rp.tot = h->d_tot; rp.betas = h->d_betas; rp.beta = h->cfg.beta;
+        rp.M = h->M; rp.K = k; rp.u_cat = multi ? duc : nullptr; rp.z = dz; rp.u_acc = dua; rp.decisions = ddec;
+        rp.pool = h->pool;
+        dispatch_pot(h->cfg.potential, [&](auto pot) {
+            constexpr int POT = decltype(pot)::value;
+            if (multi) sweep_replay_kernel<POT, true><<<h->grid, kBlock, smem, h->stream>>>(rp);
+            else sweep_replay_kernel<POT, false><<<h->grid, kBlock, 0, h->stream>>>(rp);
+            return 0;
+        });
+        CU_TRY(h, cudaGetLastError());
+        ++h->launches;
+        return ARIANNA_OK;
+    };
+
+    if (on_device) {
+        int32_t rc = launch(K, u_cat, z, u_acc, decisions_out);
+        if (rc) return rc;
+    } else {
+        // stage host draws through a bounded device buffer, chunked over steps (<= 1 GiB per array)
+        const size_t per_step = sizeof(double) * (size_t)h->M;
+        int64_t kc = (int64_t)((size_t(1) << 30) / per_step);
+        if (kc < 1) kc = 1;
+        if (kc > K) kc = K;
+        const size_t narr = multi ? 3 : 2;
+        const size_t need = narr * per_step * kc + (decisions_out ? (size_t)h->M * kc : 0);
+        if (!ensure_scratch(h, need)) return fail(h, ARIANNA_ERR_NOMEM, "arianna_sweep_replay: staging allocation failed");
+        double *dz = h->d_scratch;
+        double *dua = dz + (size_t)h->M * kc;
+        double *duc = multi ? dua + (size_t)h->M * kc : nullptr;
+        uint8_t *ddec = decisions_out ? reinterpret_cast<uint8_t *>(h->d_scratch + narr * (size_t)h->M * kc) : nullptr;
+        for (int64_t s0 = 0; s0 < K; s0 += kc) {
+            const int64_t k = (K - s0 < kc) ? K - s0 : kc;
+            const size_t off = (size_t)s0 * h->M;
+            CU_TRY(h, cudaMemcpyAsync(dz, z + off, per_step * k, cudaMemcpyHostToDevice, h->stream));
+            CU_TRY(h, cudaMemcpyAsync(dua, u_acc + off, per_step * k, cudaMemcpyHostToDevice, h->stream));
+            if (multi) CU_TRY(h, cudaMemcpyAsync(duc, u_cat + off, per_step * k, cudaMemcpyHostToDevice, h->stream));
+            int32_t rc = launch(k, duc, dz, dua, ddec);
+            if (rc) return rc;
+            if (ddec)
+                CU_TRY(h, cudaMemcpyAsync(decisions_out + off, ddec, (size_t)h->M * k, cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+        }
+    }
+    h->steps_done += K;
+    h->sums_valid = false;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_set_rng_state(arianna_handle *h, const uint64_t *states)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, states != nullptr, "arianna_set_rng_state: states is NULL");
+    if (h->cfg.rng_mode != ARIANNA_RNG_XOSHIRO)
+        return fail(h, ARIANNA_ERR_UNSUPPORTED, "arianna_set_rng_state: handle was not created with ARIANNA_RNG_XOSHIRO");
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaMemcpyAsync(h->d_rng, states, sizeof(uint64_t) * 4 * h->M, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_get_rng_state(arianna_handle *h, uint64_t *states)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, states != nullptr, "arianna_get_rng_state: states is NULL");
+    if (h->cfg.rng_mode != ARIANNA_RNG_XOSHIRO)
+        return fail(h, ARIANNA_ERR_UNSUPPORTED, "arianna_get_rng_state: handle was not created with ARIANNA_RNG_XOSHIRO");
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaMemcpyAsync(states, h->d_rng, sizeof(uint64_t) * 4 * h->M, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_set_ziggurat_tables(arianna_handle *h, const uint64_t *ki, const double *wi, const double *fi)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, ki && wi && fi, "arianna_set_ziggurat_tables: NULL table");
+    if (h->cfg.rng_mode != ARIANNA_RNG_XOSHIRO)
+        return fail(h, ARIANNA_ERR_UNSUPPORTED, "arianna_set_ziggurat_tables: handle was not created with ARIANNA_RNG_XOSHIRO");
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaMemcpyAsync(h->d_ki, ki, sizeof(uint64_t) * 256, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_wi, wi, sizeof(double) * 256, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_fi, fi, sizeof(double) * 256, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_callback_sums_device(arianna_handle *h, double **dptr, int32_t *n)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, dptr && n, "arianna_callback_sums_device: NULL output");
+    DeviceGuard guard(h->device);
+    if (!h->sums_valid) {
+        int32_t rc = launch_callback_reduce(h);
+        if (rc) return rc;
+    }
+    *dptr = h->d_sums;
+    *n = 2 + h->pool.n_moves;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_callback_sums(arianna_handle *h, double *sums)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, sums != nullptr, "arianna_callback_sums: sums is NULL");
+    double *d = nullptr;
+    int32_t n = 0;
+    int32_t rc = arianna_callback_sums_device(h, &d, &n);
+    if (rc) return rc;
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaMemcpyAsync(sums, d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_callbacks(arianna_handle *h, double *mean_energy, double *acc_per_move)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    double sums[kMaxOut];
+    int32_t rc = arianna_callback_sums(h, sums);
+    if (rc) return rc;
+    const int nm = h->pool.n_moves;
+    const double cnt = sums[1 + nm];
+    if (mean_energy) *mean_energy = sums[0] / cnt;
+    if (acc_per_move)
+        for (int k = 0; k < nm; ++k) acc_per_move[k] = sums[1 + k] / cnt;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_get_counters(arianna_handle *h, int64_t *accepted, int64_t *total)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    const int nm = h->pool.n_moves;
+    CU_TRY(h, cudaMemsetAsync(h->d_csum, 0, sizeof(unsigned long long) * 2 * kMaxMoves, h->stream));
+    counter_sum_kernel<<<h->grid, kBlock, 0, h->stream>>>(h->d_acc, h->d_tot, h->M, nm, h->steps_done, h->d_csum);
+    CU_TRY(h, cudaGetLastError());
+    ++h->launches;
+    unsigned long long out[2 * kMaxMoves];
+    CU_TRY(h, cudaMemcpyAsync(out, h->d_csum, sizeof(unsigned long long) * 2 * nm, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < nm; ++k) {
+        if (accepted) accepted[k] = (int64_t)out[k];
+        if (total) total[k] = (int64_t)out[nm + k];
+    }
+    return ARIANNA_OK;
+}
+
+int32_t arianna_get_chain_counters(arianna_handle *h, uint32_t *accepted, uint32_t *total)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    const size_t n = (size_t)h->M * h->pool.n_moves;
+    if (accepted) CU_TRY(h, cudaMemcpyAsync(accepted, h->d_acc, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (total && h->d_tot)
+        CU_TRY(h, cudaMemcpyAsync(total, h->d_tot, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (total && !h->d_tot)
+        for (size_t i = 0; i < n; ++i) total[i] = (uint32_t)h->steps_done;
+    return ARIANNA_OK;
+}
+
+static int32_t pgmc_impl(arianna_handle *h, int32_t q_batch, const int32_t *learn_ids, int32_t n_learn,
+                         const double *z, int32_t on_device, bool replay)
+{
+    REQUIRE(h, q_batch >= 1, "arianna_pgmc_estimate: q_batch must be >= 1");
+    REQUIRE(h, n_learn >= 0 && n_learn <= kMaxMoves && (n_learn == 0 || learn_ids != nullptr),
+            "arianna_pgmc_estimate: bad learn_ids");
+    for (int l = 0; l < n_learn; ++l)
+        REQUIRE(h, learn_ids[l] >= 0 && learn_ids[l] < h->pool.n_moves, "arianna_pgmc_estimate: learn id out of range");
+    if (n_learn == 0) return ARIANNA_OK;
+    DeviceGuard guard(h->device);
+    const bool exact = replay || h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
+    const double *dz = z;
+    if (replay && !on_device) {
+        const size_t bytes = sizeof(double) * (size_t)n_learn * q_batch * h->M;
+        if (!ensure_scratch(h, bytes)) return fail(h, ARIANNA_ERR_NOMEM, "arianna_pgmc_estimate_replay: staging allocation failed");
+        CU_TRY(h, cudaMemcpyAsync(h->d_scratch, z, bytes, cudaMemcpyHostToDevice, h->stream));
+        dz = h->d_scratch;
+    }
+    for (int l = 0; l < n_learn; ++l) {
+        const int k = learn_ids[l];
+        PgmcParams pp{};
+        pp.x = h->d_x; pp.betas = h->d_betas; pp.beta = h->cfg.beta; pp.M = h->M; pp.q_batch = q_batch;
+        pp.q0 = h->pgmc_samples + (int64_t)l * q_batch;
+        pp.sid0 = (uint64_t)(h->cfg.seed + h->cfg.chain_offset);
+        pp.sigma = h->pool.sigma[k]; pp.lognorm = h->pool.lognorm[k];
+        pp.z = replay ? dz + (size_t)l * q_batch * h->M : nullptr;
+        pp.partials = h->d_partials; pp.ticket = h->d_ticket; pp.gd = h->d_gd + 5 * l;
+        dispatch_pot(h->cfg.potential, [&](auto pot) {
+            constexpr int POT = decltype(pot)::value;
+            if (replay) pgmc_kernel<POT, ARITH_EXACT, true><<<h->grid, kBlock, 0, h->stream>>>(pp);
+            else if (exact) pgmc_kernel<POT, ARITH_EXACT, false><<<h->grid, kBlock, 0, h->stream>>>(pp);
+            else pgmc_kernel<POT, ARITH_FAST, false><<<h->grid, kBlock, 0, h->stream>>>(pp);
+            return 0;
+        });
+        CU_TRY(h, cudaGetLastError());
+        ++h->launches;
+    }
+    if (!replay) h->pgmc_samples += (int64_t)n_learn * q_batch;
+    if (replay && !on_device) CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (exact) h->sums_valid = false;  // chain state drifted by the perform/undo rounding
+    return ARIANNA_OK;
+}
+
+int32_t arianna_pgmc_estimate(arianna_handle *h, int32_t q_batch, const int32_t *learn_ids, int32_t n_learn)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    if (h->cfg.rng_mode != ARIANNA_RNG_PHILOX)
+        return fail(h, ARIANNA_ERR_UNSUPPORTED, "arianna_pgmc_estimate: native estimator draws need ARIANNA_RNG_PHILOX");
+    return pgmc_impl(h, q_batch, learn_ids, n_learn, nullptr, 0, false);
+}
+
+int32_t arianna_pgmc_estimate_replay(arianna_handle *h, int32_t q_batch, const int32_t *learn_ids, int32_t n_learn,
+                                     const double *z, int32_t on_device)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, z != nullptr, "arianna_pgmc_estimate_replay: z is NULL");
+    return pgmc_impl(h, q_batch, learn_ids, n_learn, z, on_device, true);
+}
+
+int32_t arianna_pgmc_read(arianna_handle *h, arianna_gradient_data *out, int32_t n_learn)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, out != nullptr && n_learn >= 0 && n_learn <= kMaxMoves, "arianna_pgmc_read: bad arguments");
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaMemcpyAsync(out, h->d_gd, sizeof(double) * 5 * n_learn, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_pgmc_reset(arianna_handle *h)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaMemsetAsync(h->d_gd, 0, sizeof(double) * kMaxMoves * 5, h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_pgmc_sums_device(arianna_handle *h, double **dptr, int32_t *n)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, dptr && n, "arianna_pgmc_sums_device: NULL output");
+    *dptr = h->d_gd;
+    *n = kMaxMoves * 5;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_get_stream(arianna_handle *h, void **stream)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, stream != nullptr, "arianna_get_stream: NULL output");
+    *stream = (void *)h->stream;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_synchronize(arianna_handle *h)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_launch_count(arianna_handle *h, int64_t *n_launches)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, n_launches != nullptr, "arianna_launch_count: NULL output");
+    *n_launches = h->launches;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_steps_done(arianna_handle *h, int64_t *steps)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, steps != nullptr, "arianna_steps_done: NULL output");
+    *steps = h->steps_done;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_device_info(arianna_handle *h, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor,
+                            int64_t *hbm_bytes)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    if (sm_count) *sm_count = h->sm_count;
+    if (cc_major) *cc_major = h->cc_major;
+    if (cc_minor) *cc_minor = h->cc_minor;
+    if (hbm_bytes) *hbm_bytes = (int64_t)h->hbm_bytes;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_measure_fp64_peak(arianna_handle *h, double *flops_per_s)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, flops_per_s != nullptr, "arianna_measure_fp64_peak: NULL output");
+    DeviceGuard guard(h->device);
+    const int grid = h->sm_count * 8;
+    const int iters = 2048;
+    if (!ensure_scratch(h, sizeof(double) * (size_t)grid * kBlock))
+        return fail(h, ARIANNA_ERR_NOMEM, "arianna_measure_fp64_peak: scratch allocation failed");
+    cudaEvent_t e0, e1;
+    CU_TRY(h, cudaEventCreate(&e0));
+    CU_TRY(h, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU_TRY(h, cudaEventRecord(e0, h->stream));
+        dfma_peak_kernel<<<grid, kBlock, 0, h->stream>>>(h->d_scratch, iters, 0.999999, 1e-9);
+        CU_TRY(h, cudaEventRecord(e1, h->stream));
+        CU_TRY(h, cudaEventSynchronize(e1));
+        ++h->launches;
+        float ms = 0.f;
+        CU_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * (double)iters * (double)grid * kBlock;  // 64 DFMA per iteration
+        const double rate = flops / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CU_TRY(h, cudaGetLastError());
+    *flops_per_s = best;
+    return ARIANNA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,682 @@
+// kernels.cuh -- the fused Metropolis sweep, callback-reduction and PGMC kernels (sm_100a).
+//
+// Layout in HBM (struct-of-arrays, one chain per thread, coalesced 8-byte lanes):
+//   x[M]                 f64   chain positions (Particle.x, particle_1d.jl:10); e = potential(x) is recomputed
+//   acc[n_moves][M]      u32   Move.accepted_calls per chain and move (metropolis.jl:146)
+//   tot[n_moves][M]      u32   Move.total_calls -- only materialised for multi-move pools; a single-move pool has
+//                              tot == steps_done for every chain
+//   betas[M]             f64   optional per-chain β
+//   rng[M][4]            u64   only in XOSHIRO mode
+// Each thread keeps its chain's (x, e, counters) in registers across the K fused steps of one launch and writes
+// back once: algorithmic HBM traffic is 24/K bytes per chain-step (x r+w 16 B, acc r+w 8 B).
+//
+// Reference mapping: mc_step! (src/metropolis.jl:176-190), mc_sweep! (:203-212), the particle_1d methods
+// (example/particle_1d/particle_1d.jl:20-59), callback_energy (:68-70), callback_acceptance
+// (src/metropolis.jl:319-321), pgmc_estimate (src/PolicyGuided/gradients.jl:93-109).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "rng.cuh"
+
+namespace arianna {
+
+constexpr int kBlock = 256;
+constexpr int kMaxMoves = 16;
+constexpr int kWarpsPerBlock = kBlock / 32;
+
+enum { POT_HARMONIC = 0, POT_QUARTIC = 1, POT_DOUBLE_WELL = 2 };
+enum { ARITH_EXACT = 0, ARITH_FAST = 1 };
+
+struct PoolParams {
+    int n_moves;
+    double sigma[kMaxMoves];
+    double weight[kMaxMoves];
+    double lognorm[kMaxMoves];  // log((2π)·(σ·σ))/2, host-computed (particle_1d.jl:53)
+};
+
+struct SweepParams {
+    double *x;
+    uint32_t *acc;
+    uint32_t *tot;          // nullptr for single-move pools
+    const double *betas;    // nullptr -> beta
+    double beta;
+    int64_t M;
+    int64_t K;
+    int64_t t0;             // MC steps already done by every chain (draw index base)
+    uint64_t sid0;          // seed + chain_offset: stream id of local chain 0
+    int reduce;             // fuse the callback sums into the tail of the sweep (single-move kernels)
+    double *partials;       // [gridDim.x][kMaxOut]
+    unsigned int *ticket;
+    double *sums;           // [2 + n_moves]
+    PoolParams pool;
+};
+
+constexpr int kMaxOut = 2 + kMaxMoves;
+
+// ---------------------------------------------------------------------------------------------------------
+// potential(x)
+// ---------------------------------------------------------------------------------------------------------
+template <int POT, int ARITH>
+__device__ __forceinline__ double potential(double x)
+{
+    if constexpr (ARITH == ARITH_EXACT) {
+        if constexpr (POT == POT_HARMONIC) {
+            return __dmul_rn(x, x);
+        } else if constexpr (POT == POT_QUARTIC) {
+            double x2 = __dmul_rn(x, x);
+            return __dmul_rn(x2, x2);
+        } else {
+            double w = __dsub_rn(__dmul_rn(x, x), 1.0);
+            return __dmul_rn(w, w);
+        }
+    } else {
+        if constexpr (POT == POT_HARMONIC) {
+            return x * x;
+        } else if constexpr (POT == POT_QUARTIC) {
+            double x2 = x * x;
+            return x2 * x2;
+        } else {
+            double w = fma(x, x, -1.0);
+            return w * w;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One Metropolis step.  Returns mc_step!'s return value.
+// EXACT: every statement is one round-to-nearest binary64 operation in the reference's order; the __d*_rn
+// intrinsics are never contracted into FMAs.
+// ---------------------------------------------------------------------------------------------------------
+template <int POT>
+__device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, double sigma, double lognorm,
+                                             double z, double u_acc)
+{
+    double delta = __dadd_rn(0.0, __dmul_rn(sigma, z));                       // particle_1d.jl:57
+    double s2 = __dmul_rn(sigma, sigma);
+    double t1 = __ddiv_rn(-__dmul_rn(delta, delta), __dmul_rn(2.0, s2));      // :53
+    double lqf = __dsub_rn(t1, lognorm);                                      // metropolis.jl:178
+    double e1 = e;                                                            // particle_1d.jl:31
+    x = __dadd_rn(x, delta);                                                  // :32
+    e = potential<POT, ARITH_EXACT>(x);                                       // :33
+    double dlogp = __dsub_rn(__dmul_rn(-e, beta), __dmul_rn(-e1, beta));      // metropolis.jl:98
+    delta = -delta;                                                           // particle_1d.jl:38
+    double lqb = lqf;  // log_proposal_density of -δ: only (-δ)·(-δ) == δ·δ enters -> bitwise equal (metropolis.jl:182)
+    double arg = __dsub_rn(__dadd_rn(dlogp, lqb), lqf);                       // :183, NOT simplified to dlogp
+    double ex = exp(arg);
+    double alpha = (ex > 1.0) ? 1.0 : ex;                                     // min(one(T), ·), NaN propagates
+    if (alpha > u_acc) return 1;                                              // :184 strict >
+    x = __dadd_rn(x, delta);                                                  // :187 re-applied negated move:
+    e = potential<POT, ARITH_EXACT>(x);                                       //      x = fl(fl(x+δ)-δ), not a restore
+    return 0;
+}
+
+// FAST: symmetric proposal => log q terms cancel; α > u  <=>  exp(β(e - e')) > u  because u < 1; reject restores x.
+template <int POT>
+__device__ __forceinline__ int mc_step_fast(double &x, double &e, double beta, double sigma, double z, double u_acc)
+{
+    double xn = fma(sigma, z, x);
+    double en = potential<POT, ARITH_FAST>(xn);
+    double ex = exp(beta * (e - en));
+    bool a = ex > u_acc;
+    x = a ? xn : x;
+    e = a ? en : e;
+    return a ? 1 : 0;
+}
+
+template <int POT, int ARITH>
+__device__ __forceinline__ int mc_step(double &x, double &e, double beta, double sigma, double lognorm, double z,
+                                       double u_acc)
+{
+    if constexpr (ARITH == ARITH_EXACT)
+        return mc_step_exact<POT>(x, e, beta, sigma, lognorm, z, u_acc);
+    else
+        return mc_step_fast<POT>(x, e, beta, sigma, z, u_acc);
+}
+
+// Distributions.Categorical inverse-CDF scan [EXT] (metropolis.jl:206); weights in shared memory.
+__device__ __forceinline__ int categorical(int n, const double *w, double u)
+{
+    int k = 0;
+    double cp = w[0];
+    while (cp <= u && k < n - 1) {
+        ++k;
+        cp = __dadd_rn(cp, w[k]);
+    }
+    return k;
+}
+
+// Box-Muller pair: z0 = r cos(2π u2), z1 = r sin(2π u2), r = sqrt(-2 log u1).
+__device__ __forceinline__ void box_muller(uint32_t u1_lo, uint32_t u1_hi, uint32_t u2_lo, uint32_t u2_hi,
+                                           double &z0, double &z1)
+{
+    double u1 = u53_open0(u1_lo, u1_hi);
+    double u2 = u53(u2_lo, u2_hi);
+    double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Block reduction of NOUT doubles per thread -> partials[blockIdx.x][*]; the last block to finish folds the
+// partials in a fixed order (deterministic for a given grid) into out[] (+= when accumulate).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NOUT_MAX>
+__device__ __forceinline__ void block_reduce_and_finish(const double *vals, int nout, double *partials,
+                                                        unsigned int *ticket, double *out, bool accumulate)
+{
+    __shared__ double s_w[kWarpsPerBlock][NOUT_MAX];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NOUT_MAX; ++i) {
+        if (i < nout) {
+            double v = warp_sum(vals[i]);
+            if (lane == 0) s_w[warp][i] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < nout) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; ++w) v += s_w[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * NOUT_MAX + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // fold: thread t sums blocks t, t+kBlock, ... for each output; then a block tree over threads
+    for (int i = 0; i < nout; ++i) {
+        double v = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += kBlock)
+            v += __ldcg(&partials[(size_t)b * NOUT_MAX + i]);
+        v = warp_sum(v);
+        __syncthreads();
+        if (lane == 0) s_w[warp][0] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarpsPerBlock; ++w) t += s_w[w][0];
+            out[i] = accumulate ? out[i] + t : t;
+        }
+    }
+    if (threadIdx.x == 0) *ticket = 0u;  // re-arm for the next launch on this stream
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: fused sweep, native Philox.  MULTI = pool with more than one move (categorical pick, per-move counters in
+// shared memory so that the dynamically indexed counters never spill to local memory).
+// ---------------------------------------------------------------------------------------------------------
+template <int POT, int ARITH, bool MULTI>
+__global__ void __launch_bounds__(kBlock) sweep_philox_kernel(const SweepParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    // MULTI: [n_moves][kBlock] acc, [n_moves][kBlock] tot (u32), then sigma/weight/lognorm tables
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *s_tot = s_acc + (MULTI ? p.pool.n_moves * kBlock : 0);
+    __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves];
+    if (threadIdx.x < kMaxMoves) {
+        s_sigma[threadIdx.x] = p.pool.sigma[threadIdx.x];
+        s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
+        s_lognorm[threadIdx.x] = p.pool.lognorm[threadIdx.x];
+    }
+    __syncthreads();
+
+    const int nm = p.pool.n_moves;
+    const int64_t tend = p.t0 + p.K;
+    double sum_e = 0.0, sum_r = 0.0, cnt = 0.0;
+    const double sigma0 = p.pool.sigma[0], lognorm0 = p.pool.lognorm[0];
+
+    for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
+        double x = p.x[c];
+        double e = potential<POT, ARITH>(x);
+        const double beta = p.betas ? p.betas[c] : p.beta;
+        const uint64_t sid = p.sid0 + (uint64_t)c;
+        uint32_t acc = 0;
+        if constexpr (MULTI) {
+            for (int k = 0; k < nm; ++k) {
+                s_acc[k * kBlock + threadIdx.x] = p.acc[(size_t)k * p.M + c];
+                s_tot[k * kBlock + threadIdx.x] = p.tot[(size_t)k * p.M + c];
+            }
+        } else {
+            acc = p.acc[c];
+        }
+
+        for (int64_t pr = p.t0 >> 1; 2 * pr < tend; ++pr) {
+            const U64Pair b0 = philox_block<kTagMetropolis>(sid, 4 * (uint64_t)pr + 0);
+            const U64Pair b1 = philox_block<kTagMetropolis>(sid, 4 * (uint64_t)pr + 1);
+            double z0, z1;
+            box_muller(b0.b_lo, b0.b_hi, b1.b_lo, b1.b_hi, z0, z1);
+            U64Pair b2{};
+            if constexpr (MULTI) b2 = philox_block<kTagMetropolis>(sid, 4 * (uint64_t)pr + 2);
+            if (2 * pr >= p.t0) {  // uniform branch: first pair of a launch that starts on an odd step
+                const double ua = u53(b0.a_lo, b0.a_hi);
+                if constexpr (MULTI) {
+                    const int k = categorical(nm, s_weight, u53(b2.a_lo, b2.a_hi));
+                    int d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], z0, ua);
+                    s_acc[k * kBlock + threadIdx.x] += d;
+                    s_tot[k * kBlock + threadIdx.x] += 1;
+                } else {
+                    acc += mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, z0, ua);
+                }
+            }
+            if (2 * pr + 1 < tend) {  // uniform branch: last pair of a launch that ends on an even step
+                const double ua = u53(b1.a_lo, b1.a_hi);
+                if constexpr (MULTI) {
+                    const int k = categorical(nm, s_weight, u53(b2.b_lo, b2.b_hi));
+                    int d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], z1, ua);
+                    s_acc[k * kBlock + threadIdx.x] += d;
+                    s_tot[k * kBlock + threadIdx.x] += 1;
+                } else {
+                    acc += mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, z1, ua);
+                }
+            }
+        }
+
+        p.x[c] = x;
+        if constexpr (MULTI) {
+            for (int k = 0; k < nm; ++k) {
+                p.acc[(size_t)k * p.M + c] = s_acc[k * kBlock + threadIdx.x];
+                p.tot[(size_t)k * p.M + c] = s_tot[k * kBlock + threadIdx.x];
+            }
+        } else {
+            p.acc[c] = acc;
+            if (p.reduce) {
+                sum_e += e;                                   // callback_energy: Σ system.e
+                sum_r += (double)acc / (double)tend;           // callback_acceptance: Σ acc/tot (0/0 = NaN at t = 0)
+                cnt += 1.0;
+            }
+        }
+    }
+
+    if constexpr (!MULTI) {
+        if (p.reduce) {
+            double vals[3] = {sum_e, sum_r, cnt};
+            block_reduce_and_finish<3>(vals, 3, p.partials, p.ticket, p.sums, false);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K6: replay sweep -- consumes caller-supplied draws, always EXACT arithmetic.  HBM-bound: 16 B (24 B with
+// u_cat) of draws per chain-step.  Draws are streamed with evict-first loads, 4 steps prefetched ahead.
+// ---------------------------------------------------------------------------------------------------------
+struct ReplayParams {
+    double *x;
+    uint32_t *acc;
+    uint32_t *tot;
+    const double *betas;
+    double beta;
+    int64_t M;
+    int64_t K;
+    const double *u_cat;  // [K][M] or nullptr
+    const double *z;      // [K][M]
+    const double *u_acc;  // [K][M]
+    uint8_t *decisions;   // [K][M] or nullptr
+    PoolParams pool;
+};
+
+template <int POT, bool MULTI>
+__global__ void __launch_bounds__(kBlock) sweep_replay_kernel(const ReplayParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *s_tot = s_acc + (MULTI ? p.pool.n_moves * kBlock : 0);
+    __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves];
+    if (threadIdx.x < kMaxMoves) {
+        s_sigma[threadIdx.x] = p.pool.sigma[threadIdx.x];
+        s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
+        s_lognorm[threadIdx.x] = p.pool.lognorm[threadIdx.x];
+    }
+    __syncthreads();
+    const int nm = p.pool.n_moves;
+    constexpr int PF = 4;
+
+    for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
+        double x = p.x[c];
+        double e = potential<POT, ARITH_EXACT>(x);
+        const double beta = p.betas ? p.betas[c] : p.beta;
+        uint32_t acc = 0;
+        if constexpr (MULTI) {
+            for (int k = 0; k < nm; ++k) {
+                s_acc[k * kBlock + threadIdx.x] = p.acc[(size_t)k * p.M + c];
+                s_tot[k * kBlock + threadIdx.x] = p.tot[(size_t)k * p.M + c];
+            }
+        } else {
+            acc = p.acc[c];
+        }
+        for (int64_t s0 = 0; s0 < p.K; s0 += PF) {
+            double zz[PF], ua[PF], uc[PF];
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                if (s0 + i < p.K) {
+                    const size_t o = (size_t)(s0 + i) * p.M + c;
+                    zz[i] = __ldcs(p.z + o);
+                    ua[i] = __ldcs(p.u_acc + o);
+                    uc[i] = (MULTI && p.u_cat) ? __ldcs(p.u_cat + o) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                if (s0 + i < p.K) {
+                    int d;
+                    if constexpr (MULTI) {
+                        const int k = categorical(nm, s_weight, uc[i]);
+                        d = mc_step_exact<POT>(x, e, beta, s_sigma[k], s_lognorm[k], zz[i], ua[i]);
+                        s_acc[k * kBlock + threadIdx.x] += d;
+                        s_tot[k * kBlock + threadIdx.x] += 1;
+                    } else {
+                        d = mc_step_exact<POT>(x, e, beta, s_sigma[0], s_lognorm[0], zz[i], ua[i]);
+                        acc += d;
+                    }
+                    if (p.decisions) __stcs(p.decisions + (size_t)(s0 + i) * p.M + c, (uint8_t)d);
+                }
+            }
+        }
+        p.x[c] = x;
+        if constexpr (MULTI) {
+            for (int k = 0; k < nm; ++k) {
+                p.acc[(size_t)k * p.M + c] = s_acc[k * kBlock + threadIdx.x];
+                p.tot[(size_t)k * p.M + c] = s_tot[k * kBlock + threadIdx.x];
+            }
+        } else {
+            p.acc[c] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// XOSHIRO sweep: the reference's own draw order per step -- u_cat = rand, z = randn, u_acc = rand
+// (metropolis.jl:206, particle_1d.jl:57, metropolis.jl:184) -- from a per-chain xoshiro256++ state in HBM.
+// ---------------------------------------------------------------------------------------------------------
+struct XoshiroParams {
+    double *x;
+    uint32_t *acc;
+    uint32_t *tot;
+    const double *betas;
+    double beta;
+    int64_t M;
+    int64_t K;
+    uint64_t *rng;        // [M][4]
+    const uint64_t *ki;   // ziggurat tables in global memory (copied to shared)
+    const double *wi;
+    const double *fi;
+    PoolParams pool;
+};
+
+template <int POT, int ARITH, bool MULTI>
+__global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *s_tot = s_acc + (MULTI ? p.pool.n_moves * kBlock : 0);
+    __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves];
+    __shared__ uint64_t s_ki[256];
+    __shared__ double s_wi[256], s_fi[256];
+    if (threadIdx.x < kMaxMoves) {
+        s_sigma[threadIdx.x] = p.pool.sigma[threadIdx.x];
+        s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
+        s_lognorm[threadIdx.x] = p.pool.lognorm[threadIdx.x];
+    }
+    for (int i = threadIdx.x; i < 256; i += kBlock) {
+        s_ki[i] = p.ki[i];
+        s_wi[i] = p.wi[i];
+        s_fi[i] = p.fi[i];
+    }
+    __syncthreads();
+    const ZigTables T{s_ki, s_wi, s_fi};
+    const int nm = p.pool.n_moves;
+
+    for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
+        double x = p.x[c];
+        double e = potential<POT, ARITH>(x);
+        const double beta = p.betas ? p.betas[c] : p.beta;
+        const ulonglong2 r01 = *reinterpret_cast<const ulonglong2 *>(p.rng + 4 * c);
+        const ulonglong2 r23 = *reinterpret_cast<const ulonglong2 *>(p.rng + 4 * c + 2);
+        Xoshiro g{r01.x, r01.y, r23.x, r23.y};
+        uint32_t acc = 0;
+        if constexpr (MULTI) {
+            for (int k = 0; k < nm; ++k) {
+                s_acc[k * kBlock + threadIdx.x] = p.acc[(size_t)k * p.M + c];
+                s_tot[k * kBlock + threadIdx.x] = p.tot[(size_t)k * p.M + c];
+            }
+        } else {
+            acc = p.acc[c];
+        }
+        for (int64_t s = 0; s < p.K; ++s) {
+            const double uc = g.rand();  // always consumed, even when n_moves == 1 (metropolis.jl:206)
+            const double zz = xoshiro_randn(g, T);
+            const double ua = g.rand();
+            if constexpr (MULTI) {
+                const int k = categorical(nm, s_weight, uc);
+                int d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], zz, ua);
+                s_acc[k * kBlock + threadIdx.x] += d;
+                s_tot[k * kBlock + threadIdx.x] += 1;
+            } else {
+                (void)uc;
+                acc += mc_step<POT, ARITH>(x, e, beta, s_sigma[0], s_lognorm[0], zz, ua);
+            }
+        }
+        p.x[c] = x;
+        *reinterpret_cast<ulonglong2 *>(p.rng + 4 * c) = make_ulonglong2(g.s0, g.s1);
+        *reinterpret_cast<ulonglong2 *>(p.rng + 4 * c + 2) = make_ulonglong2(g.s2, g.s3);
+        if constexpr (MULTI) {
+            for (int k = 0; k < nm; ++k) {
+                p.acc[(size_t)k * p.M + c] = s_acc[k * kBlock + threadIdx.x];
+                p.tot[(size_t)k * p.M + c] = s_tot[k * kBlock + threadIdx.x];
+            }
+        } else {
+            p.acc[c] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2 (standalone): callback sums over the resident state.  sums = [Σ e, Σ_c acc_ck/tot_ck (k < n_moves), count].
+// Used for multi-move pools and whenever callbacks are requested without a preceding fused-reduce sweep.
+// ---------------------------------------------------------------------------------------------------------
+struct ReduceParams {
+    const double *x;
+    const uint32_t *acc;
+    const uint32_t *tot;   // nullptr -> steps_done
+    int64_t M;
+    int64_t steps_done;
+    int n_moves;
+    int potential;
+    double *partials;
+    unsigned int *ticket;
+    double *sums;
+};
+
+__global__ void __launch_bounds__(kBlock) callback_reduce_kernel(const ReduceParams p)
+{
+    double vals[kMaxOut];
+#pragma unroll
+    for (int i = 0; i < kMaxOut; ++i) vals[i] = 0.0;
+    for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
+        const double x = p.x[c];
+        double e;
+        if (p.potential == POT_HARMONIC) e = potential<POT_HARMONIC, ARITH_EXACT>(x);
+        else if (p.potential == POT_QUARTIC) e = potential<POT_QUARTIC, ARITH_EXACT>(x);
+        else e = potential<POT_DOUBLE_WELL, ARITH_EXACT>(x);
+        vals[0] += e;
+#pragma unroll
+        for (int k = 0; k < kMaxMoves; ++k) {
+            if (k < p.n_moves) {
+                const double a = (double)p.acc[(size_t)k * p.M + c];
+                const double t = p.tot ? (double)p.tot[(size_t)k * p.M + c] : (double)p.steps_done;
+                vals[1 + k] += a / t;
+            }
+        }
+        vals[kMaxOut - 1] += 1.0;
+    }
+    // count is exported right after the per-move sums: move it to slot 1 + n_moves
+    double cnt = vals[kMaxOut - 1];
+#pragma unroll
+    for (int k = 0; k < kMaxOut; ++k)
+        if (k == 1 + p.n_moves) vals[k] = cnt;
+    block_reduce_and_finish<kMaxOut>(vals, 2 + p.n_moves, p.partials, p.ticket, p.sums, false);
+}
+
+// Per-move totals of the counters (what a single-ensemble host Move would hold): out[k] = Σ_c acc, out[nm+k] = Σ_c tot
+__global__ void __launch_bounds__(kBlock) counter_sum_kernel(const uint32_t *acc, const uint32_t *tot, int64_t M,
+                                                             int n_moves, int64_t steps_done,
+                                                             unsigned long long *out)
+{
+    for (int k = 0; k < n_moves; ++k) {
+        unsigned long long a = 0, t = 0;
+        for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < M; c += (int64_t)gridDim.x * kBlock) {
+            a += acc[(size_t)k * M + c];
+            t += tot ? tot[(size_t)k * M + c] : (unsigned long long)steps_done;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(out + k, a);           // integer atomics: order-independent, deterministic
+            atomicAdd(out + n_moves + k, t);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: PGMC estimator for ONE learnable move per launch (the reference's outer loop, estimator.jl:112).
+// Per chain: q_batch x pgmc_estimate (gradients.jl:93-109) with the analytic ∂σ log q; sums of
+// (j, ∇j, ∇logq_forward, g, n) are block-reduced and ADDED to gd[5] by the last block (gradients_data[k] += gd,
+// estimator.jl:130).  REPLAY reads z[q_batch][M] instead of the Philox estimator stream.
+// ---------------------------------------------------------------------------------------------------------
+struct PgmcParams {
+    double *x;
+    const double *betas;
+    double beta;
+    int64_t M;
+    int q_batch;
+    int64_t q0;           // estimator samples already drawn per chain (draw index base)
+    uint64_t sid0;
+    double sigma;
+    double lognorm;
+    const double *z;      // replay only
+    double *partials;
+    unsigned int *ticket;
+    double *gd;           // [5] accumulators of this learnable move
+};
+
+template <int POT, int ARITH>
+__device__ __forceinline__ void pgmc_sample(double &x, double &e, double beta, double sigma, double lognorm,
+                                            double z, double &sj, double &sdj, double &sgf, double &sg)
+{
+    if constexpr (ARITH == ARITH_EXACT) {
+        double delta = __dadd_rn(0.0, __dmul_rn(sigma, z));                                    // gradients.jl:119
+        double s2 = __dmul_rn(sigma, sigma);
+        // ∂σ log q = δ²/σ³ − 1/σ, evaluated as (δ·δ)/((σ·σ)·σ) − 1/σ (oracle: ao_dlogq_dsigma)
+        double gf = __dsub_rn(__ddiv_rn(__dmul_rn(delta, delta), __dmul_rn(s2, sigma)), __ddiv_rn(1.0, sigma));
+        double lqf = __dsub_rn(__ddiv_rn(-__dmul_rn(delta, delta), __dmul_rn(2.0, s2)), lognorm);
+        double e1 = e;
+        x = __dadd_rn(x, delta);                                                               // :98
+        e = potential<POT, ARITH_EXACT>(x);
+        double dlogp = __dsub_rn(__dmul_rn(-e, beta), __dmul_rn(-e1, beta));                   // :99
+        double r = __dmul_rn(delta, delta);                                                    // :100
+        delta = -delta;                                                                        // :101
+        double gb = gf, lqb = lqf;                                                             // :102 (even in δ)
+        x = __dadd_rn(x, delta);                                                               // :103 undo (drifts)
+        e = potential<POT, ARITH_EXACT>(x);
+        double ex = exp(__dsub_rn(__dadd_rn(dlogp, lqb), lqf));                                // :104
+        double alpha = (ex > 1.0) ? 1.0 : ex;
+        double j = __dmul_rn(r, alpha);                                                        // :105
+        double dj = __dmul_rn(j, (alpha == 1.0) ? gf : gb);                                    // :106
+        sj += j; sdj += dj; sgf += gf; sg += __dmul_rn(gf, gf);                                // :107, :68-76
+    } else {
+        double delta = sigma * z;
+        double inv_s = 1.0 / sigma;
+        double gf = fma(z, z, -1.0) * inv_s;   // δ²/σ³ − 1/σ = (z² − 1)/σ
+        double xn = x + delta;
+        double en = potential<POT, ARITH_FAST>(xn);
+        double ex = exp(beta * (e - en));
+        double alpha = (ex > 1.0) ? 1.0 : ex;
+        double j = delta * delta * alpha;
+        sj += j; sdj = fma(j, gf, sdj); sgf += gf; sg = fma(gf, gf, sg);
+    }
+}
+
+template <int POT, int ARITH, bool REPLAY>
+__global__ void __launch_bounds__(kBlock) pgmc_kernel(const PgmcParams p)
+{
+    double sj = 0.0, sdj = 0.0, sgf = 0.0, sg = 0.0, sn = 0.0;
+    const int64_t qend = p.q0 + p.q_batch;
+    for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
+        double x = p.x[c];
+        double e = potential<POT, ARITH>(x);
+        const double beta = p.betas ? p.betas[c] : p.beta;
+        if constexpr (REPLAY) {
+            for (int b = 0; b < p.q_batch; ++b)
+                pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, __ldcs(p.z + (size_t)b * p.M + c), sj, sdj,
+                                        sgf, sg);
+        } else {
+            const uint64_t sid = p.sid0 + (uint64_t)c;
+            for (int64_t pr = p.q0 >> 1; 2 * pr < qend; ++pr) {
+                const U64Pair blk = philox_block<kTagEstimator>(sid, (uint64_t)pr);
+                double z0, z1;
+                box_muller(blk.a_lo, blk.a_hi, blk.b_lo, blk.b_hi, z0, z1);
+                if (2 * pr >= p.q0) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z0, sj, sdj, sgf, sg);
+                if (2 * pr + 1 < qend) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z1, sj, sdj, sgf, sg);
+            }
+        }
+        sn += (double)p.q_batch;
+        if constexpr (ARITH == ARITH_EXACT) p.x[c] = x;  // perform/undo rounding drift is part of the reference
+    }
+    double vals[5] = {sj, sdj, sgf, sg, sn};
+    block_reduce_and_finish<5>(vals, 5, p.partials, p.ticket, p.gd, true);
+}
+
+// K5: synthetic initial condition x0 = 4u − 2 (MC_harmonic_oscillator.jl:13) from stream tag 0.
+__global__ void __launch_bounds__(kBlock) init_kernel(double *x, int64_t M, uint64_t sid0)
+{
+    for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < M; c += (int64_t)gridDim.x * kBlock) {
+        const U64Pair b = philox_block<kTagInit>(sid0 + (uint64_t)c, 0);
+        x[c] = __dsub_rn(__dmul_rn(4.0, u53(b.a_lo, b.a_hi)), 2.0);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) energy_kernel(const double *x, double *e, int64_t M, int pot)
+{
+    for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < M; c += (int64_t)gridDim.x * kBlock) {
+        const double v = x[c];
+        if (pot == POT_HARMONIC) e[c] = potential<POT_HARMONIC, ARITH_EXACT>(v);
+        else if (pot == POT_QUARTIC) e[c] = potential<POT_QUARTIC, ARITH_EXACT>(v);
+        else e[c] = potential<POT_DOUBLE_WELL, ARITH_EXACT>(v);
+    }
+}
+
+// FP64 pipe peak: 8 independent DFMA chains per thread, no memory traffic.
+__global__ void __launch_bounds__(kBlock) dfma_peak_kernel(double *out, int iters, double a, double b)
+{
+    double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+            v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * kBlock + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+
+}  // namespace arianna

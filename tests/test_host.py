@@ -1,0 +1,306 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, argument validation,
+the Python mirror of Arianna's driver (schedules, event order, lazy fused flush, file formats, learner rules) and
+the multi-rank path under gloo with world_size 2.  No kernel runs here (there is no GPU in this container)."""
+import ctypes as C
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import montecarlo_b200 as mb
+from montecarlo_b200 import _lib as L
+from montecarlo_b200 import arianna as A
+from montecarlo_b200 import policy_guided as PG
+from oracle import oracle as O
+from oracle import oracle_np as N
+
+from fake_engine import OracleEngine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- the C ABI -------------------------------------------------------------------------------------------
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "arianna_cuda.h")).read()
+    return sorted(set(re.findall(r"ARIANNA_API[^;(]*?\b(arianna_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _header_symbols()
+    assert len(names) >= 30
+    lib = C.CDLL(mb.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/arianna_cuda.h but not exported"
+    assert sorted(L.SYMBOLS) == names            # the ctypes table binds exactly the declared surface
+    assert L.load().arianna_abi_version() == 1
+
+
+def test_library_is_sm100a_native():
+    out = subprocess.run(["cuobjdump", "-lelf", mb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def _cfg(**kw):
+    cfg = L.Config()
+    cfg.struct_size = C.sizeof(L.Config)
+    cfg.device, cfg.n_chains, cfg.beta, cfg.n_moves = -1, 16, 2.0, 1
+    cfg.sigma[0], cfg.weight[0] = 0.1, 1.0
+    cfg.arith_mode = L.ARITH_FAST
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _create(cfg):
+    h = C.c_void_p()
+    rc = L.load().arianna_create(C.byref(cfg), C.byref(h))
+    return rc, L.load().arianna_last_error(None).decode()
+
+
+def test_create_validates_arguments_before_touching_the_device():
+    assert _create(_cfg(struct_size=8))[0] == L.ERR_INVALID
+    assert _create(_cfg(n_chains=0))[0] == L.ERR_INVALID
+    assert _create(_cfg(n_moves=0))[0] == L.ERR_INVALID
+    assert _create(_cfg(n_moves=17))[0] == L.ERR_INVALID
+    assert _create(_cfg(potential=9))[0] == L.ERR_INVALID
+    assert _create(_cfg(rng_mode=7))[0] == L.ERR_INVALID
+    c = _cfg()
+    c.sigma[0] = -0.1
+    assert _create(c)[0] == L.ERR_INVALID
+    c = _cfg()
+    c.weight[0] = 0.7                              # Categorical([0.7]) throws in the reference [EXT]
+    rc, msg = _create(c)
+    assert rc == L.ERR_INVALID and "sum to 1" in msg
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    rc, msg = _create(_cfg())
+    assert rc == L.ERR_NO_DEVICE and "no CPU fallback" in msg
+    with pytest.raises(mb.AriannaError):
+        mb.CudaEnsemble(8, 2.0, [0.1])
+
+
+def test_null_handle_is_an_error_not_a_crash():
+    lib = L.load()
+    assert lib.arianna_sweep(None, 1, 0) == L.ERR_INVALID
+    assert lib.arianna_destroy(None) == L.OK
+
+
+# ---- build_schedule (simulation.jl:95-117) -------------------------------------------------------------------
+def test_build_schedule_matches_restatement():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        steps = int(rng.integers(10, 5000))
+        burn = int(rng.integers(0, steps))
+        dt = int(rng.integers(1, 200))
+        assert A.build_schedule(steps, burn, dt) == N.build_schedule(steps, burn, dt)
+        blk = sorted(set(int(v) for v in rng.integers(0, 50, size=3))) or [1]
+        if blk[-1] == 0:
+            blk.append(5)
+        assert A.build_schedule(steps, burn, blk) == N.build_schedule(steps, burn, blk)
+    assert A.build_schedule(10 ** 5, 1000, [0, 10])[:3] == [1000, 1010, 1020]
+    assert A.build_schedule(1000, 10, 2.0) == N.build_schedule(1000, 10, 2.0)
+    assert A.build_schedule(100, 10, 30) == [10, 40, 70, 100]
+
+
+def test_shard_bounds_partition():
+    for n, w in [(10, 1), (10, 2), (10, 3), (2 ** 27, 8), (7, 8)]:
+        spans = [A.shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+        for (o1, c1), (o2, _) in zip(spans, spans[1:]):
+            assert o1 + c1 == o2
+
+
+def test_julia_number_rendering():
+    assert A._jl(0.25) == "0.25" and A._jl(1e-5) == "1.0e-5" and A._jl(float("nan")) == "NaN"
+    assert A._jl([0.5, float("nan")]) == "[0.5, NaN]" and A._jl(3) == "3"
+
+
+# ---- learner rules -------------------------------------------------------------------------------------------
+OPTS = [(PG.VPG(1e-3), O.OPT_VPG, 1e-3, 0), (PG.BLPG(1e-3), O.OPT_BLPG, 1e-3, 0),
+        (PG.BLAPG(1e-6, 1e-6), O.OPT_BLAPG, 1e-6, 1e-6), (PG.NPG(1e-2, 1e-6), O.OPT_NPG, 1e-2, 1e-6),
+        (PG.ANPG(1e-6, 1e-6), O.OPT_ANPG, 1e-6, 1e-6), (PG.BLANPG(1e-6, 1e-6), O.OPT_BLANPG, 1e-6, 1e-6)]
+
+
+@pytest.mark.parametrize("opt,kind,p1,p2", OPTS)
+def test_learning_step_matches_oracle(opt, kind, p1, p2):
+    rec = [3.1, 1.2, -40.0, 210.0, 100.0]          # sums over n = 100 samples
+    gd = PG.average(PG.GradientData.from_record(rec))
+    th = np.array([0.2])
+    PG.learning_step(th, gd, opt)
+    want = O.learning_step(kind, p1, p2, np.array(rec[:4]) / 100.0, 0.2)
+    assert abs(th[0] - want) < 1e-15
+
+
+def test_analytic_gradient_matches_reference_tolerance():
+    """ad_backends_test.jl:31-32 (atol 1e-10) at its own point δ = 0, σ = 0.2."""
+    assert abs(PG.log_proposal_density(0.0, 0.2) - (-math.log(2 * math.pi * 0.04) / 2)) < 1e-10
+    assert abs(PG.dlogq_dsigma(0.0, 0.2) + 5.0) < 1e-10
+    for d, s in [(0.3, 0.2), (-1.1, 0.7)]:
+        assert abs(PG.dlogq_dsigma(d, s) - O.dlogq_dsigma(d, s)) < 1e-12
+
+
+# ---- the driver loop over a test double (oracle-backed engine) -------------------------------------------------
+@pytest.fixture
+def fake_engine(monkeypatch):
+    monkeypatch.setattr(A, "CudaEnsemble", OracleEngine)
+
+
+def _mc_setup(tmp_path, M=64, steps=200, burn=50):
+    beta, seed = 2.0, 42
+    x0 = O.init_synthetic(seed, 0, M)
+    chains = mb.ParticleEnsemble(x0, beta)
+    pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.1), 1.0),)
+    sampletimes = mb.build_schedule(steps, burn, [0, 10])
+    algorithm_list = (
+        dict(algorithm=mb.Metropolis, pool=pool, seed=seed, parallel=False),
+        dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance), scheduler=sampletimes),
+        dict(algorithm=mb.StoreTrajectories, scheduler=sampletimes),
+        dict(algorithm=mb.StoreLastFrames, scheduler=[steps]),
+        dict(algorithm=mb.PrintTimeSteps, scheduler=mb.build_schedule(steps, burn, steps // 10)),
+    )
+    return x0, chains, sampletimes, mb.Simulation(chains, algorithm_list, steps, path=str(tmp_path))
+
+
+def test_run_matches_stepwise_oracle_and_fuses_steps(tmp_path, fake_engine):
+    M, steps, burn = 64, 200, 50
+    x0, chains, sampletimes, sim = _mc_setup(tmp_path, M, steps, burn)
+    mb.run(sim)
+    # fused flushes: one launch per gap between observation points, not one per step
+    assert chains.engine.launch_count == len(sampletimes)
+    assert chains.engine.steps_done == steps
+    # reference order: callbacks at t see the state after t Metropolis steps (simulation.jl:184-191)
+    ref = O.Ensemble(x0, 2.0, [0.1])
+    lines = open(tmp_path / "energy.dat").read().split("\n")[:-1]
+    assert lines[0].split()[0] == "0"                              # store_first record at t = 0
+    assert float(lines[0].split()[1]) == ref.callback_energy()
+    acc_lines = open(tmp_path / "acceptance.dat").read().split("\n")[:-1]
+    assert acc_lines[0] == "0 [NaN]"                               # 0/0 at t = 0 (metropolis.jl:320)
+    done = 0
+    for ln, al, t in zip(lines[1:], acc_lines[1:], sampletimes):
+        _, z, ua = O.draws_philox(42, 0, M, done, t - done, with_cat=False)
+        ref.sweep_replay(None, z, ua)
+        done = t
+        # summation order differs (device/test-double tree sums vs the reference's sequential sum): ≤ 1e-13 rel.
+        assert int(ln.split()[0]) == t and abs(float(ln.split()[1]) / ref.callback_energy() - 1) < 1e-13
+        assert al.startswith(f"{t} [") and abs(float(al.split("[")[1][:-1]) / ref.callback_acceptance()[0] - 1) < 1e-13
+    # trajectories: reference text layout, 1-based chain directories, "t x" lines (particle_1d.jl:63-66)
+    rows = open(tmp_path / "trajectories" / "1" / "trajectory.dat").read().split("\n")[:-1]
+    assert len(rows) == 1 + len(sampletimes) and rows[-1] == f"{steps} {A._jl(float(ref.x[0]))}"
+    t, x = mb.StoreTrajectories.read_binary(str(tmp_path / "trajectories" / "rank0.bin"), M)
+    assert list(t) == [0] + sampletimes and np.array_equal(x[-1], ref.x)
+    last = open(tmp_path / "trajectories" / str(M) / "lastframe.dat").read()
+    assert last == f"{steps} {A._jl(float(ref.x[-1]))}\n"
+    assert "Metropolis" in open(tmp_path / "summary.log").read()
+
+
+def test_simulation_constructor_contract(tmp_path, fake_engine):
+    chains = mb.ParticleEnsemble(np.zeros(4), 2.0)
+    pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.1), 1.0),)
+    with pytest.raises(AssertionError):                            # scheduler entries must be in 0..steps
+        mb.Simulation(chains, (dict(algorithm=mb.Metropolis, pool=pool, scheduler=[5, 500]),), 100, path=str(tmp_path))
+    chains = mb.ParticleEnsemble(np.zeros(4), 2.0)
+    with pytest.raises(AssertionError):                            # schedulers must be sorted
+        mb.Simulation(chains, (dict(algorithm=mb.Metropolis, pool=pool, scheduler=[5, 3]),), 100, path=str(tmp_path))
+    with pytest.raises(TypeError):
+        mb.Move(mb.Displacement(0.0), object(), mb.ComponentArray(σ=0.1), 1.0)
+    # list of Particles (the reference's `chains` vector) is accepted for small ensembles
+    sim = mb.Simulation([mb.System(0.5, 2.0), mb.System(-0.5, 2.0)],
+                        (dict(algorithm=mb.Metropolis, pool=pool, seed=3),), 10, path=str(tmp_path))
+    assert len(sim.chains) == 2 and sim.counters == [0]
+    mb.run(sim)
+    assert sim.chains.engine.steps_done == 10
+
+
+def test_pgmc_driver_learns(tmp_path, fake_engine):
+    """pgmc_test.jl:10-52 shrunk: 3 moves (Static, VPG, BLANPG); every learner must move σ from 0.2 towards 1.2."""
+    M, steps, burn = 1024, 260, 20
+    x0 = O.init_synthetic(42, 0, M)
+    chains = mb.ParticleEnsemble(x0, 2.0)
+    mk = lambda w: mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.2), w)
+    pool = (mk(0.4), mk(0.3), mk(0.3))
+    optimisers = (PG.Static(), PG.VPG(0.08), PG.BLANPG(4e-3, 1e-6))
+    sampletimes = mb.build_schedule(steps, burn, [0, 10])
+    algorithm_list = (
+        dict(algorithm=mb.Metropolis, pool=pool, seed=42, parallel=False),
+        dict(algorithm=PG.PolicyGradientEstimator, dependencies=(mb.Metropolis,), optimisers=optimisers, q_batch_size=4),
+        dict(algorithm=PG.PolicyGradientUpdate, dependencies=(PG.PolicyGradientEstimator,),
+             scheduler=mb.build_schedule(steps, burn, 2)),
+        dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance), scheduler=sampletimes),
+        dict(algorithm=mb.StoreParameters, dependencies=(mb.Metropolis,), scheduler=sampletimes),
+    )
+    sim = mb.Simulation(chains, algorithm_list, steps, path=str(tmp_path))
+    mb.run(sim)
+    sig = [m.parameters.σ for m in pool]
+    assert sig[0] == 0.2 and abs(sig[1] - 1.2) < 0.2 and abs(sig[2] - 1.2) < 0.2, sig
+    rows = open(tmp_path / "parameters" / "2" / "parameters.dat").read().split("\n")[:-1]
+    assert rows[0] == "0 [0.2]" and rows[-1] == f"{steps} [{sig[1]!r}]"
+    e = np.loadtxt(tmp_path / "energy.dat")[:, 1]
+    assert abs(e[len(e) // 2:].mean() - 0.25) < 5e-2               # pgmc_test.jl:45
+    # estimator accumulates between updates and is reset by the update (update.jl:55)
+    assert np.all(chains.engine.gd == 0)
+
+
+# ---- N > 1: world_size-2 gloo -----------------------------------------------------------------------------------
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch.distributed as dist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+import montecarlo_b200 as mb
+from montecarlo_b200 import arianna as A
+from fake_engine import OracleEngine
+from oracle import oracle as O
+A.CudaEnsemble = OracleEngine
+M, steps = 101, 60                      # odd M: ragged shards
+x0 = O.init_synthetic(7, 0, M)
+chains = mb.ParticleEnsemble(x0, 2.0)
+pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.3), 0.5),
+        mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.05), 0.5))
+sched = mb.build_schedule(steps, 10, 10)
+sim = mb.Simulation(chains, (dict(algorithm=mb.Metropolis, pool=pool, seed=7),
+                             dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance),
+                                  scheduler=sched),
+                             dict(algorithm=mb.StoreTrajectories, scheduler=[steps], store_first=False)),
+                    steps, path={path!r})
+mb.run(sim)
+np.save(os.path.join({path!r}, f"x_rank{{chains.rank}}.npy"), chains.x)
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_matches_single_process(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port, path=str(tmp_path)))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    # single-process oracle over the WHOLE ensemble
+    M, steps = 101, 60
+    x0 = O.init_synthetic(7, 0, M)
+    ref = O.Ensemble(x0, 2.0, [0.3, 0.05], [0.5, 0.5])
+    sched = A.build_schedule(steps, 10, 10)
+    rows_e = open(tmp_path / "energy.dat").read().split("\n")[:-1]
+    rows_a = open(tmp_path / "acceptance.dat").read().split("\n")[:-1]
+    done = 0
+    for i, t in enumerate(sched):
+        uc, z, ua = O.draws_philox(7, 0, M, done, t - done)
+        ref.sweep_replay(uc, z, ua)
+        done = t
+        te, ve = rows_e[1 + i].split(" ", 1)
+        assert int(te) == t and abs(float(ve) - ref.callback_energy()) < 1e-13
+        got = np.array([float(v.replace("NaN", "nan")) for v in rows_a[1 + i].split(" ", 1)[1].strip("[]").split(", ")])
+        np.testing.assert_allclose(got, ref.callback_acceptance(), rtol=1e-13, equal_nan=True)
+    # per-chain results are invariant to the sharding (global chain id keys the stream)
+    x = np.concatenate([np.load(tmp_path / f"x_rank{r}.npy") for r in range(2)])
+    assert np.array_equal(x, ref.x)
+    assert os.path.exists(tmp_path / "trajectories" / "rank1.bin")
