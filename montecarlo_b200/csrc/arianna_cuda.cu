@@ -450,11 +450,11 @@ int32_t arianna_sweep_replay(arianna_handle *h, int64_t K, const double *u_cat, 
 {
     if (!h) return ARIANNA_ERR_INVALID;
     REQUIRE(h, K >= 0, "arianna_sweep_replay: K must be >= 0");
+    if (K == 0) return ARIANNA_OK;
     REQUIRE(h, z != nullptr && u_acc != nullptr, "arianna_sweep_replay: z and u_acc are required");
     const bool multi = h->pool.n_moves > 1;
     REQUIRE(h, !multi || u_cat != nullptr, "arianna_sweep_replay: u_cat is required for multi-move pools");
     REQUIRE(h, h->steps_done + K <= 0xFFFFFFFFll, "arianna_sweep_replay: per-chain counters are 32-bit");
-    if (K == 0) return ARIANNA_OK;
     DeviceGuard guard(h->device);
     const size_t smem = multi ? sizeof(uint32_t) * 2 * h->pool.n_moves * kBlock : 0;
 

@@ -24,7 +24,7 @@ class _DeviceBuffer:
     def __init__(self, ptr: int, n: int, stream: int):
         self.__cuda_array_interface__ = {
             "shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None,
-            "stream": stream if stream else None,
+            "stream": None,  # ordering is the caller's job: use the tensor on the engine's own stream
         }
 
 

@@ -1,0 +1,463 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (ctypes), against the CPU oracle on the same seeded
+inputs, against the committed golden fixtures, and -- at BASELINE.json's full sizes -- through size-independent
+properties (chunking / sharding invariance, determinism, analytic ensemble averages).
+
+Bars (north star): replay mode -> accept/reject decisions bit-identical, positions bit-identical (stricter than
+the required 1e-12 relative); native-Philox mode -> identical decisions and |Δx| ≤ 1e-12 against the oracle fed
+the same counter-based draws, plus 3σ agreement with the analytic harmonic averages.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import montecarlo_b200 as mb
+from montecarlo_b200 import policy_guided as PG
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+POTS = {"harmonic": O.POT_HARMONIC, "quartic": O.POT_QUARTIC, "double_well": O.POT_DOUBLE_WELL}
+
+
+def _xoshiro_draws(x0, beta, sigma, weight, K, seed=42):
+    gen = O.Ensemble(x0, beta, sigma, weight)
+    gen.seed_xoshiro(seed)
+    return gen.draws_xoshiro(K)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# replay mode: bit-exact
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pot", ["harmonic", "quartic", "double_well"])
+@pytest.mark.parametrize("sigma,weight", [([0.1], [1.0]), ([0.2] * 7, [0.4] + [0.1] * 6), ([1.5, 0.01], [0.3, 0.7])])
+def test_replay_bit_exact(pot, sigma, weight):
+    M, K, beta = 10007, 67, 2.0                       # ragged M (not a multiple of the block), K not a multiple of 4
+    x0 = O.init_synthetic(11, 0, M)
+    uc, z, ua = _xoshiro_draws(x0, beta, sigma, weight, K)
+    ref = O.Ensemble(x0, beta, sigma, weight, potential=POTS[pot])
+    dec_ref, _, alpha = ref.sweep_replay(uc, z, ua, want_decisions=True, want_alpha=True)
+    with mb.CudaEnsemble(M, beta, sigma, weight, potential=pot, arith="exact") as eng:
+        eng.set_state(x0)
+        dec = eng.sweep_replay(uc if len(sigma) > 1 else None, z, ua, want_decisions=True)
+        x, e = eng.get_state(with_energy=True)
+        acc, tot = eng.chain_counters()
+        bad = np.argwhere(dec != dec_ref)
+        # a flip is only legitimate if |α − u| is within an ulp of exp(); report it instead of assuming impossibility
+        assert bad.size == 0, [(int(s), int(c), float(alpha[s, c] - ua[s, c])) for s, c in bad[:5]]
+        assert np.array_equal(x, ref.x), float(np.max(np.abs(x - ref.x)))
+        assert np.array_equal(e, ref.e)
+        assert np.array_equal(acc.astype(np.int64), ref.acc) and np.array_equal(tot.astype(np.int64), ref.tot)
+        assert eng.steps_done == K
+        a_sum, t_sum = eng.counters()
+        assert np.array_equal(a_sum, ref.acc.sum(axis=1)) and np.array_equal(t_sum, ref.tot.sum(axis=1))
+
+
+@pytest.mark.parametrize("name", ["replay_single.npz", "replay_multi.npz", "replay_doublewell.npz"])
+def test_replay_golden_fixtures(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    pot = {v: k for k, v in POTS.items()}[int(g["pot"])]
+    M = g["x0"].size
+    with mb.CudaEnsemble(M, float(g["beta"]), g["sigma"], g["weight"], potential=pot, arith="exact") as eng:
+        eng.set_state(g["x0"])
+        dec = eng.sweep_replay(g["u_cat"], g["z"], g["u_acc"], want_decisions=True)
+        x, e = eng.get_state(with_energy=True)
+        acc, tot = eng.chain_counters()
+        assert np.array_equal(np.packbits(dec), g["decisions"])
+        assert np.array_equal(x, g["x"]) and np.array_equal(e, g["e"])
+        assert np.array_equal(acc, g["acc"]) and np.array_equal(tot, g["tot"])
+        me, ma = eng.callbacks()
+        assert abs(me / float(g["energy"]) - 1) < 1e-13
+        np.testing.assert_allclose(ma, g["acceptance"], rtol=1e-13, equal_nan=True)
+
+
+def test_replay_per_chain_beta_and_chunked_calls():
+    M, K = 4099, 40
+    x0 = O.init_synthetic(5, 0, M)
+    betas = np.linspace(0.5, 4.0, M)                  # the β sweep {0.5,1,2,4} of config 5, in one ensemble
+    uc, z, ua = _xoshiro_draws(x0, 2.0, [0.3], [1.0], K)
+    ref = O.Ensemble(x0, 2.0, [0.3])
+    dec_ref, _, _ = ref.sweep_replay(None, z, ua, want_decisions=True, betas=betas)
+    with mb.CudaEnsemble(M, 2.0, [0.3], arith="exact") as eng:
+        eng.set_state(x0)
+        eng.set_betas(betas)
+        d1 = eng.sweep_replay(None, z[:13], ua[:13], want_decisions=True)
+        d2 = eng.sweep_replay(None, z[13:], ua[13:], want_decisions=True)
+        assert np.array_equal(np.concatenate([d1, d2]), dec_ref)
+        assert np.array_equal(eng.get_state(), ref.x)
+        assert np.array_equal(eng.chain_counters()[0][0], ref.acc[0])
+
+
+def test_replay_edge_cases():
+    # M = 1, K = 1; u_acc = 0 (always accept unless α = 0/NaN); NaN / inf states reject (min(1, NaN) semantics)
+    with mb.CudaEnsemble(1, 2.0, [0.1], arith="exact") as eng:
+        eng.set_state(np.array([0.25]))
+        assert eng.sweep_replay(None, np.zeros((0, 1)), np.zeros((0, 1)), want_decisions=True).shape == (0, 1)  # K = 0
+        d = eng.sweep_replay(None, np.array([[1.0]]), np.array([[0.0]]), want_decisions=True)
+        assert d[0, 0] == 1 and eng.get_state()[0] == 0.25 + 0.1
+    x0 = np.array([np.inf, np.nan, 1e308, 0.1 + 3 * 2.0 ** -54, -0.0])
+    z = np.array([[1.0, 1.0, 1e10, 3.0, 0.0]])
+    ua = np.array([[0.5, 0.5, 0.5, 0.999999, 1 - 2.0 ** -53]])
+    ref = O.Ensemble(x0, 2.0, [1.0])
+    with np.errstate(all="ignore"):
+        dref, _, _ = ref.sweep_replay(None, z, ua, want_decisions=True)
+    with mb.CudaEnsemble(5, 2.0, [1.0], arith="exact") as eng:
+        eng.set_state(x0)
+        d = eng.sweep_replay(None, z, ua, want_decisions=True)
+        assert np.array_equal(d, dref) and list(d[0]) == [0, 0, 0, 0, 1]
+        x = eng.get_state()
+        assert np.array_equal(x, ref.x, equal_nan=True)
+        assert x[3] == (x0[3] + 3.0) - 3.0 and x[3] != x0[3]      # reject path is fl(fl(x+δ)−δ), not a restore
+
+
+def test_replay_device_pointers():
+    import torch
+    M, K = 3000, 20
+    x0 = O.init_synthetic(9, 0, M)
+    uc, z, ua = _xoshiro_draws(x0, 2.0, [0.2, 0.4], [0.5, 0.5], K)
+    ref = O.Ensemble(x0, 2.0, [0.2, 0.4], [0.5, 0.5])
+    dref, _, _ = ref.sweep_replay(uc, z, ua, want_decisions=True)
+    with mb.CudaEnsemble(M, 2.0, [0.2, 0.4], [0.5, 0.5], arith="exact") as eng:
+        eng.set_state(x0)
+        with torch.cuda.stream(eng.torch_stream()):
+            duc, dz, dua = (torch.from_numpy(a).cuda() for a in (uc, z, ua))
+            ddec = torch.empty((K, M), dtype=torch.uint8, device="cuda")
+            eng.sweep_replay_device(K, duc.data_ptr(), dz.data_ptr(), dua.data_ptr(), ddec.data_ptr())
+            eng.synchronize()
+        assert np.array_equal(ddec.cpu().numpy(), dref) and np.array_equal(eng.get_state(), ref.x)
+
+
+def test_error_behaviour():
+    with mb.CudaEnsemble(8, 2.0, [0.2, 0.4], [0.5, 0.5]) as eng:
+        with pytest.raises(mb.AriannaError):                      # multi-move replay needs u_cat
+            eng.sweep_replay(None, np.zeros((1, 8)), np.zeros((1, 8)))
+        with pytest.raises(mb.AriannaError):                      # Normal(0, σ ≤ 0) throws in the reference
+            eng.set_params(0, -1.0)
+        with pytest.raises(mb.AriannaError):
+            eng.set_params(5, 0.1)
+        with pytest.raises(mb.AriannaError):                      # XOSHIRO state on a PHILOX handle
+            eng.set_rng_state(np.zeros((8, 4), dtype=np.uint64))
+        with pytest.raises(mb.AriannaError):
+            eng.pgmc_estimate(0, [1])
+    with pytest.raises(mb.AriannaError):
+        mb.CudaEnsemble(8, 2.0, [0.1, 0.1], [0.7, 0.7])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# native Philox mode against the oracle fed the same counter-based draws
+# ---------------------------------------------------------------------------------------------------------
+def test_init_synthetic_bit_exact():
+    with mb.CudaEnsemble(5001, 2.0, [0.1], seed=42, chain_offset=12345) as eng:
+        eng.init_synthetic()
+        assert np.array_equal(eng.get_state(), O.init_synthetic(42, 12345, 5001))
+        eng.init_synthetic(7)
+        assert np.array_equal(eng.get_state(), O.init_synthetic(7, 12345, 5001))
+
+
+@pytest.mark.parametrize("arith", ["exact", "fast"])
+@pytest.mark.parametrize("sigma,weight", [([0.1], [1.0]), ([0.2] * 7, [0.4] + [0.1] * 6)])
+def test_philox_native_matches_oracle(arith, sigma, weight):
+    M, K, beta, seed, off = 6000, 101, 2.0, 42, 777     # odd K: exercises the half-used Box-Muller pair
+    x0 = O.init_synthetic(seed, off, M)
+    uc, z, ua = O.draws_philox(seed, off, M, 0, K)
+    ref = O.Ensemble(x0, beta, sigma, weight)
+    ref.sweep_replay(uc, z, ua)
+    with mb.CudaEnsemble(M, beta, sigma, weight, seed=seed, chain_offset=off, arith=arith) as eng:
+        eng.init_synthetic()
+        eng.sweep(K)
+        x = eng.get_state()
+        acc, tot = eng.chain_counters()
+    # Box-Muller on the device uses CUDA's log/sincospi, the oracle glibc's: normals agree to a few ulp, so x agrees
+    # to ~1e-15 and a decision can only flip when |α − u| ≲ 1e-15
+    assert np.max(np.abs(x - ref.x)) < 1e-12
+    assert np.array_equal(tot.astype(np.int64), ref.tot)
+    assert np.array_equal(acc.astype(np.int64), ref.acc)
+
+
+@pytest.mark.parametrize("arith", ["exact", "fast"])
+@pytest.mark.parametrize("nm", [1, 3])
+def test_chunk_and_shard_invariance(arith, nm):
+    M, seed = 5000, 3
+    sigma, weight = [0.1, 0.3, 0.9][:nm], [[1.0], None, [0.5, 0.25, 0.25]][nm - 1]
+
+    def run(chunks, offset=0, n=M):
+        with mb.CudaEnsemble(n, 2.0, sigma, weight, seed=seed, chain_offset=offset, arith=arith) as eng:
+            eng.init_synthetic()
+            for k in chunks:
+                eng.sweep(k, reduce=(k % 2 == 0))
+            return eng.get_state(), eng.chain_counters()
+
+    x_ref, (a_ref, t_ref) = run([20])
+    for chunks in ([7, 12, 1], [1] * 20, [3, 17], [10, 10]):   # includes launches that start / end on odd steps
+        x, (a, t) = run(chunks)
+        assert np.array_equal(x, x_ref) and np.array_equal(a, a_ref) and np.array_equal(t, t_ref), chunks
+    # sharding: two handles with chain offsets == one handle (global chain id keys the stream)
+    xa, (aa, _) = run([20], 0, 1234)
+    xb, (ab, _) = run([20], 1234, M - 1234)
+    assert np.array_equal(np.concatenate([xa, xb]), x_ref)
+    assert np.array_equal(np.concatenate([aa, ab], axis=1), a_ref)
+    # seed + c − 1 (metropolis.jl:262): chain c+1 under `seed` == chain c under `seed + 1`
+    with mb.CudaEnsemble(M - 1, 2.0, sigma, weight, seed=seed + 1, arith=arith) as eng:
+        eng.set_state(O.init_synthetic(seed, 1, M - 1))
+        eng.sweep(20)
+        assert np.array_equal(eng.get_state(), x_ref[1:])
+
+
+def test_callbacks_fused_and_standalone_match_oracle():
+    M, seed = 100003, 42
+    x0 = O.init_synthetic(seed, 0, M)
+    ref = O.Ensemble(x0, 2.0, [0.1])
+    with mb.CudaEnsemble(M, 2.0, [0.1], seed=seed, arith="exact") as eng:
+        eng.init_synthetic()
+        me, ma = eng.callbacks()                                  # t = 0 store_first record
+        assert abs(me / ref.callback_energy() - 1) < 1e-13 and math.isnan(ma[0])
+        done = 0
+        for K in (10, 1, 33):
+            _, z, ua = O.draws_philox(seed, 0, M, done, K, with_cat=False)
+            ref.sweep_replay(None, z, ua)
+            done += K
+            eng.sweep(K, reduce=True)                             # fused tail reduction
+            s_fused = eng.callback_sums()
+            eng.sweep(0, reduce=True)                             # standalone kernel over the same state
+            s_alone = eng.callback_sums()
+            np.testing.assert_allclose(s_fused, s_alone, rtol=1e-13)
+            assert s_fused[2] == M
+            me, ma = eng.callbacks()
+            assert abs(me / ref.callback_energy() - 1) < 1e-12
+            assert abs(ma[0] / ref.callback_acceptance()[0] - 1) < 1e-12
+
+
+def test_multi_move_acceptance_is_mean_of_ratios_with_nan():
+    M, seed, K = 5000, 8, 3                                       # after 3 steps some chain has never tried move 7
+    sigma, weight = [0.2] * 7, [0.4] + [0.1] * 6
+    x0 = O.init_synthetic(seed, 0, M)
+    uc, z, ua = O.draws_philox(seed, 0, M, 0, K)
+    ref = O.Ensemble(x0, 2.0, sigma, weight)
+    ref.sweep_replay(uc, z, ua)
+    with mb.CudaEnsemble(M, 2.0, sigma, weight, seed=seed) as eng:
+        eng.init_synthetic()
+        eng.sweep(K, reduce=True)
+        me, ma = eng.callbacks()
+        want = ref.callback_acceptance()
+        assert np.all(np.isnan(want))                             # 0/0 somewhere in every move at K = 3
+        assert np.all(np.isnan(ma))
+        eng.sweep(200, reduce=True)
+        uc, z, ua = O.draws_philox(seed, 0, M, K, 200)
+        ref.sweep_replay(uc, z, ua)
+        me, ma = eng.callbacks()
+        np.testing.assert_allclose(ma, ref.callback_acceptance(), rtol=1e-12)
+        assert abs(me / ref.callback_energy() - 1) < 1e-11
+
+
+# ---------------------------------------------------------------------------------------------------------
+# XOSHIRO mode: the reference's generator family on the device
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sigma,weight", [([0.1], [1.0]), ([0.2, 0.6], [0.6, 0.4])])
+def test_xoshiro_mode_matches_oracle(sigma, weight):
+    M, K, seed = 4000, 300, 42
+    x0 = O.init_synthetic(seed, 0, M)
+    ref = O.Ensemble(x0, 2.0, sigma, weight)
+    ref.seed_xoshiro(seed)
+    states0 = ref.states.copy()
+    ref.sweep_xoshiro(K)
+    with mb.CudaEnsemble(M, 2.0, sigma, weight, seed=seed, rng="xoshiro", arith="exact") as eng:
+        eng.set_state(x0)
+        eng.set_rng_state(states0)
+        eng.set_ziggurat_tables(*O.ziggurat_tables())
+        eng.sweep(K)
+        x = eng.get_state()
+        acc, tot = eng.chain_counters()
+        st = eng.get_rng_state()
+    assert np.array_equal(st, ref.states)                         # same number of raw draws consumed by every chain
+    assert np.array_equal(acc.astype(np.int64), ref.acc) and np.array_equal(tot.astype(np.int64), ref.tot)
+    # fast-path normals are bit-identical; ziggurat tail/wedge samples go through log/exp (≤ 1 ulp apart)
+    assert np.max(np.abs(x - ref.x)) < 1e-12
+    assert np.mean(x == ref.x) > 0.9
+
+
+# ---------------------------------------------------------------------------------------------------------
+# PGMC estimator
+# ---------------------------------------------------------------------------------------------------------
+def test_pgmc_replay_matches_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "pgmc.npz"))
+    ns = g["sigma"].size
+    with mb.CudaEnsemble(g["x0"].size, float(g["beta"]), g["sigma"], [1.0 / ns] * ns, arith="exact") as eng:
+        eng.set_state(g["x0"])
+        eng.pgmc_estimate_replay(int(g["q_batch"]), list(g["learn_ids"]), g["z"])
+        gd = eng.pgmc_read(len(g["learn_ids"]))
+        np.testing.assert_allclose(gd, g["gd"], rtol=1e-12)       # tree sum vs sequential fold
+        assert np.array_equal(eng.get_state(), g["x"])            # perform/undo rounding drift reproduced exactly
+        eng.pgmc_estimate_replay(int(g["q_batch"]), list(g["learn_ids"]), g["z"])   # accumulates (estimator.jl:130)
+        assert eng.pgmc_read(2)[0, 4] == 2 * g["gd"][0, 4]
+        eng.pgmc_reset()
+        assert np.all(eng.pgmc_read(2) == 0)
+
+
+@pytest.mark.parametrize("arith", ["exact", "fast"])
+def test_pgmc_native_matches_oracle(arith):
+    M, seed, q = 20011, 42, 5                                     # odd q: second call starts on an odd sample index
+    sigma = [0.2, 0.5, 1.3]
+    learn = [1, 2]
+    x0 = O.init_synthetic(seed, 0, M)
+    ref = O.Ensemble(x0, 2.0, sigma, [0.4, 0.3, 0.3])
+    want = np.zeros((2, 5))
+    with mb.CudaEnsemble(M, 2.0, sigma, [0.4, 0.3, 0.3], seed=seed, arith=arith) as eng:
+        eng.init_synthetic()
+        for call in range(3):
+            z = O.draws_pgmc_philox(seed, 0, M, call * len(learn) * q, len(learn) * q).reshape(len(learn), q, M)
+            want += ref.pgmc_replay(q, learn, z)
+            eng.pgmc_estimate(q, learn)
+        gd = eng.pgmc_read(2)
+        np.testing.assert_allclose(gd, want, rtol=1e-10)          # the reference's own AD-parity tolerance is 1e-10
+        assert gd[0, 4] == 3 * q * M
+        if arith == "exact":
+            assert np.max(np.abs(eng.get_state() - ref.x)) < 1e-13
+        else:
+            assert np.array_equal(eng.get_state(), x0)            # FAST never perturbs the chains
+
+
+# ---------------------------------------------------------------------------------------------------------
+# statistical acceptance tests of the reference (3σ bars), native mode
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("beta", [2.0, 2.5, 3.0])
+@pytest.mark.parametrize("arith", ["fast", "exact"])
+def test_harmonic_distribution(beta, arith):
+    """test/distribution_test.jl:9-39 with M = 2^20 chains: ⟨x⟩ = 0, std = 1/√(2β), ⟨E⟩ = 1/(2β), acceptance."""
+    M = 1 << 20
+    with mb.CudaEnsemble(M, beta, [0.1], seed=42, arith=arith) as eng:
+        eng.init_synthetic()
+        eng.sweep(3000)                                           # x0 ~ U[−2,2) is far from stationary: burn
+        x = eng.get_state()
+        me, ma = eng.callbacks()
+    s = 1 / math.sqrt(2 * beta)
+    assert abs(x.mean()) < 3 * s / math.sqrt(M)
+    assert abs(x.std() - s) < 3 * s / math.sqrt(2 * M)
+    assert abs(me - 1 / (2 * beta)) < 3 * math.sqrt(1 / (2 * beta ** 2) / M)
+    # cumulative acceptance since t = 0 includes the burn-in transient: loose window around (2/π)·atan(2s/σ)
+    assert abs(ma[0] - 2 / math.pi * math.atan(2 * s / 0.1)) < 3e-3
+
+
+def test_pgmc_learns_sigma_through_the_driver(tmp_path):
+    """test/pgmc_test.jl:10-52 at M = 2^16 with faster learning rates: Static keeps σ₀, learners reach ≈1.2±0.2,
+    ⟨energy⟩ ≈ 0.25 ± 0.05."""
+    M, steps, burn = 1 << 16, 600, 50
+    chains = mb.ParticleEnsemble(n_chains=M, beta=2.0)
+    mk = lambda w: mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.2), w)
+    pool = (mk(0.4), mk(0.1), mk(0.1), mk(0.1), mk(0.1), mk(0.1), mk(0.1))
+    optimisers = (PG.Static(), PG.VPG(0.05), PG.BLPG(0.05), PG.BLAPG(2e-3, 1e-6), PG.NPG(0.5, 1e-6),
+                  PG.ANPG(2e-3, 1e-6), PG.BLANPG(2e-3, 1e-6))
+    sampletimes = mb.build_schedule(steps, burn, [0, 10])
+    algorithm_list = (
+        dict(algorithm=mb.Metropolis, pool=pool, seed=42, parallel=False),
+        dict(algorithm=PG.PolicyGradientEstimator, dependencies=(mb.Metropolis,), optimisers=optimisers,
+             q_batch_size=10, parallel=True),
+        dict(algorithm=PG.PolicyGradientUpdate, dependencies=(PG.PolicyGradientEstimator,),
+             scheduler=mb.build_schedule(steps, burn, 2)),
+        dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance), scheduler=sampletimes),
+        dict(algorithm=mb.StoreParameters, dependencies=(mb.Metropolis,), scheduler=sampletimes),
+    )
+    sim = mb.Simulation(chains, algorithm_list, steps, path=str(tmp_path))
+    mb.run(sim)
+    energies = np.loadtxt(tmp_path / "energy.dat")[:, 1]
+    assert abs(energies[len(energies) // 2:].mean() - 0.25) < 5e-2
+    sig = [m.parameters.σ for m in pool]
+    assert sig[0] == 0.2
+    assert all(abs(s - 1.2) < 0.2 for s in sig[1:]), sig
+
+
+def test_driver_matches_oracle_on_gpu(tmp_path):
+    """Simulation / run! through the real engine == the stepwise oracle (same check as the CPU test double)."""
+    M, steps, burn, seed = 2048, 300, 100, 42
+    x0 = O.init_synthetic(seed, 0, M)
+    chains = mb.ParticleEnsemble(x0, 2.0, arith="exact")
+    pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.1), 1.0),)
+    sched = mb.build_schedule(steps, burn, [0, 10])
+    sim = mb.Simulation(chains, (dict(algorithm=mb.Metropolis, pool=pool, seed=seed),
+                                 dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance),
+                                      scheduler=sched),
+                                 dict(algorithm=mb.StoreTrajectories, scheduler=sched)), steps, path=str(tmp_path))
+    mb.run(sim)
+    assert chains.engine.steps_done == steps
+    ref = O.Ensemble(x0, 2.0, [0.1])
+    rows = np.loadtxt(tmp_path / "energy.dat")
+    assert rows[0, 0] == 0 and abs(rows[0, 1] / ref.callback_energy() - 1) < 1e-13
+    done = 0
+    for row, t in zip(rows[1:], sched):
+        _, z, ua = O.draws_philox(seed, 0, M, done, t - done, with_cat=False)
+        ref.sweep_replay(None, z, ua)
+        done = t
+        assert row[0] == t and abs(row[1] / ref.callback_energy() - 1) < 1e-11
+    t, x = mb.StoreTrajectories.read_binary(str(tmp_path / "trajectories" / "rank0.bin"), M)
+    assert list(t) == [0] + sched and np.max(np.abs(x[-1] - ref.x)) < 1e-12
+    chains.sync_move_counters()
+    assert pool[0].total_calls == steps * M and pool[0].accepted_calls == int(ref.acc.sum())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes through size-independent properties
+# ---------------------------------------------------------------------------------------------------------
+def test_config2_replay_full_width():
+    """Config 2 width (M = 2^24) in replay mode on a K = 6 chunk of the Julia-like xoshiro stream: decisions,
+    counters and positions bit-identical to the oracle for ALL 2^24 chains."""
+    M, K, beta = 1 << 24, 6, 2.0
+    x0 = O.init_synthetic(42, 0, M)
+    gen = O.Ensemble(x0, beta, [0.1])
+    gen.seed_xoshiro(42)
+    _, z, ua = gen.draws_xoshiro(K)
+    ref = O.Ensemble(x0, beta, [0.1])
+    dref, _, _ = ref.sweep_replay(None, z, ua, want_decisions=True)
+    with mb.CudaEnsemble(M, beta, [0.1], arith="exact") as eng:
+        eng.set_state(x0)
+        dec = eng.sweep_replay(None, z, ua, want_decisions=True)
+        assert np.array_equal(dec, dref)
+        assert np.array_equal(eng.get_state(), ref.x)
+        assert np.array_equal(eng.chain_counters()[0][0].astype(np.int64), ref.acc[0])
+
+
+def test_config2_xoshiro_full_length_subset():
+    """Config 2 length (10^4 steps) with the reference's generator family on the device: a shard of 2^14 chains run
+    for the FULL 10^4 steps must reproduce the oracle's counters and generator states exactly, positions ≤1e-12."""
+    M, K, seed = 1 << 14, 10 ** 4, 42
+    x0 = O.init_synthetic(seed, 0, M)
+    ref = O.Ensemble(x0, 2.0, [0.1])
+    ref.seed_xoshiro(seed)
+    st0 = ref.states.copy()
+    ref.sweep_xoshiro(K)
+    with mb.CudaEnsemble(M, 2.0, [0.1], seed=seed, rng="xoshiro", arith="exact") as eng:
+        eng.set_state(x0)
+        eng.set_rng_state(st0)
+        eng.set_ziggurat_tables(*O.ziggurat_tables())
+        eng.sweep(K)
+        assert np.array_equal(eng.get_rng_state(), ref.states)
+        assert np.array_equal(eng.chain_counters()[0][0].astype(np.int64), ref.acc[0])
+        assert np.max(np.abs(eng.get_state() - ref.x)) < 1e-12
+
+
+def test_config3_full_size_properties():
+    """Config 3 (M = 2^27, callbacks every 10 steps): determinism, chunk invariance and the analytic averages at
+    full size; a random subset of chains is checked against the oracle."""
+    M, seed = 1 << 27, 42
+    with mb.CudaEnsemble(M, 2.0, [0.1], seed=seed, arith="fast") as eng:
+        eng.init_synthetic()
+        for _ in range(100):
+            eng.sweep(10, reduce=True)                            # 1000 steps = burn
+        s1 = eng.callback_sums()
+        x1 = eng.get_state()
+        assert s1[2] == M
+        assert abs(s1[0] / M - 0.25) < 3 * math.sqrt(1 / 8 / M) + 2e-4   # + residual burn-in bias at t = 1000
+    # a slice of 4096 chains from the middle of the ensemble against the oracle (1000 steps)
+    off, n = (1 << 26) + 12345, 4096
+    x0 = O.init_synthetic(seed, off, n)
+    ref = O.Ensemble(x0, 2.0, [0.1])
+    _, z, ua = O.draws_philox(seed, off, n, 0, 1000, with_cat=False)
+    ref.sweep_replay(None, z, ua)
+    assert np.max(np.abs(x1[off:off + n] - ref.x)) < 1e-12
+    # determinism + chunk invariance at full size: one launch of 1000 steps == 100 launches of 10
+    with mb.CudaEnsemble(M, 2.0, [0.1], seed=seed, arith="fast") as eng:
+        eng.init_synthetic()
+        eng.sweep(1000, reduce=True)
+        s2 = eng.callback_sums()
+        x2 = eng.get_state()
+    assert np.array_equal(x1, x2)
+    np.testing.assert_allclose(s1, s2, rtol=1e-13)
