@@ -180,9 +180,10 @@ def run_ours(args):
 
     m_local = chains_per_rank(args, world)
     K, W, S = args.steps, max(3, args.warmup), args.mc_steps
+    stream = torch.cuda.Stream(device=local_rank)      # torch owns the stream; the engine launches on it
     eng = mb.CudaEnsemble(m_local, 2.0, [0.1], [1.0], seed=42, chain_offset=rank * m_local,
-                          n_chains_total=m_local * world, arith=args.arith, device=local_rank)
-    stream = eng.torch_stream()
+                          n_chains_total=m_local * world, arith=args.arith, device=local_rank,
+                          stream=stream.cuda_stream)
     sums_host = torch.empty(3, dtype=torch.float64).pin_memory()
 
     def one_step(timed_events=None):
@@ -300,7 +301,9 @@ def run_ours(args):
                 "sample": f"2^{args.ref_log2_chains} chains x {done} store intervals of {S} MC steps in {dt:.1f} s "
                           "(oracle: C restatement of mc_sweep! with xoshiro256++/ziggurat, OpenMP over chains)"}
         print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
     eng.close()
+    del sums_host
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -28,7 +28,8 @@ struct arianna_handle {
     bool own_stream = false;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t hbm_bytes = 0;
-    int grid = 0;  // persistent grid: resident CTAs per SM x SM count
+    int grid = 0;        // persistent grid of the light kernels: 8 resident CTAs per SM x SM count
+    int grid_sweep = 0;  // persistent grid of the fused sweep: exactly one resident wave (occupancy API)
 
     int64_t M = 0;
     double *d_x = nullptr;
@@ -42,6 +43,7 @@ struct arianna_handle {
     double *d_sums = nullptr;       // [kMaxOut]
     double *d_gd = nullptr;         // [kMaxMoves][5]
     unsigned long long *d_csum = nullptr;  // [2 * kMaxMoves]
+    m64::MathTables *d_tables = nullptr;   // exp/log tables of csrc/math64.cuh
     double *d_scratch = nullptr;    // e[] staging for get_state / dfma out
     size_t scratch_bytes = 0;
 
@@ -216,6 +218,17 @@ int32_t arianna_create(const arianna_config *cfg, arianna_handle **out)
         return bail(ARIANNA_ERR_UNSUPPORTED, "arianna_create: this library is built for sm_100a (B200) only");
     // persistent-style grid: 8 resident CTAs of 256 threads per SM cover the 64-warp SM limit
     h->grid = grid_for(h, h->M, 8);
+    {
+        // one CTA wave that is fully resident: a grid-stride loop over more CTAs than fit leaves a partial last wave
+        int per_sm = 0;
+        const bool multi = cfg->n_moves > 1;
+        const size_t smem = multi ? sizeof(uint32_t) * 2 * cfg->n_moves * kBlock : 0;
+        cudaError_t e = multi
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_philox_kernel<POT_HARMONIC, ARITH_FAST, true>, kBlock, smem)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_philox_kernel<POT_HARMONIC, ARITH_FAST, false>, kBlock, smem);
+        if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }
+        h->grid_sweep = grid_for(h, h->M, per_sm);
+    }
 
     if (cfg->stream) {
         h->stream = (cudaStream_t)cfg->stream;
@@ -249,6 +262,13 @@ int32_t arianna_create(const arianna_config *cfg, arianna_handle **out)
     CU_CREATE(cudaMalloc(&h->d_gd, sizeof(double) * kMaxMoves * 5));
     CU_CREATE(cudaMemsetAsync(h->d_gd, 0, sizeof(double) * kMaxMoves * 5, h->stream));
     CU_CREATE(cudaMalloc(&h->d_csum, sizeof(unsigned long long) * 2 * kMaxMoves));
+    {
+        m64::MathTables T;
+        m64::build_math_tables(T);
+        CU_CREATE(cudaMalloc(&h->d_tables, sizeof T));
+        CU_CREATE(cudaMemcpyAsync(h->d_tables, &T, sizeof T, cudaMemcpyHostToDevice, h->stream));
+        CU_CREATE(cudaStreamSynchronize(h->stream));
+    }
 
     if (cfg->rng_mode == ARIANNA_RNG_XOSHIRO) {
         CU_CREATE(cudaMalloc(&h->d_rng, sizeof(uint64_t) * 4 * h->M));
@@ -278,7 +298,7 @@ int32_t arianna_destroy(arianna_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_x); cudaFree(h->d_acc); cudaFree(h->d_tot); cudaFree(h->d_betas); cudaFree(h->d_rng);
     cudaFree(h->d_ki); cudaFree(h->d_wi); cudaFree(h->d_fi); cudaFree(h->d_partials); cudaFree(h->d_ticket);
-    cudaFree(h->d_sums); cudaFree(h->d_gd); cudaFree(h->d_csum); cudaFree(h->d_scratch);
+    cudaFree(h->d_sums); cudaFree(h->d_gd); cudaFree(h->d_csum); cudaFree(h->d_scratch); cudaFree(h->d_tables);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -405,15 +425,16 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
         sp.sid0 = (uint64_t)(h->cfg.seed + h->cfg.chain_offset);
         sp.reduce = (want_reduce && !multi) ? 1 : 0;
         sp.partials = h->d_partials; sp.ticket = h->d_ticket; sp.sums = h->d_sums;
+        sp.tables = h->d_tables;
         sp.pool = h->pool;
         dispatch_pot(h->cfg.potential, [&](auto pot) {
             constexpr int POT = decltype(pot)::value;
             if (exact) {
-                if (multi) sweep_philox_kernel<POT, ARITH_EXACT, true><<<h->grid, kBlock, smem, h->stream>>>(sp);
-                else sweep_philox_kernel<POT, ARITH_EXACT, false><<<h->grid, kBlock, 0, h->stream>>>(sp);
+                if (multi) sweep_philox_kernel<POT, ARITH_EXACT, true><<<h->grid_sweep, kBlock, smem, h->stream>>>(sp);
+                else sweep_philox_kernel<POT, ARITH_EXACT, false><<<h->grid_sweep, kBlock, 0, h->stream>>>(sp);
             } else {
-                if (multi) sweep_philox_kernel<POT, ARITH_FAST, true><<<h->grid, kBlock, smem, h->stream>>>(sp);
-                else sweep_philox_kernel<POT, ARITH_FAST, false><<<h->grid, kBlock, 0, h->stream>>>(sp);
+                if (multi) sweep_philox_kernel<POT, ARITH_FAST, true><<<h->grid_sweep, kBlock, smem, h->stream>>>(sp);
+                else sweep_philox_kernel<POT, ARITH_FAST, false><<<h->grid_sweep, kBlock, 0, h->stream>>>(sp);
             }
             return 0;
         });
@@ -421,6 +442,7 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
         XoshiroParams xp{};
         xp.x = h->d_x; xp.acc = h->d_acc; xp.tot = h->d_tot; xp.betas = h->d_betas; xp.beta = h->cfg.beta;
         xp.M = h->M; xp.K = K; xp.rng = h->d_rng; xp.ki = h->d_ki; xp.wi = h->d_wi; xp.fi = h->d_fi;
+        xp.tables = h->d_tables;
         xp.pool = h->pool;
         dispatch_pot(h->cfg.potential, [&](auto pot) {
             constexpr int POT = decltype(pot)::value;
@@ -648,6 +670,7 @@ static int32_t pgmc_impl(arianna_handle *h, int32_t q_batch, const int32_t *lear
         pp.sigma = h->pool.sigma[k]; pp.lognorm = h->pool.lognorm[k];
         pp.z = replay ? dz + (size_t)l * q_batch * h->M : nullptr;
         pp.partials = h->d_partials; pp.ticket = h->d_ticket; pp.gd = h->d_gd + 5 * l;
+        pp.tables = h->d_tables;
         dispatch_pot(h->cfg.potential, [&](auto pot) {
             constexpr int POT = decltype(pot)::value;
             if (replay) pgmc_kernel<POT, ARITH_EXACT, true><<<h->grid, kBlock, 0, h->stream>>>(pp);

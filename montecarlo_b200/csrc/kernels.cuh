@@ -15,11 +15,23 @@
 // (src/metropolis.jl:319-321), pgmc_estimate (src/PolicyGuided/gradients.jl:93-109).
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
+#include "math64.cuh"
 #include "rng.cuh"
 
 namespace arianna {
+
+// Tuning knobs of the fused sweep (overridable for A/B builds, see scripts/ab_variants.sh):
+//   ARIANNA_MINB  resident CTAs per SM requested through __launch_bounds__ (register cap = 65536 / (256·MINB))
+//   ARIANNA_PIPE  1 = software-pipeline the Box-Muller/Philox work of pair p+1 over the two steps of pair p
+#ifndef ARIANNA_MINB
+#define ARIANNA_MINB 4
+#endif
+#ifndef ARIANNA_PIPE
+#define ARIANNA_PIPE 1
+#endif
 
 constexpr int kBlock = 256;
 constexpr int kMaxMoves = 16;
@@ -49,10 +61,18 @@ struct SweepParams {
     double *partials;       // [gridDim.x][kMaxOut]
     unsigned int *ticket;
     double *sums;           // [2 + n_moves]
+    const m64::MathTables *tables;  // exp/log tables in global memory (copied to shared by every CTA)
     PoolParams pool;
 };
 
 constexpr int kMaxOut = 2 + kMaxMoves;
+
+__device__ __forceinline__ void load_tables(m64::MathTables *dst, const m64::MathTables *src)
+{
+    const double *s = reinterpret_cast<const double *>(src);
+    double *d = reinterpret_cast<double *>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(m64::MathTables) / sizeof(double)); i += blockDim.x) d[i] = s[i];
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // potential(x)
@@ -113,25 +133,26 @@ __device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, 
 
 // FAST: symmetric proposal => log q terms cancel; α > u  <=>  exp(β(e - e')) > u  because u < 1; reject restores x.
 template <int POT>
-__device__ __forceinline__ int mc_step_fast(double &x, double &e, double beta, double sigma, double z, double u_acc)
+__device__ __forceinline__ bool mc_step_fast(double &x, double &e, double beta, double sigma, double z,
+                                             uint32_t ua_lo, uint32_t ua_hi, const double *exp2_j)
 {
-    double xn = fma(sigma, z, x);
-    double en = potential<POT, ARITH_FAST>(xn);
-    double ex = exp(beta * (e - en));
-    bool a = ex > u_acc;
+    const double xn = fma(sigma, z, x);
+    const double en = potential<POT, ARITH_FAST>(xn);
+    const bool a = m64::exp_accept(beta * (e - en), ua_lo, ua_hi, exp2_j);
     x = a ? xn : x;
     e = a ? en : e;
-    return a ? 1 : 0;
+    return a;
 }
 
+// u_acc is passed as the raw 64-bit random word (lo, hi): u = (word >> 11)·2^-53.
 template <int POT, int ARITH>
-__device__ __forceinline__ int mc_step(double &x, double &e, double beta, double sigma, double lognorm, double z,
-                                       double u_acc)
+__device__ __forceinline__ bool mc_step(double &x, double &e, double beta, double sigma, double lognorm, double z,
+                                        uint32_t ua_lo, uint32_t ua_hi, const double *exp2_j)
 {
     if constexpr (ARITH == ARITH_EXACT)
-        return mc_step_exact<POT>(x, e, beta, sigma, lognorm, z, u_acc);
+        return mc_step_exact<POT>(x, e, beta, sigma, lognorm, z, u53(ua_lo, ua_hi)) != 0;
     else
-        return mc_step_fast<POT>(x, e, beta, sigma, z, u_acc);
+        return mc_step_fast<POT>(x, e, beta, sigma, z, ua_lo, ua_hi, exp2_j);
 }
 
 // Distributions.Categorical inverse-CDF scan [EXT] (metropolis.jl:206); weights in shared memory.
@@ -146,18 +167,7 @@ __device__ __forceinline__ int categorical(int n, const double *w, double u)
     return k;
 }
 
-// Box-Muller pair: z0 = r cos(2π u2), z1 = r sin(2π u2), r = sqrt(-2 log u1).
-__device__ __forceinline__ void box_muller(uint32_t u1_lo, uint32_t u1_hi, uint32_t u2_lo, uint32_t u2_hi,
-                                           double &z0, double &z1)
-{
-    double u1 = u53_open0(u1_lo, u1_hi);
-    double u2 = u53(u2_lo, u2_hi);
-    double r = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    z0 = r * c;
-    z1 = r * s;
-}
+__device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Block reduction of NOUT doubles per thread -> partials[blockIdx.x][*]; the last block to finish folds the
@@ -224,24 +234,34 @@ __device__ __forceinline__ void block_reduce_and_finish(const double *vals, int 
 // shared memory so that the dynamically indexed counters never spill to local memory).
 // ---------------------------------------------------------------------------------------------------------
 template <int POT, int ARITH, bool MULTI>
-__global__ void __launch_bounds__(kBlock) sweep_philox_kernel(const SweepParams p)
+__global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(const SweepParams p)
 {
     extern __shared__ unsigned char smem_raw[];
     // MULTI: [n_moves][kBlock] acc, [n_moves][kBlock] tot (u32), then sigma/weight/lognorm tables
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *s_tot = s_acc + (MULTI ? p.pool.n_moves * kBlock : 0);
     __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves];
+    __shared__ m64::MathTables s_T;
     if (threadIdx.x < kMaxMoves) {
         s_sigma[threadIdx.x] = p.pool.sigma[threadIdx.x];
         s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
         s_lognorm[threadIdx.x] = p.pool.lognorm[threadIdx.x];
     }
+    load_tables(&s_T, p.tables);
     __syncthreads();
 
     const int nm = p.pool.n_moves;
     const int64_t tend = p.t0 + p.K;
     double sum_e = 0.0, sum_r = 0.0, cnt = 0.0;
     const double sigma0 = p.pool.sigma[0], lognorm0 = p.pool.lognorm[0];
+    // Steps are consumed in Box-Muller pairs (pair index = step >> 1).  A launch that starts on an odd step uses
+    // only the sine half of its first pair and one that ends on an even step only the cosine half of its last, so
+    // the result does not depend on how the steps are chunked into launches.
+    const bool lead = (p.t0 & 1) != 0;
+    const int64_t tfull = p.t0 + (lead ? 1 : 0);
+    const int npairs = (int)((tend - tfull) >> 1);
+    const bool trail = ((tend - tfull) & 1) != 0;
+    const uint64_t pair0 = (uint64_t)(p.t0 >> 1);
 
     for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
         double x = p.x[c];
@@ -258,36 +278,70 @@ __global__ void __launch_bounds__(kBlock) sweep_philox_kernel(const SweepParams 
             acc = p.acc[c];
         }
 
-        for (int64_t pr = p.t0 >> 1; 2 * pr < tend; ++pr) {
-            const U64Pair b0 = philox_block<kTagMetropolis>(sid, 4 * (uint64_t)pr + 0);
-            const U64Pair b1 = philox_block<kTagMetropolis>(sid, 4 * (uint64_t)pr + 1);
+        // draws of one pair of steps (pure function of the pair index: no dependence on the chain state)
+        struct PairDraws {
             double z0, z1;
-            box_muller(b0.b_lo, b0.b_hi, b1.b_lo, b1.b_hi, z0, z1);
-            U64Pair b2{};
-            if constexpr (MULTI) b2 = philox_block<kTagMetropolis>(sid, 4 * (uint64_t)pr + 2);
-            if (2 * pr >= p.t0) {  // uniform branch: first pair of a launch that starts on an odd step
-                const double ua = u53(b0.a_lo, b0.a_hi);
+            U64Pair b0, b1, b2;
+        };
+        auto gen_pair = [&](uint64_t pr) {
+            PairDraws d;
+            d.b0 = philox_block<kTagMetropolis>(sid, 4 * pr + 0);
+            d.b1 = philox_block<kTagMetropolis>(sid, 4 * pr + 1);
+            m64::box_muller_u64(u64_of(d.b0.b_lo, d.b0.b_hi), u64_of(d.b1.b_lo, d.b1.b_hi), &s_T, d.z0, d.z1);
+            d.b2 = U64Pair{};
+            if constexpr (MULTI) d.b2 = philox_block<kTagMetropolis>(sid, 4 * pr + 2);
+            return d;
+        };
+        // the two (state-dependent, serial) Metropolis steps of a pair; DO0 / DO1 are compile-time
+        auto do_steps = [&](const PairDraws &d, auto do0, auto do1) {
+            if constexpr (decltype(do0)::value) {
                 if constexpr (MULTI) {
-                    const int k = categorical(nm, s_weight, u53(b2.a_lo, b2.a_hi));
-                    int d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], z0, ua);
-                    s_acc[k * kBlock + threadIdx.x] += d;
+                    const int k = categorical(nm, s_weight, u53(d.b2.a_lo, d.b2.a_hi));
+                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z0, d.b0.a_lo,
+                                                       d.b0.a_hi, s_T.exp2_j);
+                    if (a) s_acc[k * kBlock + threadIdx.x] += 1;
                     s_tot[k * kBlock + threadIdx.x] += 1;
                 } else {
-                    acc += mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, z0, ua);
+                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, d.b0.a_lo, d.b0.a_hi, s_T.exp2_j))
+                        ++acc;
                 }
             }
-            if (2 * pr + 1 < tend) {  // uniform branch: last pair of a launch that ends on an even step
-                const double ua = u53(b1.a_lo, b1.a_hi);
+            if constexpr (decltype(do1)::value) {
                 if constexpr (MULTI) {
-                    const int k = categorical(nm, s_weight, u53(b2.b_lo, b2.b_hi));
-                    int d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], z1, ua);
-                    s_acc[k * kBlock + threadIdx.x] += d;
+                    const int k = categorical(nm, s_weight, u53(d.b2.b_lo, d.b2.b_hi));
+                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z1, d.b1.a_lo,
+                                                       d.b1.a_hi, s_T.exp2_j);
+                    if (a) s_acc[k * kBlock + threadIdx.x] += 1;
                     s_tot[k * kBlock + threadIdx.x] += 1;
                 } else {
-                    acc += mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, z1, ua);
+                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, d.b1.a_lo, d.b1.a_hi, s_T.exp2_j))
+                        ++acc;
                 }
             }
+        };
+        using T_ = std::true_type;
+        using F_ = std::false_type;
+        uint64_t pr = pair0;
+        if (lead) { do_steps(gen_pair(pr), F_{}, T_{}); ++pr; }
+#if ARIANNA_PIPE
+        // Software pipeline: the draws of pair p+1 are generated while the serial accept chain of pair p runs, so
+        // every warp carries two independent dependency chains (the sweep is FP64-latency bound, not issue bound).
+        if (npairs > 0) {
+            PairDraws cur = gen_pair(pr);
+#pragma unroll 1
+            for (int i = 1; i < npairs; ++i) {
+                const PairDraws nxt = gen_pair(pr + (uint64_t)i);
+                do_steps(cur, T_{}, T_{});
+                cur = nxt;
+            }
+            do_steps(cur, T_{}, T_{});
+            pr += (uint64_t)npairs;
         }
+#else
+#pragma unroll 1
+        for (int i = 0; i < npairs; ++i, ++pr) do_steps(gen_pair(pr), T_{}, T_{});
+#endif
+        if (trail) do_steps(gen_pair(pr), T_{}, F_{});
 
         p.x[c] = x;
         if constexpr (MULTI) {
@@ -417,6 +471,7 @@ struct XoshiroParams {
     const uint64_t *ki;   // ziggurat tables in global memory (copied to shared)
     const double *wi;
     const double *fi;
+    const m64::MathTables *tables;
     PoolParams pool;
 };
 
@@ -429,6 +484,8 @@ __global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroPara
     __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves];
     __shared__ uint64_t s_ki[256];
     __shared__ double s_wi[256], s_fi[256];
+    __shared__ double s_exp2[m64::kExpTab];
+    if (threadIdx.x < m64::kExpTab) s_exp2[threadIdx.x] = p.tables->exp2_j[threadIdx.x];
     if (threadIdx.x < kMaxMoves) {
         s_sigma[threadIdx.x] = p.pool.sigma[threadIdx.x];
         s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
@@ -462,15 +519,16 @@ __global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroPara
         for (int64_t s = 0; s < p.K; ++s) {
             const double uc = g.rand();  // always consumed, even when n_moves == 1 (metropolis.jl:206)
             const double zz = xoshiro_randn(g, T);
-            const double ua = g.rand();
+            const uint64_t uaw = g.next();  // rand(rng) = (next >> 11)·2^-53 [EXT]
+            const uint32_t ua_lo = (uint32_t)uaw, ua_hi = (uint32_t)(uaw >> 32);
             if constexpr (MULTI) {
                 const int k = categorical(nm, s_weight, uc);
-                int d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], zz, ua);
-                s_acc[k * kBlock + threadIdx.x] += d;
+                const bool d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], zz, ua_lo, ua_hi, s_exp2);
+                if (d) s_acc[k * kBlock + threadIdx.x] += 1;
                 s_tot[k * kBlock + threadIdx.x] += 1;
             } else {
                 (void)uc;
-                acc += mc_step<POT, ARITH>(x, e, beta, s_sigma[0], s_lognorm[0], zz, ua);
+                if (mc_step<POT, ARITH>(x, e, beta, s_sigma[0], s_lognorm[0], zz, ua_lo, ua_hi, s_exp2)) ++acc;
             }
         }
         p.x[c] = x;
@@ -577,11 +635,13 @@ struct PgmcParams {
     double *partials;
     unsigned int *ticket;
     double *gd;           // [5] accumulators of this learnable move
+    const m64::MathTables *tables;
 };
 
 template <int POT, int ARITH>
 __device__ __forceinline__ void pgmc_sample(double &x, double &e, double beta, double sigma, double lognorm,
-                                            double z, double &sj, double &sdj, double &sgf, double &sg)
+                                            double z, double &sj, double &sdj, double &sgf, double &sg,
+                                            const double *exp2_j)
 {
     if constexpr (ARITH == ARITH_EXACT) {
         double delta = __dadd_rn(0.0, __dmul_rn(sigma, z));                                    // gradients.jl:119
@@ -609,8 +669,7 @@ __device__ __forceinline__ void pgmc_sample(double &x, double &e, double beta, d
         double gf = fma(z, z, -1.0) * inv_s;   // δ²/σ³ − 1/σ = (z² − 1)/σ
         double xn = x + delta;
         double en = potential<POT, ARITH_FAST>(xn);
-        double ex = exp(beta * (e - en));
-        double alpha = (ex > 1.0) ? 1.0 : ex;
+        double alpha = m64::exp_nonpos(beta * (e - en), exp2_j);   // = min(1, exp(·))
         double j = delta * delta * alpha;
         sj += j; sdj = fma(j, gf, sdj); sgf += gf; sg = fma(gf, gf, sg);
     }
@@ -619,6 +678,9 @@ __device__ __forceinline__ void pgmc_sample(double &x, double &e, double beta, d
 template <int POT, int ARITH, bool REPLAY>
 __global__ void __launch_bounds__(kBlock) pgmc_kernel(const PgmcParams p)
 {
+    __shared__ m64::MathTables s_T;
+    load_tables(&s_T, p.tables);
+    __syncthreads();
     double sj = 0.0, sdj = 0.0, sgf = 0.0, sg = 0.0, sn = 0.0;
     const int64_t qend = p.q0 + p.q_batch;
     for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
@@ -628,15 +690,17 @@ __global__ void __launch_bounds__(kBlock) pgmc_kernel(const PgmcParams p)
         if constexpr (REPLAY) {
             for (int b = 0; b < p.q_batch; ++b)
                 pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, __ldcs(p.z + (size_t)b * p.M + c), sj, sdj,
-                                        sgf, sg);
+                                        sgf, sg, s_T.exp2_j);
         } else {
             const uint64_t sid = p.sid0 + (uint64_t)c;
             for (int64_t pr = p.q0 >> 1; 2 * pr < qend; ++pr) {
                 const U64Pair blk = philox_block<kTagEstimator>(sid, (uint64_t)pr);
                 double z0, z1;
-                box_muller(blk.a_lo, blk.a_hi, blk.b_lo, blk.b_hi, z0, z1);
-                if (2 * pr >= p.q0) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z0, sj, sdj, sgf, sg);
-                if (2 * pr + 1 < qend) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z1, sj, sdj, sgf, sg);
+                m64::box_muller_u64(u64_of(blk.a_lo, blk.a_hi), u64_of(blk.b_lo, blk.b_hi), &s_T, z0, z1);
+                if (2 * pr >= p.q0)
+                    pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z0, sj, sdj, sgf, sg, s_T.exp2_j);
+                if (2 * pr + 1 < qend)
+                    pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z1, sj, sdj, sgf, sg, s_T.exp2_j);
             }
         }
         sn += (double)p.q_batch;

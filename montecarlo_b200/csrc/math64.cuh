@@ -1,0 +1,351 @@
+// math64.cuh -- FP64 transcendental kernels of the sweep, written for the B200 FP64 pipe (64 DFMA/clk/SM).
+//
+// The fused sweep is FP64-pipe / issue bound (DESIGN.md "Roofline"): CUDA's libm exp/log/sincospi/sqrt cost ≈150
+// FP64 instructions per chain-step.  These replacements are specialised to what the sweep actually needs and take
+// their arguments straight from the Philox INTEGER words (no int->fp64 conversion instructions):
+//
+//   exp_core / exp_accept / exp_nonpos   exp for the accept test / PGMC α      11 FP64, 1 table load, integer range checks
+//   neg2log_u53(n)       −2·ln(n·2^-53), n ∈ [1, 2^53)  (Box-Muller radius²)   10 FP64, 3 table loads
+//   sqrt_pos(w)          √w, w > 0 normal                                       7 FP64 + 1 MUFU.RSQ64H
+//   sincos_turn53(k,…)   sin/cos(2π·k·2^-53), k ∈ [0, 2^53)                    18 FP64, integer quadrant reduction
+//
+// Accuracy target: ≤ 2 ulp (validated against long-double references on the host, tests/test_math64.py, and on
+// the device through arianna_debug_math, tests/test_gpu_math.py).  Every function is also compilable for the host
+// (ARIANNA_MATH_HOST) so the accuracy tests run without a GPU.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDA_ARCH__) || (defined(__CUDACC__) && !defined(ARIANNA_MATH_HOST))
+#define AM_DEV 1
+#define AM_FN __device__ __forceinline__
+#else
+#define AM_DEV 0
+#define AM_FN static inline
+#include <cmath>
+#include <cstring>
+#endif
+
+namespace arianna {
+namespace m64 {
+
+// ---- bit helpers ---------------------------------------------------------------------------------------
+AM_FN double hilo2double(uint32_t hi, uint32_t lo)
+{
+#if AM_DEV
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    uint64_t b = ((uint64_t)hi << 32) | lo;
+    double d;
+    std::memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+AM_FN uint32_t double2hi(double d)
+{
+#if AM_DEV
+    return (uint32_t)__double2hiint(d);
+#else
+    uint64_t b;
+    std::memcpy(&b, &d, 8);
+    return (uint32_t)(b >> 32);
+#endif
+}
+AM_FN uint32_t double2lo(double d)
+{
+#if AM_DEV
+    return (uint32_t)__double2loint(d);
+#else
+    uint64_t b;
+    std::memcpy(&b, &d, 8);
+    return (uint32_t)b;
+#endif
+}
+AM_FN double ll2double_bits(int64_t b)
+{
+#if AM_DEV
+    return __longlong_as_double(b);
+#else
+    double d;
+    std::memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+AM_FN int clz64(uint64_t v)
+{
+#if AM_DEV
+    return __clzll((long long)v);
+#else
+    return __builtin_clzll(v);
+#endif
+}
+AM_FN double fma64(double a, double b, double c)
+{
+#if AM_DEV
+    return __fma_rn(a, b, c);
+#else
+    return std::fma(a, b, c);
+#endif
+}
+// MUFU.RSQ64H: ≈22-bit reciprocal square root seed (PTX rsqrt.approx.ftz.f64).  The host emulation degrades a
+// correctly rounded value to 22 bits so that the Newton steps are exercised from a realistic seed.
+AM_FN double rsqrt_seed(double w)
+{
+#if AM_DEV
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w));
+    return y;
+#else
+    double y = 1.0 / std::sqrt(w);
+    uint64_t b;
+    std::memcpy(&b, &y, 8);
+    b &= ~((uint64_t(1) << 30) - 1);  // keep 22 mantissa bits
+    std::memcpy(&y, &b, 8);
+    return y;
+#endif
+}
+
+// ---- polynomial coefficients -----------------------------------------------------------------------------
+// On the device these live in the constant bank so that DFMA reads them as c[bank][offset] operands: a full 64-bit
+// immediate otherwise costs two UMOV/MOV issue slots per use, and the sweep is issue-bound.
+#if AM_DEV
+#define AM_CONST __constant__
+#else
+#define AM_CONST static const
+#endif
+AM_CONST double kExpK[8] = {
+    0x1.71547652b82fep+5,   // [0] 32/ln2
+    0x1.62e42fefa0000p-6,   // [1] ln2/32, top 37 bits (n·hi exact for |n| < 2^16)
+    0x1.cf79abc9e3b3ap-45,  // [2] ln2/32 − hi
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,  // [3..6] expm1 Taylor, |r| ≤ ln2/64
+    6755399441055744.0};    // [7] 1.5·2^52
+AM_CONST double kLogK[4] = {-2.0 / 7.0, 1.0 / 3.0, -0.4, -2.0 / 3.0};  // −2·log1p(r) = r(−2 + r(1 + k3 r + ½r² + k2 r³ + k1 r⁴ + k0 r⁵))
+AM_CONST double kSinK[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+                            -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};
+AM_CONST double kCosK[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+                            2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+AM_CONST double kTurnK[2] = {0x1.921fb54442d18p-51,  // 2π·2^-53
+                             6755399441055744.0};    // 1.5·2^52
+
+// ---- tables (filled on the host once, copied to shared memory by each CTA) ---------------------------------
+constexpr int kLogTab = 128;  // mantissa intervals of [√½, √2)
+constexpr int kExpTab = 32;   // 2^(j/32)
+constexpr int kETab = 64;     // −2·E·ln2 for E = 0 … −53
+constexpr uint32_t kHxBase = 0x3fe6a09eu;  // high word of √½ (fdlibm's log reduction constant)
+
+struct MathTables {
+    double log_rc[kLogTab];    // 1 / c_i (c_i: centre of mantissa interval i; exactly 1.0 for the interval holding 1)
+    double log_m2lc[kLogTab];  // −2·ln(c_i) == +2·ln(rc_i), computed from the ROUNDED rc_i
+    double e_m2ln2[kETab];     // −2·E·ln2, index −E
+    double exp2_j[kExpTab];    // 2^(j/32)
+};
+
+// Host-side table construction (long double where available).
+static inline void build_math_tables(MathTables &T)
+{
+    for (int i = 0; i < kLogTab; ++i) {
+        const uint32_t h0 = kHxBase + ((uint32_t)i << 13), h1 = h0 + (1u << 13);
+        uint64_t b0 = (uint64_t)h0 << 32, b1 = (uint64_t)h1 << 32;
+        double a, b;
+        __builtin_memcpy(&a, &b0, 8);
+        __builtin_memcpy(&b, &b1, 8);
+        double c = 0.5 * (a + b);
+        if (a <= 1.0 && 1.0 < b) c = 1.0;
+        const double rc = (double)(1.0L / (long double)c);
+        T.log_rc[i] = rc;
+        T.log_m2lc[i] = (c == 1.0) ? 0.0 : (double)(2.0L * __builtin_logl((long double)rc));
+    }
+    for (int e = 0; e < kETab; ++e) T.e_m2ln2[e] = (double)(2.0L * e * 0.693147180559945309417232121458176568L);
+    for (int j = 0; j < kExpTab; ++j) T.exp2_j[j] = (double)__builtin_exp2l((long double)j / 32.0L);
+}
+
+// ---- exp ------------------------------------------------------------------------------------------------
+// exp(x) for x ∈ [−708, 0] (also correct for small positive x): n = round(x·32/ln2) = 32m + j,
+// r = x − n·ln2/32 (|r| ≤ ln2/64), exp(x) = 2^m · 2^(j/32) · (1 + expm1(r)).  11 FP64 instructions, no range checks:
+// outside the interval the result is garbage and the CALLER must not use it (see exp_class / exp_nonpos).
+AM_FN double exp_core(double x, const double *exp2_j)
+{
+    const double nf = fma64(x, kExpK[0], kExpK[7]);
+    const int32_t n = (int32_t)double2lo(nf);
+    const double nd = nf - kExpK[7];
+    double r = fma64(nd, -kExpK[1], x);
+    r = fma64(nd, -kExpK[2], r);
+    double q = kExpK[3];
+    q = fma64(q, r, kExpK[4]);
+    q = fma64(q, r, kExpK[5]);
+    q = fma64(q, r, kExpK[6]);
+    q = fma64(q, r, 0.5);
+    const double p = r * fma64(q, r, 1.0);                  // expm1(r) = r·(1 + r·q)
+    const double t = exp2_j[n & 31];
+    const double res = fma64(t, p, t);
+    return hilo2double(double2hi(res) + ((uint32_t)(n >> 5) << 20), double2lo(res));
+}
+
+// Integer classification of x from its high word (ALU pipe instead of two FP64 compares + selects):
+//   kExpOne   x ≥ +0 finite                -> min(1, exp(x)) = 1
+//   kExpCore  x ∈ [−708, −0]               -> exp_core(x)
+//   kExpZero  x < −708, ±inf, NaN          -> 0 (underflow; NaN/inf states reject like min(1, NaN) > u does)
+enum { kExpZero = 0, kExpCore = 1, kExpOne = 2 };
+AM_FN int exp_class(double x)
+{
+    const uint32_t t = double2hi(x) - 0x7ff00000u;
+    if (t >= 0x80100000u) return kExpOne;
+    return (t - 0x00100000u) < (0x40962000u - 0x00100000u) ? kExpCore : kExpZero;
+}
+
+// min(1, exp(x)) as a value (PGMC's α).
+AM_FN double exp_nonpos(double x, const double *exp2_j)
+{
+    const int c = exp_class(x);
+    const double v = exp_core(x, exp2_j);
+    return c == kExpCore ? v : (c == kExpOne ? 1.0 : 0.0);
+}
+
+// u53 of a raw 64-bit word given as two 32-bit halves: (w >> 11)·2^-53 ∈ [0,1), exactly, without an int->fp64
+// conversion instruction (two exact DADDs on bit-assembled doubles).
+AM_FN double u53_words(uint32_t lo, uint32_t hi)
+{
+    const double dh = hilo2double(0x41E00000u, hi >> 11);                       // 2^31 + k_hi·2^-21
+    const double dl = hilo2double(0x3FE00000u, (hi << 21) | (lo >> 11));         // 2^-1 + k_lo·2^-53
+    return (dh - 2147483648.5) + dl;
+}
+
+AM_FN float ex2_approx(float y)
+{
+#if AM_DEV
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+    return r;
+#else
+    return exp2f(y);
+#endif
+}
+AM_FN float uint_as_float(uint32_t b)
+{
+#if AM_DEV
+    return __uint_as_float(b);
+#else
+    float f;
+    std::memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+// The Metropolis accept test  min(1, exp(x)) > u  with u = u53(word) ∈ [0, 1), decided EXACTLY as the FP64
+// evaluation would, but through an FP32 filter:  E ≈ exp(x) from MUFU.EX2 with a rigorous relative error bound ε,
+// u bracketed by its top 23 bits [u_lo, u_lo + 2^-23).  E(1−ε) ≥ u_hi accepts, E(1+ε) ≤ u_lo rejects; only the
+// ambiguous sliver (≈2^-19 of the steps) evaluates exp_core and the 53-bit uniform on the FP64 pipe.
+// Why: on B200 the FP64 pipe is shared with IMAD.WIDE/IMAD.HI (Philox) and is THE bound of the sweep
+// (profiles/microbench/pipes.cu); the FP32, XU (F2F, MUFU) and ALU pipes run beside it for free.
+// Error budget: a = RN32(x) (2^-24), y = a·log2e (2·2^-24), EX2 (2^-22) -> |Ê/E − 1| ≤ 2^-22 + 3·2^-24·|x|·ln2·...
+// ε = 2^-21·(1 + |a|) over-covers it by > 2.5x.
+AM_FN bool exp_accept(double x, uint32_t w_lo, uint32_t w_hi, const double *exp2_j)
+{
+    const uint32_t t = double2hi(x) - 0x7ff00000u;
+    const bool always = t >= 0x80100000u;                                   // x ≥ +0, finite
+    const bool core = (t - 0x00100000u) < (0x40962000u - 0x00100000u);      // x ∈ [−708, −0]
+    const float a = (float)x;
+    const float E = ex2_approx(a * 1.44269504f);
+    const float eps = fmaf(fabsf(a), 4.76837158e-07f, 4.76837158e-07f);      // 2^-21·(|a| + 1)
+    const float Elo = fmaf(-E, eps, E), Ehi = fmaf(E, eps, E);
+    const float ulo = uint_as_float(0x3f800000u | (w_hi >> 9)) - 1.0f;       // top 23 bits of u, exact
+    const float uhi = ulo + 1.1920929e-07f;                                  // + 2^-23, exact
+    bool acc = Elo >= uhi;
+    const bool rej = Ehi <= ulo;
+    if (!(acc || rej)) acc = exp_core(x, exp2_j) > u53_words(w_lo, w_hi);    // rare: full FP64 decision
+    return always || (core && acc);
+}
+
+// Reference decision (no filter) -- used by the accuracy tests to prove the filter never changes a decision.
+AM_FN bool exp_accept_ref(double x, uint32_t w_lo, uint32_t w_hi, const double *exp2_j)
+{
+    const int c = exp_class(x);
+    return c == kExpOne || (c == kExpCore && exp_core(x, exp2_j) > u53_words(w_lo, w_hi));
+}
+
+// ---- −2·ln(n·2^-53) --------------------------------------------------------------------------------------
+AM_FN double neg2log_u53(uint64_t n, const double *log_rc, const double *log_m2lc, const double *e_m2ln2)
+{
+    const int lz = clz64(n);                // n ∈ [1, 2^53] -> lz ∈ [10, 63]
+    const uint64_t nm = n << lz;            // bit 63 set; at most 53 significant bits
+    int E = 10 - lz;                        // n·2^-53 = (nm/2^63)·2^E
+    uint32_t hx = 0x3ff00000u | (uint32_t)((nm >> 43) & 0xfffffu);
+    const uint32_t lx = (uint32_t)(nm >> 11);
+    // fdlibm reduction to m ∈ [√½, √2): fold the mantissa's top bit into the exponent
+    hx += 0x3ff00000u - kHxBase;
+    E += (int)(hx >> 20) - 0x3ff;
+    hx = (hx & 0x000fffffu) + kHxBase;
+    const double m = hilo2double(hx, lx);
+    const int i = (int)((hx - kHxBase) >> 13);
+    const double rc = log_rc[i];
+    const double r = fma64(m, rc, -1.0);    // |r| ≤ 2^-8
+    // −2·log1p(r) = r·(−2 + r·(1 − (2/3)r + (1/2)r² − (2/5)r³ + (1/3)r⁴ − (2/7)r⁵))
+    double q = kLogK[0];
+    q = fma64(q, r, kLogK[1]);
+    q = fma64(q, r, kLogK[2]);
+    q = fma64(q, r, 0.5);
+    q = fma64(q, r, kLogK[3]);
+    q = fma64(q, r, 1.0);
+    const double t = r * fma64(q, r, -2.0);
+    return (e_m2ln2[-E] + log_m2lc[i]) + t;
+}
+
+// ---- √w, w > 0 normal ---------------------------------------------------------------------------------------
+AM_FN double sqrt_pos(double w)
+{
+    const double y = rsqrt_seed(w);
+    double g = w * y, h = 0.5 * y;
+    double r = fma64(-h, g, 0.5);
+    g = fma64(g, r, g);
+    h = fma64(h, r, h);
+    const double d = fma64(-g, g, w);
+    return fma64(d, h, g);
+}
+
+// ---- sin/cos(2π·k·2^-53) ------------------------------------------------------------------------------------
+// Quadrant reduction in the integer domain: q = round(4t) mod 4, φ = 2π(t − q/4) ∈ [−π/4, π/4); fdlibm kernels.
+AM_FN void sincos_turn53(uint64_t k, double &sn, double &cs)
+{
+    const uint64_t kk = k + (uint64_t(1) << 50);
+    const uint32_t q = (uint32_t)(kk >> 51) & 3u;
+    const int64_t rem = (int64_t)(kk & ((uint64_t(1) << 51) - 1)) - (int64_t(1) << 50);
+    const double d = ll2double_bits(0x4338000000000000LL + rem) - kTurnK[1];  // exact int -> fp64
+    const double x = d * kTurnK[0];
+    const double z = x * x;
+    double ps = kSinK[0];
+    ps = fma64(ps, z, kSinK[1]);
+    ps = fma64(ps, z, kSinK[2]);
+    ps = fma64(ps, z, kSinK[3]);
+    ps = fma64(ps, z, kSinK[4]);
+    ps = fma64(ps, z, kSinK[5]);
+    const double s = fma64(z * x, ps, x);
+    double pc = kCosK[0];
+    pc = fma64(pc, z, kCosK[1]);
+    pc = fma64(pc, z, kCosK[2]);
+    pc = fma64(pc, z, kCosK[3]);
+    pc = fma64(pc, z, kCosK[4]);
+    pc = fma64(pc, z, kCosK[5]);
+    const double c = fma64(z * z, pc, fma64(-0.5, z, 1.0));
+    // rotate by q quarter turns: (cos, sin)(φ + qπ/2)
+    const bool swap = q & 1u;
+    double cc = swap ? s : c, ss = swap ? c : s;
+    const uint32_t neg_c = ((q + 1u) >> 1) & 1u;  // q = 1, 2
+    const uint32_t neg_s = q >> 1;                // q = 2, 3
+    cs = hilo2double(double2hi(cc) ^ (neg_c << 31), double2lo(cc));
+    sn = hilo2double(double2hi(ss) ^ (neg_s << 31), double2lo(ss));
+}
+
+// Box-Muller from two raw 64-bit Philox words (B0 -> radius, B1 -> angle); same definition as the oracle:
+//   u1 = ((B0 >> 11) | 1)·2^-53 ∈ (0,1) (odd lattice: never 0 or 1, so −2 ln u1 > 0 without a special case),
+//   u2 = (B1 >> 11)·2^-53, z0 = √(−2 ln u1)·cos(2π u2), z1 = …·sin(2π u2).
+AM_FN void box_muller_u64(uint64_t B0, uint64_t B1, const MathTables *T, double &z0, double &z1)
+{
+    const double w = neg2log_u53((B0 >> 11) | 1u, T->log_rc, T->log_m2lc, T->e_m2ln2);
+    const double r = sqrt_pos(w);
+    double s, c;
+    sincos_turn53(B1 >> 11, s, c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+}  // namespace m64
+}  // namespace arianna

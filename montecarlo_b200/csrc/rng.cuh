@@ -59,13 +59,10 @@ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi)
     return u53_from_k(hi >> 11, (hi << 21) | (lo >> 11));
 }
 
-// ((w >> 11) + 1) * 2^-53 in (0,1]: the Box-Muller radius uniform (log never sees 0).
+// ((w >> 11) | 1) * 2^-53 in (0,1): the Box-Muller radius uniform on the odd lattice (log never sees 0 or 1).
 __device__ __forceinline__ double u53_open0(uint32_t lo, uint32_t hi)
 {
-    uint32_t k_hi = hi >> 11, k_lo = (hi << 21) | (lo >> 11);
-    k_lo += 1u;
-    k_hi += (k_lo == 0u);
-    return u53_from_k(k_hi, k_lo);
+    return u53_from_k(hi >> 11, ((hi << 21) | (lo >> 11)) | 1u);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -73,8 +73,8 @@ static inline void philox_block(uint64_t sid, uint64_t n, uint32_t tag, uint64_t
 }
 
 static inline double u53(uint64_t w) { return (double)(w >> 11) * 0x1.0p-53; }
-/* (0,1] variant for the Box-Muller radius so that log() never sees 0 */
-static inline double u53_open0(uint64_t w) { return (double)((w >> 11) + 1) * 0x1.0p-53; }
+/* (0,1) variant for the Box-Muller radius: odd 53-bit lattice, so log() never sees 0 and never returns 0 */
+static inline double u53_open0(uint64_t w) { return (double)((w >> 11) | 1) * 0x1.0p-53; }
 
 #define AO_TWO_PI 6.283185307179586 /* binary64 nearest of 2pi == Julia's 2π (particle_1d.jl:53) */
 

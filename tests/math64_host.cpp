@@ -1,0 +1,26 @@
+// Host build of montecarlo_b200/csrc/math64.cuh for the CPU accuracy tests (tests/test_math64.py).
+// g++ -O2 -std=c++17 -ffp-contract=off -DARIANNA_MATH_HOST -shared -fPIC
+#include "../montecarlo_b200/csrc/math64.cuh"
+
+using namespace arianna::m64;
+static MathTables T;
+static bool ready = false;
+static void init() { if (!ready) { build_math_tables(T); ready = true; } }
+
+extern "C" {
+void m64_exp(const double *x, double *out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = exp_nonpos(x[i], T.exp2_j); }
+void m64_neg2log(const uint64_t *k, double *out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = neg2log_u53(k[i], T.log_rc, T.log_m2lc, T.e_m2ln2); }
+void m64_sqrt(const double *x, double *out, long n) { for (long i = 0; i < n; ++i) out[i] = sqrt_pos(x[i]); }
+void m64_sincos(const uint64_t *k, double *s, double *c, long n) { for (long i = 0; i < n; ++i) sincos_turn53(k[i], s[i], c[i]); }
+void m64_box_muller(const uint64_t *b0, const uint64_t *b1, double *z0, double *z1, long n) { init(); for (long i = 0; i < n; ++i) box_muller_u64(b0[i], b1[i], &T, z0[i], z1[i]); }
+void m64_accept(const double *x, const uint64_t *w, unsigned char *filt, unsigned char *ref, long n)
+{
+    init();
+    for (long i = 0; i < n; ++i) {
+        filt[i] = exp_accept(x[i], (uint32_t)w[i], (uint32_t)(w[i] >> 32), T.exp2_j);
+        ref[i] = exp_accept_ref(x[i], (uint32_t)w[i], (uint32_t)(w[i] >> 32), T.exp2_j);
+    }
+}
+void m64_u53(const uint64_t *w, double *out, long n) { for (long i = 0; i < n; ++i) out[i] = u53_words((uint32_t)w[i], (uint32_t)(w[i] >> 32)); }
+void m64_tables(double *out) { init(); __builtin_memcpy(out, &T, sizeof T); }
+}
