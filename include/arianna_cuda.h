@@ -187,6 +187,13 @@ ARIANNA_API int32_t arianna_device_info(arianna_handle *h, int32_t *sm_count, in
  * FP64 roofline denominator because MEASURED_PEAKS.json holds none. */
 ARIANNA_API int32_t arianna_measure_fp64_peak(arianna_handle *h, double *flops_per_s);
 
+/* Diagnostic: evaluates the device FP64 math layer (csrc/math64.cuh) on host arrays so that tests can compare
+ * the device code paths with extended-precision references.  kind: 0 min(1,exp(a)) | 1 -2 ln(b 2^-53) | 2 sqrt(a) |
+ * 3 sin/cos(2 pi b 2^-53) -> out[2i], out[2i+1] | 4 Box-Muller(b, c) -> out[2i], out[2i+1] | 5 accept test of
+ * x = a with prefix word b and refinement word c -> out[2i] = FP32-filtered, out[2i+1] = plain FP64 decision. */
+ARIANNA_API int32_t arianna_debug_math(arianna_handle *h, int32_t kind, const double *a, const uint64_t *b,
+                                       const uint64_t *c, double *out, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,7 @@ SYMBOLS = {
     "arianna_device_info": (C.c_int32, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int64)]),
     "arianna_measure_fp64_peak": (C.c_int32, [_H, _D]),
+    "arianna_debug_math": (C.c_int32, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
 }
 
 _lib = None

@@ -773,6 +773,31 @@ int32_t arianna_device_info(arianna_handle *h, int32_t *sm_count, int32_t *cc_ma
     return ARIANNA_OK;
 }
 
+int32_t arianna_debug_math(arianna_handle *h, int32_t kind, const double *a, const uint64_t *b, const uint64_t *c,
+                           double *out, int64_t n)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, kind >= 0 && kind <= 5 && out != nullptr && n >= 0, "arianna_debug_math: bad arguments");
+    if (n == 0) return ARIANNA_OK;
+    DeviceGuard guard(h->device);
+    const int64_t nout = (kind >= 3) ? 2 * n : n;
+    const size_t bytes = sizeof(double) * (size_t)(nout + 3 * n);
+    if (!ensure_scratch(h, bytes)) return fail(h, ARIANNA_ERR_NOMEM, "arianna_debug_math: scratch allocation failed");
+    double *d_out = h->d_scratch;
+    double *d_a = d_out + nout;
+    uint64_t *d_b = reinterpret_cast<uint64_t *>(d_a + n);
+    uint64_t *d_c = d_b + n;
+    if (a) CU_TRY(h, cudaMemcpyAsync(d_a, a, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    if (b) CU_TRY(h, cudaMemcpyAsync(d_b, b, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, h->stream));
+    if (c) CU_TRY(h, cudaMemcpyAsync(d_c, c, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, h->stream));
+    debug_math_kernel<<<h->grid > 0 ? h->sm_count * 4 : 1, kBlock, 0, h->stream>>>(kind, d_a, d_b, d_c, d_out, n, h->d_tables);
+    CU_TRY(h, cudaGetLastError());
+    ++h->launches;
+    CU_TRY(h, cudaMemcpyAsync(out, d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ARIANNA_OK;
+}
+
 int32_t arianna_measure_fp64_peak(arianna_handle *h, double *flops_per_s)
 {
     if (!h) return ARIANNA_ERR_INVALID;

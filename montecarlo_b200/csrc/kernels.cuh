@@ -30,7 +30,7 @@ namespace arianna {
 #define ARIANNA_MINB 4
 #endif
 #ifndef ARIANNA_PIPE
-#define ARIANNA_PIPE 1
+#define ARIANNA_PIPE 0
 #endif
 
 constexpr int kBlock = 256;
@@ -132,27 +132,28 @@ __device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, 
 }
 
 // FAST: symmetric proposal => log q terms cancel; α > u  <=>  exp(β(e - e')) > u  because u < 1; reject restores x.
-template <int POT>
-__device__ __forceinline__ bool mc_step_fast(double &x, double &e, double beta, double sigma, double z,
-                                             uint32_t ua_lo, uint32_t ua_hi, const double *exp2_j)
+// The accept uniform arrives as (ulo, cell, exact_u): a float cell [ulo, ulo + cell) that contains u and a callable
+// producing the exact 53-bit u on demand (see m64::exp_accept).
+template <int POT, class ExactU>
+__device__ __forceinline__ bool mc_step_fast(double &x, double &e, double beta, double sigma, double z, float ulo,
+                                             float cell, ExactU exact_u, const double *exp2_j)
 {
     const double xn = fma(sigma, z, x);
     const double en = potential<POT, ARITH_FAST>(xn);
-    const bool a = m64::exp_accept(beta * (e - en), ua_lo, ua_hi, exp2_j);
+    const bool a = m64::exp_accept(beta * (e - en), ulo, cell, exact_u, exp2_j);
     x = a ? xn : x;
     e = a ? en : e;
     return a;
 }
 
-// u_acc is passed as the raw 64-bit random word (lo, hi): u = (word >> 11)·2^-53.
-template <int POT, int ARITH>
+template <int POT, int ARITH, class ExactU>
 __device__ __forceinline__ bool mc_step(double &x, double &e, double beta, double sigma, double lognorm, double z,
-                                        uint32_t ua_lo, uint32_t ua_hi, const double *exp2_j)
+                                        float ulo, float cell, ExactU exact_u, const double *exp2_j)
 {
     if constexpr (ARITH == ARITH_EXACT)
-        return mc_step_exact<POT>(x, e, beta, sigma, lognorm, z, u53(ua_lo, ua_hi)) != 0;
+        return mc_step_exact<POT>(x, e, beta, sigma, lognorm, z, exact_u()) != 0;
     else
-        return mc_step_fast<POT>(x, e, beta, sigma, z, ua_lo, ua_hi, exp2_j);
+        return mc_step_fast<POT>(x, e, beta, sigma, z, ulo, cell, exact_u, exp2_j);
 }
 
 // Distributions.Categorical inverse-CDF scan [EXT] (metropolis.jl:206); weights in shared memory.
@@ -263,31 +264,46 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
     const bool trail = ((tend - tfull) & 1) != 0;
     const uint64_t pair0 = (uint64_t)(p.t0 >> 1);
 
-    for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
-        double x = p.x[c];
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    // the next chain's state is fetched while the current chain runs its K serial steps (hides the HBM latency
+    // that would otherwise be exposed once per chain at the top of the loop)
+    double x_next = (c < p.M) ? p.x[c] : 0.0;
+    uint32_t acc_next = (!MULTI && c < p.M) ? p.acc[c] : 0u;
+    for (; c < p.M; c += stride) {
+        double x = x_next;
+        uint32_t acc = acc_next;
+        if (c + stride < p.M) {
+            x_next = p.x[c + stride];
+            if constexpr (!MULTI) acc_next = p.acc[c + stride];
+        }
         double e = potential<POT, ARITH>(x);
         const double beta = p.betas ? p.betas[c] : p.beta;
         const uint64_t sid = p.sid0 + (uint64_t)c;
-        uint32_t acc = 0;
         if constexpr (MULTI) {
             for (int k = 0; k < nm; ++k) {
                 s_acc[k * kBlock + threadIdx.x] = p.acc[(size_t)k * p.M + c];
                 s_tot[k * kBlock + threadIdx.x] = p.tot[(size_t)k * p.M + c];
             }
-        } else {
-            acc = p.acc[c];
         }
 
-        // draws of one pair of steps (pure function of the pair index: no dependence on the chain state)
+        // Draws of one pair of steps (a pure function of the pair index, independent of the chain state).
+        // ONE Philox block feeds the pair: words B0/B1 give the two 53-bit Box-Muller uniforms (top 53 bits) and,
+        // in their low 11 bits, the PREFIXES of the two accept uniforms.  The remaining 42 bits of an accept
+        // uniform come from block 4p+1 and are only generated when the FP32 filter cannot decide (lazy refinement).
         struct PairDraws {
             double z0, z1;
-            U64Pair b0, b1, b2;
+            uint32_t f0, f1;   // 11-bit prefixes of u_acc(2p), u_acc(2p+1)
+            uint64_t pr;
+            U64Pair b2;        // categorical uniforms (multi-move pools)
         };
         auto gen_pair = [&](uint64_t pr) {
             PairDraws d;
-            d.b0 = philox_block<kTagMetropolis>(sid, 4 * pr + 0);
-            d.b1 = philox_block<kTagMetropolis>(sid, 4 * pr + 1);
-            m64::box_muller_u64(u64_of(d.b0.b_lo, d.b0.b_hi), u64_of(d.b1.b_lo, d.b1.b_hi), &s_T, d.z0, d.z1);
+            const U64Pair b0 = philox_block<kTagMetropolis>(sid, 4 * pr + 0);
+            m64::box_muller_u64(u64_of(b0.a_lo, b0.a_hi), u64_of(b0.b_lo, b0.b_hi), &s_T, d.z0, d.z1);
+            d.f0 = b0.a_lo & 0x7ffu;
+            d.f1 = b0.b_lo & 0x7ffu;
+            d.pr = pr;
             d.b2 = U64Pair{};
             if constexpr (MULTI) d.b2 = philox_block<kTagMetropolis>(sid, 4 * pr + 2);
             return d;
@@ -295,26 +311,36 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         // the two (state-dependent, serial) Metropolis steps of a pair; DO0 / DO1 are compile-time
         auto do_steps = [&](const PairDraws &d, auto do0, auto do1) {
             if constexpr (decltype(do0)::value) {
+                auto exact_u = [&]() {
+                    const U64Pair r = philox_block<kTagMetropolis>(sid, 4 * d.pr + 1);
+                    return m64::u53_prefix_refine(d.f0, r.a_lo, r.a_hi);
+                };
+                const float ulo = m64::ulo_from_prefix11(d.f0);
                 if constexpr (MULTI) {
                     const int k = categorical(nm, s_weight, u53(d.b2.a_lo, d.b2.a_hi));
-                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z0, d.b0.a_lo,
-                                                       d.b0.a_hi, s_T.exp2_j);
+                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z0, ulo, 0x1p-11f,
+                                                       exact_u, s_T.exp2_j);
                     if (a) s_acc[k * kBlock + threadIdx.x] += 1;
                     s_tot[k * kBlock + threadIdx.x] += 1;
                 } else {
-                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, d.b0.a_lo, d.b0.a_hi, s_T.exp2_j))
+                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, ulo, 0x1p-11f, exact_u, s_T.exp2_j))
                         ++acc;
                 }
             }
             if constexpr (decltype(do1)::value) {
+                auto exact_u = [&]() {
+                    const U64Pair r = philox_block<kTagMetropolis>(sid, 4 * d.pr + 1);
+                    return m64::u53_prefix_refine(d.f1, r.b_lo, r.b_hi);
+                };
+                const float ulo = m64::ulo_from_prefix11(d.f1);
                 if constexpr (MULTI) {
                     const int k = categorical(nm, s_weight, u53(d.b2.b_lo, d.b2.b_hi));
-                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z1, d.b1.a_lo,
-                                                       d.b1.a_hi, s_T.exp2_j);
+                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z1, ulo, 0x1p-11f,
+                                                       exact_u, s_T.exp2_j);
                     if (a) s_acc[k * kBlock + threadIdx.x] += 1;
                     s_tot[k * kBlock + threadIdx.x] += 1;
                 } else {
-                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, d.b1.a_lo, d.b1.a_hi, s_T.exp2_j))
+                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, ulo, 0x1p-11f, exact_u, s_T.exp2_j))
                         ++acc;
                 }
             }
@@ -521,14 +547,18 @@ __global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroPara
             const double zz = xoshiro_randn(g, T);
             const uint64_t uaw = g.next();  // rand(rng) = (next >> 11)·2^-53 [EXT]
             const uint32_t ua_lo = (uint32_t)uaw, ua_hi = (uint32_t)(uaw >> 32);
+            auto exact_u = [&]() { return u53(ua_lo, ua_hi); };
+            const float ulo = m64::ulo_from_word23(ua_hi);
             if constexpr (MULTI) {
                 const int k = categorical(nm, s_weight, uc);
-                const bool d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], zz, ua_lo, ua_hi, s_exp2);
+                const bool d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], zz, ulo, 0x1p-23f, exact_u,
+                                                   s_exp2);
                 if (d) s_acc[k * kBlock + threadIdx.x] += 1;
                 s_tot[k * kBlock + threadIdx.x] += 1;
             } else {
                 (void)uc;
-                if (mc_step<POT, ARITH>(x, e, beta, s_sigma[0], s_lognorm[0], zz, ua_lo, ua_hi, s_exp2)) ++acc;
+                if (mc_step<POT, ARITH>(x, e, beta, s_sigma[0], s_lognorm[0], zz, ulo, 0x1p-23f, exact_u, s_exp2))
+                    ++acc;
             }
         }
         p.x[c] = x;
@@ -726,6 +756,33 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const double *x, double 
         if (pot == POT_HARMONIC) e[c] = potential<POT_HARMONIC, ARITH_EXACT>(v);
         else if (pot == POT_QUARTIC) e[c] = potential<POT_QUARTIC, ARITH_EXACT>(v);
         else e[c] = potential<POT_DOUBLE_WELL, ARITH_EXACT>(v);
+    }
+}
+
+// Diagnostic: evaluates the device math layer (csrc/math64.cuh) on arrays so the tests can compare the DEVICE code
+// paths (MUFU.RSQ64H seed, MUFU.EX2 filter) with long-double references.  kind: 0 exp_nonpos(x) | 1 neg2log_u53(k) |
+// 2 sqrt_pos(x) | 3 sincos_turn53(k) -> out[2i], out[2i+1] | 4 box_muller_u64(a, b) -> out[2i], out[2i+1] |
+// 5 accept test (x = a, prefix word = b, refinement word = c) -> out[2i] = filtered, out[2i+1] = reference decision
+__global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const double *a, const uint64_t *b,
+                                                            const uint64_t *cc, double *out, int64_t n,
+                                                            const m64::MathTables *tables)
+{
+    __shared__ m64::MathTables s_T;
+    load_tables(&s_T, tables);
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        if (kind == 0) out[i] = m64::exp_nonpos(a[i], s_T.exp2_j);
+        else if (kind == 1) out[i] = m64::neg2log_u53(b[i], s_T.log_rc, s_T.log_m2lc, s_T.e_m2ln2);
+        else if (kind == 2) out[i] = m64::sqrt_pos(a[i]);
+        else if (kind == 3) m64::sincos_turn53(b[i], out[2 * i], out[2 * i + 1]);
+        else if (kind == 4) m64::box_muller_u64(b[i], cc[i], &s_T, out[2 * i], out[2 * i + 1]);
+        else {
+            const uint32_t f = (uint32_t)b[i] & 0x7ffu;
+            const uint64_t r = cc[i];
+            auto exact_u = [&]() { return m64::u53_prefix_refine(f, (uint32_t)r, (uint32_t)(r >> 32)); };
+            out[2 * i] = m64::exp_accept(a[i], m64::ulo_from_prefix11(f), 0x1p-11f, exact_u, s_T.exp2_j) ? 1.0 : 0.0;
+            out[2 * i + 1] = m64::exp_accept_ref(a[i], exact_u(), s_T.exp2_j) ? 1.0 : 0.0;
+        }
     }
 }
 

@@ -230,15 +230,18 @@ AM_FN float uint_as_float(uint32_t b)
 #endif
 }
 
-// The Metropolis accept test  min(1, exp(x)) > u  with u = u53(word) ∈ [0, 1), decided EXACTLY as the FP64
-// evaluation would, but through an FP32 filter:  E ≈ exp(x) from MUFU.EX2 with a rigorous relative error bound ε,
-// u bracketed by its top 23 bits [u_lo, u_lo + 2^-23).  E(1−ε) ≥ u_hi accepts, E(1+ε) ≤ u_lo rejects; only the
-// ambiguous sliver (≈2^-19 of the steps) evaluates exp_core and the 53-bit uniform on the FP64 pipe.
+// The Metropolis accept test  min(1, exp(x)) > u,  u ∈ [0, 1), decided EXACTLY as the FP64 evaluation would, but
+// through an FP32 filter:  E ≈ exp(x) from MUFU.EX2 with a rigorous relative error bound ε, and u known only through
+// a coarse cell [u_lo, u_lo + cell) (its leading bits).  E(1−ε) ≥ u_lo + cell accepts, E(1+ε) < u_lo rejects; only the
+// ambiguous sliver evaluates exp_core and asks `exact_u()` for the full 53-bit uniform on the FP64 pipe.
 // Why: on B200 the FP64 pipe is shared with IMAD.WIDE/IMAD.HI (Philox) and is THE bound of the sweep
-// (profiles/microbench/pipes.cu); the FP32, XU (F2F, MUFU) and ALU pipes run beside it for free.
-// Error budget: a = RN32(x) (2^-24), y = a·log2e (2·2^-24), EX2 (2^-22) -> |Ê/E − 1| ≤ 2^-22 + 3·2^-24·|x|·ln2·...
+// (profiles/microbench/pipes.cu); the FP32, XU (F2F, MUFU) and ALU pipes run beside it for free.  Letting the
+// filter see only the leading bits of u is what allows the native stream to spend ONE Philox block per pair of
+// steps (lazy uniform refinement, DESIGN.md "RNG stream layout").
+// Error budget: a = RN32(x) (2^-24), y = a·log2e (2·2^-24), EX2 (2^-22) -> |Ê/E − 1| ≤ 2^-22 + 3·2^-24·|x|;
 // ε = 2^-21·(1 + |a|) over-covers it by > 2.5x.
-AM_FN bool exp_accept(double x, uint32_t w_lo, uint32_t w_hi, const double *exp2_j)
+template <class ExactU>
+AM_FN bool exp_accept(double x, float ulo, float cell, ExactU exact_u, const double *exp2_j)
 {
     const uint32_t t = double2hi(x) - 0x7ff00000u;
     const bool always = t >= 0x80100000u;                                   // x ≥ +0, finite
@@ -247,19 +250,35 @@ AM_FN bool exp_accept(double x, uint32_t w_lo, uint32_t w_hi, const double *exp2
     const float E = ex2_approx(a * 1.44269504f);
     const float eps = fmaf(fabsf(a), 4.76837158e-07f, 4.76837158e-07f);      // 2^-21·(|a| + 1)
     const float Elo = fmaf(-E, eps, E), Ehi = fmaf(E, eps, E);
-    const float ulo = uint_as_float(0x3f800000u | (w_hi >> 9)) - 1.0f;       // top 23 bits of u, exact
-    const float uhi = ulo + 1.1920929e-07f;                                  // + 2^-23, exact
+    const float uhi = ulo + cell;                                            // exact (both are short dyadics)
     bool acc = Elo >= uhi;
-    const bool rej = Ehi <= ulo;
-    if (!(acc || rej)) acc = exp_core(x, exp2_j) > u53_words(w_lo, w_hi);    // rare: full FP64 decision
+    // strict: when E underflowed to 0 in FP32 the relative bound is void, but then α < 2^-125 < any non-zero u_lo;
+    // with u_lo == 0 the comparison is false and the exact path decides (α > 0 = u accepts).
+    const bool rej = Ehi < ulo;
+    if (!(always || acc || rej)) acc = exp_core(x, exp2_j) > exact_u();      // rare: full FP64 decision
     return always || (core && acc);
 }
 
+// Filter cell from the top 23 bits of a raw 64-bit word whose u is (w >> 11)·2^-53 (XOSHIRO mode).
+AM_FN float ulo_from_word23(uint32_t w_hi) { return uint_as_float(0x3f800000u | (w_hi >> 9)) - 1.0f; }
+// Filter cell from an 11-bit prefix f: u ∈ [f·2^-11, (f+1)·2^-11) (native Philox mode).
+AM_FN float ulo_from_prefix11(uint32_t f) { return uint_as_float(0x3f800000u | (f << 12)) - 1.0f; }
+// Exact native-mode uniform: u = ((f << 42) | r)·2^-53 with r = (word >> 22) the 42 refinement bits.
+AM_FN double u53_prefix_refine(uint32_t f, uint32_t r_lo, uint32_t r_hi)
+{
+    // r = word >> 22: r_hi10 = r_hi >> 22 (10 bits), r_lo32 = (r_hi << 10) | (r_lo >> 22)
+    const uint32_t k_hi = (f << 10) | (r_hi >> 22);
+    const uint32_t k_lo = (r_hi << 10) | (r_lo >> 22);
+    const double dh = hilo2double(0x41E00000u, k_hi);
+    const double dl = hilo2double(0x3FE00000u, k_lo);
+    return (dh - 2147483648.5) + dl;
+}
+
 // Reference decision (no filter) -- used by the accuracy tests to prove the filter never changes a decision.
-AM_FN bool exp_accept_ref(double x, uint32_t w_lo, uint32_t w_hi, const double *exp2_j)
+AM_FN bool exp_accept_ref(double x, double u, const double *exp2_j)
 {
     const int c = exp_class(x);
-    return c == kExpOne || (c == kExpCore && exp_core(x, exp2_j) > u53_words(w_lo, w_hi));
+    return c == kExpOne || (c == kExpCore && exp_core(x, exp2_j) > u);
 }
 
 // ---- −2·ln(n·2^-53) --------------------------------------------------------------------------------------

@@ -283,6 +283,16 @@ class CudaEnsemble:
         self._ck(self._lib.arianna_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(hb)))
         return {"sm_count": sm.value, "cc": (ma.value, mi.value), "hbm_bytes": hb.value}
 
+    def debug_math(self, kind: int, a=None, b=None, c=None):
+        """Evaluate the device math layer on arrays (arianna_debug_math)."""
+        arrs = [None if v is None else np.ascontiguousarray(v, dtype=t)
+                for v, t in ((a, np.float64), (b, np.uint64), (c, np.uint64))]
+        n = next(v.size for v in arrs if v is not None)
+        out = np.empty(2 * n if kind >= 3 else n, dtype=np.float64)
+        self._ck(self._lib.arianna_debug_math(self._h, int(kind), _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
+                                              _ptr(out), n))
+        return out
+
     def measure_fp64_peak(self) -> float:
         v = C.c_double()
         self._ck(self._lib.arianna_measure_fp64_peak(self._h, C.byref(v)))

@@ -103,9 +103,12 @@ AO_API void ao_init_synthetic(int64_t seed, int64_t chain_offset, int64_t M, dou
 
 /* Native-mode Metropolis draws for MC steps t0 .. t0+K-1 of chains [chain_offset, chain_offset+M), written
  * as step-major [K][M] arrays so that native mode == replay of these arrays.
- *   pair p = t >> 1:  block 4p+0: A -> u_acc(2p),   B -> Box-Muller u1
- *                     block 4p+1: A -> u_acc(2p+1), B -> Box-Muller u2
- *                     block 4p+2: A -> u_cat(2p),   B -> u_cat(2p+1)      (only consumed when n_moves > 1)
+ *   pair p = t >> 1:  block 4p+0: words (A, B): A>>11 -> Box-Muller u1 (|1), B>>11 -> Box-Muller u2;
+ *                                 A & 0x7ff -> 11-bit PREFIX of u_acc(2p), B & 0x7ff -> prefix of u_acc(2p+1)
+ *                     block 4p+1: A>>22 -> 42 refinement bits of u_acc(2p), B>>22 -> of u_acc(2p+1)
+ *                                 u_acc = ((prefix << 42) | refinement) * 2^-53   (the engine only generates
+ *                                 this block when its FP32 filter cannot decide from the prefix alone)
+ *                     block 4p+2: A -> u_cat(2p), B -> u_cat(2p+1)      (only consumed when n_moves > 1)
  *   z(2p) = r cos(2π u2), z(2p+1) = r sin(2π u2).
  * u_cat may be NULL (single-move pools do not consume it in native mode). */
 AO_API void ao_draws_philox(int64_t seed, int64_t chain_offset, int64_t M, int64_t t0, int64_t K,
@@ -121,10 +124,12 @@ AO_API void ao_draws_philox(int64_t seed, int64_t chain_offset, int64_t M, int64
             philox_block(sid, 4 * p + 0, AO_TAG_METROPOLIS, &A0, &B0);
             philox_block(sid, 4 * p + 1, AO_TAG_METROPOLIS, &A1, &B1);
             double z0, z1;
-            box_muller(B0, B1, &z0, &z1);
+            box_muller(A0, B0, &z0, &z1);
             int odd = (int)(t & 1);
             z[s * M + c] = odd ? z1 : z0;
-            u_acc[s * M + c] = u53(odd ? A1 : A0);
+            uint64_t prefix = (odd ? B0 : A0) & 0x7ffu;
+            uint64_t refine = (odd ? B1 : A1) >> 22;
+            u_acc[s * M + c] = (double)((prefix << 42) | refine) * 0x1.0p-53;
             if (u_cat) {
                 uint64_t A2, B2;
                 philox_block(sid, 4 * p + 2, AO_TAG_METROPOLIS, &A2, &B2);

@@ -13,12 +13,26 @@ void m64_neg2log(const uint64_t *k, double *out, long n) { init(); for (long i =
 void m64_sqrt(const double *x, double *out, long n) { for (long i = 0; i < n; ++i) out[i] = sqrt_pos(x[i]); }
 void m64_sincos(const uint64_t *k, double *s, double *c, long n) { for (long i = 0; i < n; ++i) sincos_turn53(k[i], s[i], c[i]); }
 void m64_box_muller(const uint64_t *b0, const uint64_t *b1, double *z0, double *z1, long n) { init(); for (long i = 0; i < n; ++i) box_muller_u64(b0[i], b1[i], &T, z0[i], z1[i]); }
-void m64_accept(const double *x, const uint64_t *w, unsigned char *filt, unsigned char *ref, long n)
+// mode 0: XOSHIRO-style word (23-bit cell, u = (w >> 11) 2^-53); mode 1: native (11-bit prefix f = w & 0x7ff,
+// refinement word r given separately)
+void m64_accept(const double *x, const uint64_t *w, const uint64_t *r, int mode, unsigned char *filt,
+                unsigned char *ref, double *u_out, long n)
 {
     init();
     for (long i = 0; i < n; ++i) {
-        filt[i] = exp_accept(x[i], (uint32_t)w[i], (uint32_t)(w[i] >> 32), T.exp2_j);
-        ref[i] = exp_accept_ref(x[i], (uint32_t)w[i], (uint32_t)(w[i] >> 32), T.exp2_j);
+        const uint32_t lo = (uint32_t)w[i], hi = (uint32_t)(w[i] >> 32);
+        if (mode == 0) {
+            const double u = u53_words(lo, hi);
+            filt[i] = exp_accept(x[i], ulo_from_word23(hi), 1.1920929e-07f, [&] { return u; }, T.exp2_j);
+            ref[i] = exp_accept_ref(x[i], u, T.exp2_j);
+            u_out[i] = u;
+        } else {
+            const uint32_t f = lo & 0x7ffu;
+            const double u = u53_prefix_refine(f, (uint32_t)r[i], (uint32_t)(r[i] >> 32));
+            filt[i] = exp_accept(x[i], ulo_from_prefix11(f), 4.8828125e-04f, [&] { return u; }, T.exp2_j);
+            ref[i] = exp_accept_ref(x[i], u, T.exp2_j);
+            u_out[i] = u;
+        }
     }
 }
 void m64_u53(const uint64_t *w, double *out, long n) { for (long i = 0; i < n; ++i) out[i] = u53_words((uint32_t)w[i], (uint32_t)(w[i] >> 32)); }

@@ -1,0 +1,126 @@
+"""CPU accuracy tests of montecarlo_b200/csrc/math64.cuh (compiled for the host with -DARIANNA_MATH_HOST) against
+80-bit long-double references: the FP64 transcendentals of the fused sweep must stay within ≈2 ulp, and the FP32
+accept filter must NEVER change a Metropolis decision relative to the plain FP64 evaluation."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LD = np.longdouble
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    so = tmp_path_factory.mktemp("m64") / "libm64.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-DARIANNA_MATH_HOST", "-shared", "-fPIC",
+                           "-o", str(so), os.path.join(ROOT, "tests", "math64_host.cpp")])
+    return C.CDLL(str(so))
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def ulp_err(got, ref):
+    u = np.spacing(np.abs(ref.astype(np.float64))).astype(LD)
+    return np.abs((got.astype(LD) - ref) / u).astype(np.float64)
+
+
+def test_exp_core_accuracy(lib):
+    rng = np.random.default_rng(1)
+    x = np.concatenate([-rng.random(200000) * 2, -rng.random(200000) * 50, -rng.random(100000) * 700,
+                        [0.0, -0.0, -1e-300, -707.99, -1e-17, 3.0, 1e300]])
+    out = np.empty_like(x)
+    lib.m64_exp(P(x), P(out), C.c_long(x.size))
+    ref = np.exp(np.minimum(x, 0).astype(LD))
+    assert ulp_err(out, ref).max() <= 1.5
+    # min(1, exp(x)) classification: x > 0 -> 1, x < -708 / NaN / inf -> 0
+    y = np.array([5.0, 1e300, -709.0, -1e10, np.nan, -np.inf, np.inf])
+    o = np.empty_like(y)
+    lib.m64_exp(P(y), P(o), C.c_long(y.size))
+    assert list(o) == [1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0]
+
+
+def test_neg2log_accuracy(lib):
+    rng = np.random.default_rng(2)
+    k = np.concatenate([rng.integers(1, 2 ** 53, size=400000, dtype=np.uint64) | np.uint64(1),
+                        np.array([1, 3, 2 ** 53 - 1, 2 ** 52 + 1, 2 ** 52 - 1], dtype=np.uint64),
+                        (np.uint64(2 ** 53) - rng.integers(1, 2 ** 20, size=100000, dtype=np.uint64)) | np.uint64(1),
+                        rng.integers(1, 2 ** 20, size=100000, dtype=np.uint64) | np.uint64(1)])
+    out = np.empty(k.size)
+    lib.m64_neg2log(P(k), P(out), C.c_long(k.size))
+    ref = -2 * np.log(k.astype(LD) * LD(2) ** -53)
+    assert ulp_err(out, ref).max() <= 2.5
+    assert out.min() > 0                         # odd lattice: u1 < 1, the radius never collapses to 0
+
+
+def test_sqrt_is_correctly_rounded(lib):
+    rng = np.random.default_rng(3)
+    w = np.concatenate([rng.random(300000) * 75, 10.0 ** rng.uniform(-16, 2, size=300000)])
+    out = np.empty_like(w)
+    lib.m64_sqrt(P(w), P(out), C.c_long(w.size))
+    assert ulp_err(out, np.sqrt(w.astype(LD))).max() <= 0.5001
+
+
+def test_sincos_turn_accuracy(lib):
+    rng = np.random.default_rng(4)
+    k = np.concatenate([rng.integers(0, 2 ** 53, size=500000, dtype=np.uint64),
+                        np.array([0, 1, 2 ** 50, 2 ** 50 - 1, 2 ** 51, 2 ** 52, 2 ** 53 - 1, 3 * 2 ** 50], dtype=np.uint64)])
+    s, c = np.empty(k.size), np.empty(k.size)
+    lib.m64_sincos(P(k), P(s), P(c), C.c_long(k.size))
+    ang = (LD(2) * np.arctan(LD(1)) * 4) * (k.astype(LD) * LD(2) ** -53)
+    assert np.abs(s - np.sin(ang).astype(np.float64)).max() <= 2.3e-16
+    assert np.abs(c - np.cos(ang).astype(np.float64)).max() <= 2.3e-16
+    assert (s[-8], c[-8]) == (0.0, 1.0) and (s[-4], c[-4]) == (1.0, 0.0)      # exact at the quadrant points
+    assert np.abs(s * s + c * c - 1).max() < 5e-16
+
+
+def test_box_muller_matches_oracle_definition(lib):
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    b0 = rng.integers(0, 2 ** 64, size=100000, dtype=np.uint64)
+    b1 = rng.integers(0, 2 ** 64, size=100000, dtype=np.uint64)
+    z0, z1 = np.empty(b0.size), np.empty(b0.size)
+    lib.m64_box_muller(P(b0), P(b1), P(z0), P(z1), C.c_long(b0.size))
+    u1 = ((b0 >> np.uint64(11)) | np.uint64(1)).astype(LD) * LD(2) ** -53
+    u2 = (b1 >> np.uint64(11)).astype(LD) * LD(2) ** -53
+    r = np.sqrt(-2 * np.log(u1))
+    twopi = LD(2) * np.arctan(LD(1)) * 4
+    assert np.abs(z0 - (r * np.cos(twopi * u2)).astype(np.float64)).max() < 4e-15
+    assert np.abs(z1 - (r * np.sin(twopi * u2)).astype(np.float64)).max() < 4e-15
+    zz = np.concatenate([z0, z1])
+    assert abs(zz.mean()) < 4 / np.sqrt(zz.size) and abs(zz.std() - 1) < 4 / np.sqrt(2 * zz.size)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fp32_filter_never_changes_a_decision(lib, mode):
+    """mode 0: 23-bit cell of a 53-bit word (XOSHIRO path); mode 1: 11-bit prefix + lazy 42-bit refinement (native)."""
+    rng = np.random.default_rng(6 + mode)
+    n = 2_000_000
+    x = -rng.random(n) * rng.choice([0.01, 1.0, 3.0, 30.0, 300.0], size=n)
+    w = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+    r = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+    # adversarial half: u within 2^-18 .. 2^-40 (relative) of exp(x)
+    h = n // 2
+    tie = np.exp(x[:h]) * (1 + rng.normal(size=h) * 2.0 ** -rng.integers(18, 40, size=h))
+    k = np.clip(tie * 2.0 ** 53, 0, 2 ** 53 - 1).astype(np.uint64)
+    if mode == 0:
+        w[:h] = (k << np.uint64(11)) | (w[:h] & np.uint64(0x7ff))
+    else:
+        w[:h] = (w[:h] & ~np.uint64(0x7ff)) | (k >> np.uint64(42))
+        r[:h] = (k & np.uint64(2 ** 42 - 1)) << np.uint64(22)
+    x = np.concatenate([x, [0.0, -0.0, 1e-300, 5.0, -708.0, -709.0, -1e10, -np.inf, np.nan, 1e308, -1e-320]])
+    w = np.concatenate([w, rng.integers(0, 2 ** 64, size=11, dtype=np.uint64)])
+    r = np.concatenate([r, rng.integers(0, 2 ** 64, size=11, dtype=np.uint64)])
+    f, ref, u = np.empty(x.size, np.uint8), np.empty(x.size, np.uint8), np.empty(x.size)
+    lib.m64_accept(P(x), P(w), P(r), C.c_int(mode), P(f), P(ref), P(u), C.c_long(x.size))
+    assert np.array_equal(f, ref)
+    assert np.array_equal(u[:h], k.astype(np.float64) * 2.0 ** -53)             # bit-assembled uniform is exact
+    with np.errstate(all="ignore"):
+        truth = np.minimum(LD(1), np.exp(x.astype(LD))) > u.astype(LD)
+    # the FP64 decision itself differs from the infinitely precise one only on ulp-level ties of exp()
+    assert (truth != ref.astype(bool)).sum() <= 20
+    assert list(ref[-11:]) == [1, 1, 1, 1, 0, 0, 0, 0, 0, 1, 1]
