@@ -1,0 +1,189 @@
+# AriannaCUDA.jl -- thin Julia shim that plugs libarianna_cuda.so (include/arianna_cuda.h) in behind Arianna.jl's
+# own `Simulation` / `run!` / `Metropolis` / `StoreCallbacks` / `StoreTrajectories` / `PolicyGradientEstimator`.
+#
+# STATUS: written against the C ABI and the reference sources, NOT executed -- the build environment has no Julia
+# toolchain (SURVEY.md §7 item 9).  The Python mirror (montecarlo_b200/arianna.py) exercises the identical call
+# sequence through the identical ABI and is what the parity tests run.
+#
+# Design (SURVEY.md §8b): `CudaEnsemble <: AriannaSystem` is ONE system that *is* M device-resident chains, so
+# `chains = [ensemble]` lets the unmodified reference driver run:  Metropolis.make_step! calls
+# `mc_sweep!(ensemble, pool, rng; mc_steps)` once per step, which we overload to only COUNT pending steps; any
+# observation (energy, acceptance, trajectory, estimator) first flushes them as one fused K-step kernel launch.
+module AriannaCUDA
+
+using Arianna
+using Arianna.PolicyGuided
+using ComponentArrays
+using Libdl
+using Random
+
+export CudaEnsemble, callback_energy, callback_acceptance_cuda, flush!, device_positions
+
+const MAX_MOVES = 16
+const libarianna = Ref{String}(get(ENV, "ARIANNA_CUDA_LIB", "libarianna_cuda.so"))
+
+# mirror of `struct arianna_config` (include/arianna_cuda.h) -- field order and widths must match exactly
+struct AriannaConfig
+    struct_size::UInt32
+    device::Int32
+    n_chains::Int64
+    chain_offset::Int64
+    n_chains_total::Int64
+    seed::Int64
+    beta::Float64
+    potential::Int32
+    n_moves::Int32
+    sigma::NTuple{MAX_MOVES,Float64}
+    weight::NTuple{MAX_MOVES,Float64}
+    rng_mode::Int32
+    arith_mode::Int32
+    stream::Ptr{Cvoid}
+end
+
+struct GradientRecord            # arianna_gradient_data
+    j::Float64
+    dj::Float64
+    dlogq_forward::Float64
+    g::Float64
+    n::Float64
+end
+
+const POT = Dict(:harmonic => Int32(0), :quartic => Int32(1), :double_well => Int32(2))
+
+function check(h::Ptr{Cvoid}, rc::Int32)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:arianna_last_error, libarianna[]), Cstring, (Ptr{Cvoid},), h))
+    rc == 1 ? throw(ArgumentError(msg)) : error("libarianna_cuda error $rc: $msg")
+end
+
+"""
+    CudaEnsemble(x0, β, pool; seed=1, potential=:harmonic, arith=:fast, chain_offset=0, n_total=length(x0))
+
+M = length(x0) Metropolis chains of the `particle_1d` system resident in the HBM of the current CUDA device.
+Replaces `chains = [System(x, β) for x in x0]` (MC_harmonic_oscillator.jl:13): use `chains = [ensemble]`.
+"""
+mutable struct CudaEnsemble{T<:AbstractFloat} <: AriannaSystem
+    handle::Ptr{Cvoid}
+    M::Int
+    β::T
+    pool::Any
+    pending::Int            # Metropolis steps counted by mc_sweep! but not yet launched
+    cache_t::Int            # steps_done at which (energy, acceptance) were last reduced
+    energy::Float64
+    acceptance::Vector{Float64}
+end
+
+function CudaEnsemble(x0::Vector{Float64}, β::Float64, pool; seed::Int=1, potential::Symbol=:harmonic,
+                      arith::Symbol=:fast, chain_offset::Int=0, n_total::Int=length(x0), device::Int=-1)
+    nm = length(pool)
+    nm <= MAX_MOVES || throw(ArgumentError("at most $MAX_MOVES moves per pool"))
+    pad(v) = ntuple(k -> k <= nm ? Float64(v[k]) : 0.0, MAX_MOVES)
+    cfg = AriannaConfig(UInt32(sizeof(AriannaConfig)), Int32(device), length(x0), chain_offset, n_total, seed, β,
+                        POT[potential], Int32(nm), pad([m.parameters.σ for m in pool]), pad([m.weight for m in pool]),
+                        Int32(0), Int32(arith == :exact ? 0 : 1), C_NULL)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(C_NULL, ccall((:arianna_create, libarianna[]), Int32, (Ref{AriannaConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+    ens = CudaEnsemble{Float64}(h[], length(x0), β, pool, 0, -1, NaN, fill(NaN, nm))
+    check(ens.handle, ccall((:arianna_set_state, libarianna[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), ens.handle, x0))
+    finalizer(e -> ccall((:arianna_destroy, libarianna[]), Int32, (Ptr{Cvoid},), e.handle), ens)
+    return ens
+end
+
+# Metropolis(chains; pool) deep-copies the pool per chain and the estimator deep-copies the chains
+# (metropolis.jl:289, estimator.jl:86): a raw handle must never be duplicated.
+Base.deepcopy_internal(e::CudaEnsemble, ::IdDict) = e
+
+# --- the hot path --------------------------------------------------------------------------------------------
+# mc_sweep!(system, pool, rng; mc_steps) (metropolis.jl:203-212), exported and overloadable (src/Arianna.jl:36)
+function Arianna.mc_sweep!(ens::CudaEnsemble, pool, rng; mc_steps=1)
+    ens.pending += mc_steps
+    return nothing
+end
+
+"Launch the pending Metropolis steps as ONE fused kernel (K = steps since the last observation)."
+function flush!(ens::CudaEnsemble; reduce::Bool=false)
+    for (k, move) in enumerate(ens.pool)          # σ may have been mutated in place by learning_step! (learning.jl:33)
+        θ = Ref(Float64(move.parameters.σ))
+        lognorm = Ref(log(2π * move.parameters.σ^2) / 2)   # particle_1d.jl:53, Julia's own `log` for replay parity
+        check(ens.handle, ccall((:arianna_set_params, libarianna[]), Int32,
+                                (Ptr{Cvoid}, Int32, Ref{Float64}, Int32, Ref{Float64}), ens.handle, k - 1, θ, 1, lognorm))
+    end
+    if ens.pending > 0
+        check(ens.handle, ccall((:arianna_sweep, libarianna[]), Int32, (Ptr{Cvoid}, Int64, UInt32),
+                                ens.handle, ens.pending, reduce ? 1 : 0))
+        ens.pending = 0
+        ens.cache_t = -1
+    end
+    return nothing
+end
+
+function reduce_callbacks!(ens::CudaEnsemble)
+    flush!(ens; reduce=true)
+    t = Ref{Int64}(0)
+    check(ens.handle, ccall((:arianna_steps_done, libarianna[]), Int32, (Ptr{Cvoid}, Ref{Int64}), ens.handle, t))
+    if ens.cache_t != t[]
+        e = Ref{Float64}(0.0)
+        check(ens.handle, ccall((:arianna_callbacks, libarianna[]), Int32, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}),
+                                ens.handle, e, ens.acceptance))
+        ens.energy, ens.cache_t = e[], t[]
+    end
+    return nothing
+end
+
+# `callback_energy(simulation) = mean(system.e for system in simulation.chains)` (particle_1d.jl:68-70) keeps working
+# verbatim because `ensemble.e` IS the device-reduced mean energy of its M chains.
+function Base.getproperty(ens::CudaEnsemble, s::Symbol)
+    if s === :e
+        reduce_callbacks!(ens)
+        return getfield(ens, :energy)
+    elseif s === :x
+        return device_positions(ens)
+    end
+    return getfield(ens, s)
+end
+
+"callback_acceptance for device chains: per-move MEAN OVER CHAINS of accepted/total (metropolis.jl:319-321)."
+function callback_acceptance_cuda(simulation)
+    ens = simulation.chains[1]
+    reduce_callbacks!(ens)
+    return copy(getfield(ens, :acceptance))
+end
+
+function device_positions(ens::CudaEnsemble)
+    flush!(ens)
+    x = Vector{Float64}(undef, getfield(ens, :M))
+    check(ens.handle, ccall((:arianna_get_state, libarianna[]), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+                            ens.handle, x, C_NULL))
+    return x
+end
+
+# store_trajectory(io, system, t, fmt) (particle_1d.jl:63-66): one binary frame (t, x[M]) instead of M text files
+function Arianna.store_trajectory(io, ens::CudaEnsemble, t::Int, ::Arianna.DAT)
+    write(io, Int64(t))
+    write(io, device_positions(ens))
+    return nothing
+end
+
+# --- PGMC ----------------------------------------------------------------------------------------------------
+# make_step!(sim, ::PolicyGradientEstimator) (estimator.jl:111-134) for a simulation whose chains are device-resident:
+# one fused device pass per learnable move; the summed record comes back as GradientData with n = M·q_batch.
+function Arianna.make_step!(simulation::Simulation{<:CudaEnsemble}, algorithm::PolicyGradientEstimator)
+    ens = simulation.chains[1]
+    flush!(ens)
+    ids = Int32.(algorithm.learn_ids .- 1)
+    check(ens.handle, ccall((:arianna_pgmc_reset, libarianna[]), Int32, (Ptr{Cvoid},), ens.handle))
+    check(ens.handle, ccall((:arianna_pgmc_estimate, libarianna[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32),
+                            ens.handle, algorithm.q_batch_size, ids, length(ids)))
+    recs = Vector{GradientRecord}(undef, length(ids))
+    check(ens.handle, ccall((:arianna_pgmc_read, libarianna[]), Int32, (Ptr{Cvoid}, Ptr{GradientRecord}, Int32),
+                            ens.handle, recs, length(ids)))
+    for (k, r) in enumerate(recs)
+        gd = Arianna.PolicyGuided.GradientData(r.j, ComponentArray(σ=r.dj), ComponentArray(σ=r.dlogq_forward),
+                                               fill(r.g, 1, 1), Int(r.n))
+        algorithm.gradients_data[k] = algorithm.gradients_data[k] + gd             # estimator.jl:130
+        algorithm.objectives[k] = algorithm.gradients_data[k].j / algorithm.gradients_data[k].n
+    end
+    return nothing
+end
+
+end # module
