@@ -26,6 +26,9 @@ struct arianna_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // D2H of trajectory frames overlaps the next sweep
+    cudaEvent_t ev_snap = nullptr, ev_copy = nullptr;
+    double *d_snap = nullptr;             // device snapshot of x the copy stream reads from
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t hbm_bytes = 0;
     int grid = 0;        // persistent grid of the light kernels: 8 resident CTAs per SM x SM count
@@ -299,6 +302,10 @@ int32_t arianna_destroy(arianna_handle *h)
     cudaFree(h->d_x); cudaFree(h->d_acc); cudaFree(h->d_tot); cudaFree(h->d_betas); cudaFree(h->d_rng);
     cudaFree(h->d_ki); cudaFree(h->d_wi); cudaFree(h->d_fi); cudaFree(h->d_partials); cudaFree(h->d_ticket);
     cudaFree(h->d_sums); cudaFree(h->d_gd); cudaFree(h->d_csum); cudaFree(h->d_scratch); cudaFree(h->d_tables);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->ev_snap) cudaEventDestroy(h->ev_snap);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    cudaFree(h->d_snap);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -349,7 +356,21 @@ int32_t arianna_get_state_async(arianna_handle *h, double *x_pinned)
     if (!h) return ARIANNA_ERR_INVALID;
     REQUIRE(h, x_pinned != nullptr, "arianna_get_state_async: destination is NULL");
     DeviceGuard guard(h->device);
-    CU_TRY(h, cudaMemcpyAsync(x_pinned, h->d_x, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->copy_stream) {
+        CU_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+        CU_TRY(h, cudaMalloc(&h->d_snap, sizeof(double) * h->M));
+        CU_TRY(h, cudaEventRecord(h->ev_copy, h->copy_stream));
+    }
+    // snapshot x on the compute stream (D2D, ~0.1 ms/GiB-scale) so the next sweep can start at once, then drain the
+    // snapshot over PCIe on the copy stream; the previous frame must have left the snapshot first
+    CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+    CU_TRY(h, cudaMemcpyAsync(h->d_snap, h->d_x, sizeof(double) * h->M, cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(h, cudaEventRecord(h->ev_snap, h->stream));
+    CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
+    CU_TRY(h, cudaMemcpyAsync(x_pinned, h->d_snap, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->copy_stream));
+    CU_TRY(h, cudaEventRecord(h->ev_copy, h->copy_stream));
     return ARIANNA_OK;
 }
 
@@ -484,6 +505,7 @@ int32_t arianna_sweep_replay(arianna_handle *h, int64_t K, const double *u_cat, 
         ReplayParams rp{};
         rp.x = h->d_x; rp.acc = h->d_acc; rp.tot = h->d_tot; rp.betas = h->d_betas; rp.beta = h->cfg.beta;
         rp.M = h->M; rp.K = k; rp.u_cat = multi ? duc : nullptr; rp.z = dz; rp.u_acc = dua; rp.decisions = ddec;
+        rp.tables = h->d_tables;
         rp.pool = h->pool;
         dispatch_pot(h->cfg.potential, [&](auto pot) {
             constexpr int POT = decltype(pot)::value;
@@ -743,6 +765,7 @@ int32_t arianna_synchronize(arianna_handle *h)
     if (!h) return ARIANNA_ERR_INVALID;
     DeviceGuard guard(h->device);
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->copy_stream) CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
     return ARIANNA_OK;
 }
 

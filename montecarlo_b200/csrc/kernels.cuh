@@ -110,7 +110,7 @@ __device__ __forceinline__ double potential(double x)
 // ---------------------------------------------------------------------------------------------------------
 template <int POT>
 __device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, double sigma, double lognorm,
-                                             double z, double u_acc)
+                                             double z, double u_acc, const double *exp2_j)
 {
     double delta = __dadd_rn(0.0, __dmul_rn(sigma, z));                       // particle_1d.jl:57
     double s2 = __dmul_rn(sigma, sigma);
@@ -123,9 +123,11 @@ __device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, 
     delta = -delta;                                                           // particle_1d.jl:38
     double lqb = lqf;  // log_proposal_density of -δ: only (-δ)·(-δ) == δ·δ enters -> bitwise equal (metropolis.jl:182)
     double arg = __dsub_rn(__dadd_rn(dlogp, lqb), lqf);                       // :183, NOT simplified to dlogp
-    double ex = exp(arg);
-    double alpha = (ex > 1.0) ? 1.0 : ex;                                     // min(one(T), ·), NaN propagates
-    if (alpha > u_acc) return 1;                                              // :184 strict >
+    // α = min(one(T), exp(arg)); α > rand(rng) (:183-184, strict >, NaN rejects) -- decided exactly as the FP64
+    // evaluation of exp (≤1 ulp, like Julia's / glibc's) would, through the FP32 filter of m64::exp_accept
+    float ulo, uhi;
+    m64::ucell_from_double(u_acc, ulo, uhi);
+    if (m64::exp_accept(arg, ulo, uhi, [&]() { return u_acc; }, exp2_j)) return 1;
     x = __dadd_rn(x, delta);                                                  // :187 re-applied negated move:
     e = potential<POT, ARITH_EXACT>(x);                                       //      x = fl(fl(x+δ)-δ), not a restore
     return 0;
@@ -140,7 +142,7 @@ __device__ __forceinline__ bool mc_step_fast(double &x, double &e, double beta, 
 {
     const double xn = fma(sigma, z, x);
     const double en = potential<POT, ARITH_FAST>(xn);
-    const bool a = m64::exp_accept(beta * (e - en), ulo, cell, exact_u, exp2_j);
+    const bool a = m64::exp_accept(beta * (e - en), ulo, ulo + cell, exact_u, exp2_j);   // ulo + cell is exact
     x = a ? xn : x;
     e = a ? en : e;
     return a;
@@ -151,7 +153,7 @@ __device__ __forceinline__ bool mc_step(double &x, double &e, double beta, doubl
                                         float ulo, float cell, ExactU exact_u, const double *exp2_j)
 {
     if constexpr (ARITH == ARITH_EXACT)
-        return mc_step_exact<POT>(x, e, beta, sigma, lognorm, z, exact_u()) != 0;
+        return mc_step_exact<POT>(x, e, beta, sigma, lognorm, z, exact_u(), exp2_j) != 0;
     else
         return mc_step_fast<POT>(x, e, beta, sigma, z, ulo, cell, exact_u, exp2_j);
 }
@@ -409,6 +411,7 @@ struct ReplayParams {
     const double *z;      // [K][M]
     const double *u_acc;  // [K][M]
     uint8_t *decisions;   // [K][M] or nullptr
+    const m64::MathTables *tables;
     PoolParams pool;
 };
 
@@ -424,6 +427,8 @@ __global__ void __launch_bounds__(kBlock) sweep_replay_kernel(const ReplayParams
         s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
         s_lognorm[threadIdx.x] = p.pool.lognorm[threadIdx.x];
     }
+    __shared__ double s_exp2[m64::kExpTab];
+    if (threadIdx.x < m64::kExpTab) s_exp2[threadIdx.x] = p.tables->exp2_j[threadIdx.x];
     __syncthreads();
     const int nm = p.pool.n_moves;
     constexpr int PF = 4;
@@ -458,11 +463,11 @@ __global__ void __launch_bounds__(kBlock) sweep_replay_kernel(const ReplayParams
                     int d;
                     if constexpr (MULTI) {
                         const int k = categorical(nm, s_weight, uc[i]);
-                        d = mc_step_exact<POT>(x, e, beta, s_sigma[k], s_lognorm[k], zz[i], ua[i]);
+                        d = mc_step_exact<POT>(x, e, beta, s_sigma[k], s_lognorm[k], zz[i], ua[i], s_exp2);
                         s_acc[k * kBlock + threadIdx.x] += d;
                         s_tot[k * kBlock + threadIdx.x] += 1;
                     } else {
-                        d = mc_step_exact<POT>(x, e, beta, s_sigma[0], s_lognorm[0], zz[i], ua[i]);
+                        d = mc_step_exact<POT>(x, e, beta, s_sigma[0], s_lognorm[0], zz[i], ua[i], s_exp2);
                         acc += d;
                     }
                     if (p.decisions) __stcs(p.decisions + (size_t)(s0 + i) * p.M + c, (uint8_t)d);
@@ -780,7 +785,7 @@ __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const doub
             const uint32_t f = (uint32_t)b[i] & 0x7ffu;
             const uint64_t r = cc[i];
             auto exact_u = [&]() { return m64::u53_prefix_refine(f, (uint32_t)r, (uint32_t)(r >> 32)); };
-            out[2 * i] = m64::exp_accept(a[i], m64::ulo_from_prefix11(f), 0x1p-11f, exact_u, s_T.exp2_j) ? 1.0 : 0.0;
+            out[2 * i] = m64::exp_accept(a[i], m64::ulo_from_prefix11(f), m64::ulo_from_prefix11(f) + 0x1p-11f, exact_u, s_T.exp2_j) ? 1.0 : 0.0;
             out[2 * i + 1] = m64::exp_accept_ref(a[i], exact_u(), s_T.exp2_j) ? 1.0 : 0.0;
         }
     }

@@ -232,7 +232,7 @@ AM_FN float uint_as_float(uint32_t b)
 
 // The Metropolis accept test  min(1, exp(x)) > u,  u ∈ [0, 1), decided EXACTLY as the FP64 evaluation would, but
 // through an FP32 filter:  E ≈ exp(x) from MUFU.EX2 with a rigorous relative error bound ε, and u known only through
-// a coarse cell [u_lo, u_lo + cell) (its leading bits).  E(1−ε) ≥ u_lo + cell accepts, E(1+ε) < u_lo rejects; only the
+// a coarse float cell [u_lo, u_hi] (its leading bits).  E(1−ε) ≥ u_hi accepts, E(1+ε) < u_lo rejects; only the
 // ambiguous sliver evaluates exp_core and asks `exact_u()` for the full 53-bit uniform on the FP64 pipe.
 // Why: on B200 the FP64 pipe is shared with IMAD.WIDE/IMAD.HI (Philox) and is THE bound of the sweep
 // (profiles/microbench/pipes.cu); the FP32, XU (F2F, MUFU) and ALU pipes run beside it for free.  Letting the
@@ -241,7 +241,7 @@ AM_FN float uint_as_float(uint32_t b)
 // Error budget: a = RN32(x) (2^-24), y = a·log2e (2·2^-24), EX2 (2^-22) -> |Ê/E − 1| ≤ 2^-22 + 3·2^-24·|x|;
 // ε = 2^-21·(1 + |a|) over-covers it by > 2.5x.
 template <class ExactU>
-AM_FN bool exp_accept(double x, float ulo, float cell, ExactU exact_u, const double *exp2_j)
+AM_FN bool exp_accept(double x, float ulo, float uhi, ExactU exact_u, const double *exp2_j)
 {
     const uint32_t t = double2hi(x) - 0x7ff00000u;
     const bool always = t >= 0x80100000u;                                   // x ≥ +0, finite
@@ -250,8 +250,7 @@ AM_FN bool exp_accept(double x, float ulo, float cell, ExactU exact_u, const dou
     const float E = ex2_approx(a * 1.44269504f);
     const float eps = fmaf(fabsf(a), 4.76837158e-07f, 4.76837158e-07f);      // 2^-21·(|a| + 1)
     const float Elo = fmaf(-E, eps, E), Ehi = fmaf(E, eps, E);
-    const float uhi = ulo + cell;                                            // exact (both are short dyadics)
-    bool acc = Elo >= uhi;
+    bool acc = Elo >= uhi;                                                   // u ∈ [ulo, uhi]; the ε bound is strict
     // strict: when E underflowed to 0 in FP32 the relative bound is void, but then α < 2^-125 < any non-zero u_lo;
     // with u_lo == 0 the comparison is false and the exact path decides (α > 0 = u accepts).
     const bool rej = Ehi < ulo;
@@ -272,6 +271,20 @@ AM_FN double u53_prefix_refine(uint32_t f, uint32_t r_lo, uint32_t r_hi)
     const double dh = hilo2double(0x41E00000u, k_hi);
     const double dl = hilo2double(0x3FE00000u, k_lo);
     return (dh - 2147483648.5) + dl;
+}
+
+// Float cell of an arbitrary double u ∈ [0,1) (replay / EXACT paths): directed roundings on the XU pipe.
+AM_FN void ucell_from_double(double u, float &ulo, float &uhi)
+{
+#if AM_DEV
+    ulo = __double2float_rd(u);
+    uhi = __double2float_ru(u);
+#else
+    ulo = (float)u;
+    if ((double)ulo > u) ulo = nextafterf(ulo, -1.0f);
+    uhi = (float)u;
+    if ((double)uhi < u) uhi = nextafterf(uhi, 2.0f);
+#endif
 }
 
 // Reference decision (no filter) -- used by the accuracy tests to prove the filter never changes a decision.

@@ -21,15 +21,16 @@ void m64_accept(const double *x, const uint64_t *w, const uint64_t *r, int mode,
     init();
     for (long i = 0; i < n; ++i) {
         const uint32_t lo = (uint32_t)w[i], hi = (uint32_t)(w[i] >> 32);
-        if (mode == 0) {
+        if (mode == 0 || mode == 2) {
             const double u = u53_words(lo, hi);
-            filt[i] = exp_accept(x[i], ulo_from_word23(hi), 1.1920929e-07f, [&] { return u; }, T.exp2_j);
+            if (mode == 0) filt[i] = exp_accept(x[i], ulo_from_word23(hi), ulo_from_word23(hi) + 1.1920929e-07f, [&] { return u; }, T.exp2_j);
+            else { float a, b; ucell_from_double(u, a, b); filt[i] = exp_accept(x[i], a, b, [&] { return u; }, T.exp2_j); }
             ref[i] = exp_accept_ref(x[i], u, T.exp2_j);
             u_out[i] = u;
         } else {
             const uint32_t f = lo & 0x7ffu;
             const double u = u53_prefix_refine(f, (uint32_t)r[i], (uint32_t)(r[i] >> 32));
-            filt[i] = exp_accept(x[i], ulo_from_prefix11(f), 4.8828125e-04f, [&] { return u; }, T.exp2_j);
+            filt[i] = exp_accept(x[i], ulo_from_prefix11(f), ulo_from_prefix11(f) + 4.8828125e-04f, [&] { return u; }, T.exp2_j);
             ref[i] = exp_accept_ref(x[i], u, T.exp2_j);
             u_out[i] = u;
         }

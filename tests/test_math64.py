@@ -95,9 +95,10 @@ def test_box_muller_matches_oracle_definition(lib):
     assert abs(zz.mean()) < 4 / np.sqrt(zz.size) and abs(zz.std() - 1) < 4 / np.sqrt(2 * zz.size)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_fp32_filter_never_changes_a_decision(lib, mode):
-    """mode 0: 23-bit cell of a 53-bit word (XOSHIRO path); mode 1: 11-bit prefix + lazy 42-bit refinement (native)."""
+    """mode 0: 23-bit cell of a 53-bit word (XOSHIRO path); mode 1: 11-bit prefix + lazy 42-bit refinement (native);
+    mode 2: directed-rounding float cell of an arbitrary double u (replay / EXACT paths)."""
     rng = np.random.default_rng(6 + mode)
     n = 2_000_000
     x = -rng.random(n) * rng.choice([0.01, 1.0, 3.0, 30.0, 300.0], size=n)
@@ -107,7 +108,7 @@ def test_fp32_filter_never_changes_a_decision(lib, mode):
     h = n // 2
     tie = np.exp(x[:h]) * (1 + rng.normal(size=h) * 2.0 ** -rng.integers(18, 40, size=h))
     k = np.clip(tie * 2.0 ** 53, 0, 2 ** 53 - 1).astype(np.uint64)
-    if mode == 0:
+    if mode in (0, 2):
         w[:h] = (k << np.uint64(11)) | (w[:h] & np.uint64(0x7ff))
     else:
         w[:h] = (w[:h] & ~np.uint64(0x7ff)) | (k >> np.uint64(42))
