@@ -168,16 +168,25 @@ class ParticleEnsemble(AriannaSystem):
     CudaEnsemble).  Construct from host positions (sharded automatically when torch.distributed is initialised)
     or synthetically (x0 = 4u − 2 from the engine's counter-based stream, MC_harmonic_oscillator.jl:13)."""
 
-    def __init__(self, x0=None, beta: float = 1.0, *, n_chains: Optional[int] = None, potential: str = "harmonic",
+    def __init__(self, x0=None, beta=1.0, *, n_chains: Optional[int] = None, potential: str = "harmonic",
                  arith: str = "fast", rng: str = "philox", device: int = -1, init_seed: Optional[int] = None):
         if x0 is None and n_chains is None:
             raise ValueError("give x0 (host positions) or n_chains (synthetic initial condition)")
         if x0 is not None and not isinstance(x0, np.ndarray) and len(x0) and isinstance(x0[0], Particle):
-            beta = x0[0].β
+            betas = [p.β for p in x0]
+            beta = betas[0] if len(set(betas)) == 1 else np.array(betas)
             potential = x0[0].potential
             x0 = np.array([p.x for p in x0], dtype=np.float64)
         self.x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
         self.n_total = int(n_chains if self.x0 is None else self.x0.size)
+        # β may be one value or one value per chain (every Particle carries its own β, particle_1d.jl:11): a β sweep
+        # such as BASELINE config 5 runs as ONE ensemble / one launch
+        self.betas = None
+        if np.ndim(beta) > 0:
+            self.betas = np.ascontiguousarray(beta, dtype=np.float64)
+            if self.betas.shape != (self.n_total,):
+                raise ValueError("per-chain beta must have one entry per chain")
+            beta = float(self.betas[0])
         self.β = self.beta = float(beta)
         self.potential, self.arith, self.rng, self.device = potential, arith, rng, device
         self.init_seed = init_seed
@@ -205,6 +214,8 @@ class ParticleEnsemble(AriannaSystem):
             self.engine.set_state(self.x0[self.offset:self.offset + self.n_local])
         else:
             self.engine.init_synthetic(seed if self.init_seed is None else self.init_seed)
+        if self.betas is not None:
+            self.engine.set_betas(self.betas[self.offset:self.offset + self.n_local])
 
     def _push_params(self):
         for k, m in enumerate(self.pool):

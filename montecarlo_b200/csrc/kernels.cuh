@@ -255,7 +255,9 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
 
     const int nm = p.pool.n_moves;
     const int64_t tend = p.t0 + p.K;
-    double sum_e = 0.0, sum_r = 0.0, cnt = 0.0;
+    double sum_e = 0.0;
+    unsigned long long sum_acc = 0ull;   // Σ accepted_calls: exact in integers; every chain shares tot = tend
+    uint32_t cnt = 0;
     const double sigma0 = p.pool.sigma[0], lognorm0 = p.pool.lognorm[0];
     // Steps are consumed in Box-Muller pairs (pair index = step >> 1).  A launch that starts on an odd step uses
     // only the sine half of its first pair and one that ends on an even step only the cosine half of its last, so
@@ -380,16 +382,18 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         } else {
             p.acc[c] = acc;
             if (p.reduce) {
-                sum_e += e;                                   // callback_energy: Σ system.e
-                sum_r += (double)acc / (double)tend;           // callback_acceptance: Σ acc/tot (0/0 = NaN at t = 0)
-                cnt += 1.0;
+                sum_e += e;          // callback_energy: Σ system.e
+                sum_acc += acc;      // callback_acceptance: Σ_c acc_c/tot with tot == tend for every chain
+                ++cnt;
             }
         }
     }
 
     if constexpr (!MULTI) {
         if (p.reduce) {
-            double vals[3] = {sum_e, sum_r, cnt};
+            // Σ acc_c / tot == (Σ acc_c) / tot exactly in real arithmetic; the integer sum is exact in binary64 (< 2^53)
+            // and ONE division replaces a DDIV per chain.  0/0 = NaN at t = 0, like the reference's store_first record.
+            double vals[3] = {sum_e, (double)sum_acc / (double)tend, (double)cnt};
             block_reduce_and_finish<3>(vals, 3, p.partials, p.ticket, p.sums, false);
         }
     }

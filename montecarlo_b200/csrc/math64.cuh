@@ -295,19 +295,12 @@ AM_FN bool exp_accept_ref(double x, double u, const double *exp2_j)
 }
 
 // ---- −2·ln(n·2^-53) --------------------------------------------------------------------------------------
-AM_FN double neg2log_u53(uint64_t n, const double *log_rc, const double *log_m2lc, const double *e_m2ln2)
+// Core: u = m·2^E with m ∈ [√½, √2) given by its words (hx, lx) after fdlibm's fold; i = mantissa interval.
+AM_FN double neg2log_core(uint32_t hx_folded, uint32_t lx, int negE, const double *log_rc, const double *log_m2lc,
+                          const double *e_m2ln2)
 {
-    const int lz = clz64(n);                // n ∈ [1, 2^53] -> lz ∈ [10, 63]
-    const uint64_t nm = n << lz;            // bit 63 set; at most 53 significant bits
-    int E = 10 - lz;                        // n·2^-53 = (nm/2^63)·2^E
-    uint32_t hx = 0x3ff00000u | (uint32_t)((nm >> 43) & 0xfffffu);
-    const uint32_t lx = (uint32_t)(nm >> 11);
-    // fdlibm reduction to m ∈ [√½, √2): fold the mantissa's top bit into the exponent
-    hx += 0x3ff00000u - kHxBase;
-    E += (int)(hx >> 20) - 0x3ff;
-    hx = (hx & 0x000fffffu) + kHxBase;
-    const double m = hilo2double(hx, lx);
-    const int i = (int)((hx - kHxBase) >> 13);
+    const double m = hilo2double(hx_folded, lx);
+    const int i = (int)((hx_folded - kHxBase) >> 13);
     const double rc = log_rc[i];
     const double r = fma64(m, rc, -1.0);    // |r| ≤ 2^-8
     // −2·log1p(r) = r·(−2 + r·(1 − (2/3)r + (1/2)r² − (2/5)r³ + (1/3)r⁴ − (2/7)r⁵))
@@ -318,7 +311,35 @@ AM_FN double neg2log_u53(uint64_t n, const double *log_rc, const double *log_m2l
     q = fma64(q, r, kLogK[3]);
     q = fma64(q, r, 1.0);
     const double t = r * fma64(q, r, -2.0);
-    return (e_m2ln2[-E] + log_m2lc[i]) + t;
+    return (e_m2ln2[negE] + log_m2lc[i]) + t;
+}
+
+// From the integer n ∈ [1, 2^53) (clz normalisation; reference formulation used by the accuracy tests).
+AM_FN double neg2log_u53(uint64_t n, const double *log_rc, const double *log_m2lc, const double *e_m2ln2)
+{
+    const int lz = clz64(n);                // lz ∈ [11, 63]
+    const uint64_t nm = n << lz;            // bit 63 set; at most 53 significant bits
+    int E = 10 - lz;                        // n·2^-53 = (nm/2^63)·2^E
+    uint32_t hx = 0x3ff00000u | (uint32_t)((nm >> 43) & 0xfffffu);
+    const uint32_t lx = (uint32_t)(nm >> 11);
+    hx += 0x3ff00000u - kHxBase;            // fdlibm: fold the mantissa's top bit into the exponent
+    E += (int)(hx >> 20) - 0x3ff;
+    hx = (hx & 0x000fffffu) + kHxBase;
+    return neg2log_core(hx, lx, -E, log_rc, log_m2lc, e_m2ln2);
+}
+
+// Same value, from the two 32-bit halves of k = n (k_hi: top 21 bits, k_lo: low 32 bits): u = k·2^-53 is first
+// assembled EXACTLY with two DADDs (no clz / 64-bit normalising shifts: the FP64 adder does the normalisation and
+// 12 ALU-pipe instructions disappear from the hot loop), then split into exponent and mantissa words.
+AM_FN double neg2log_words(uint32_t k_hi, uint32_t k_lo, const double *log_rc, const double *log_m2lc,
+                           const double *e_m2ln2)
+{
+    const double dh = hilo2double(0x41E00000u, k_hi);   // 2^31 + k_hi·2^-21
+    const double dl = hilo2double(0x3FE00000u, k_lo);   // 2^-1 + k_lo·2^-53
+    const double u = (dh - 2147483648.5) + dl;          // exact
+    const uint32_t hx = double2hi(u) + (0x3ff00000u - kHxBase);
+    const int negE = 0x3ff - (int)(hx >> 20);           // −E ∈ [0, 53]
+    return neg2log_core((hx & 0x000fffffu) + kHxBase, double2lo(u), negE, log_rc, log_m2lc, e_m2ln2);
 }
 
 // ---- √w, w > 0 normal ---------------------------------------------------------------------------------------
@@ -371,7 +392,8 @@ AM_FN void sincos_turn53(uint64_t k, double &sn, double &cs)
 //   u2 = (B1 >> 11)·2^-53, z0 = √(−2 ln u1)·cos(2π u2), z1 = …·sin(2π u2).
 AM_FN void box_muller_u64(uint64_t B0, uint64_t B1, const MathTables *T, double &z0, double &z1)
 {
-    const double w = neg2log_u53((B0 >> 11) | 1u, T->log_rc, T->log_m2lc, T->e_m2ln2);
+    const uint32_t a_lo = (uint32_t)B0, a_hi = (uint32_t)(B0 >> 32);
+    const double w = neg2log_words(a_hi >> 11, ((a_hi << 21) | (a_lo >> 11)) | 1u, T->log_rc, T->log_m2lc, T->e_m2ln2);
     const double r = sqrt_pos(w);
     double s, c;
     sincos_turn53(B1 >> 11, s, c);

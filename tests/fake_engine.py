@@ -22,6 +22,10 @@ class OracleEngine:
         self.pgmc_samples = 0
         self.gd = np.zeros((16, 5))
         self.launch_count = 0
+        self.betas = None
+
+    def set_betas(self, betas):
+        self.betas = np.ascontiguousarray(betas, dtype=np.float64)
 
     def close(self):
         pass
@@ -48,7 +52,7 @@ class OracleEngine:
         if K:
             uc, z, ua = O.draws_philox(self.seed, self.chain_offset, self.n_chains, self.steps_done, K,
                                        with_cat=self.n_moves > 1)
-            self.ens.sweep_replay(uc, z, ua)
+            self.ens.sweep_replay(uc, z, ua, betas=self.betas)
             self.steps_done += K
             self.launch_count += 1
 

@@ -461,3 +461,85 @@ def test_config3_full_size_properties():
         x2 = eng.get_state()
     assert np.array_equal(x1, x2)
     np.testing.assert_allclose(s1, s2, rtol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 5 shape: β sweep in ONE ensemble, fused K = 100 sweeps with trajectory frames
+# ---------------------------------------------------------------------------------------------------------
+def test_config5_beta_sweep_with_trajectories(tmp_path):
+    """BASELINE config 5 shrunk: β ∈ {0.5, 1, 2, 4} as per-chain β of one ensemble, StoreTrajectories on
+    build_schedule(steps, burn, 100): every β group must sample its own N(0, 1/(2β)) (3σ bars)."""
+    G = 1 << 16
+    betas = np.repeat([0.5, 1.0, 2.0, 4.0], G)
+    M, steps, burn = betas.size, 2000, 1000
+    chains = mb.ParticleEnsemble(n_chains=M, beta=betas)
+    pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.3), 1.0),)
+    sched = mb.build_schedule(steps, burn, 100)
+    sim = mb.Simulation(chains, (dict(algorithm=mb.Metropolis, pool=pool, seed=42),
+                                 dict(algorithm=mb.StoreTrajectories, scheduler=sched, store_first=False)),
+                        steps, path=str(tmp_path))
+    mb.run(sim)
+    assert chains.engine.launch_count <= len(sched) + 2          # one fused K = 100 launch per store interval
+    t, x = mb.StoreTrajectories.read_binary(str(tmp_path / "trajectories" / "rank0.bin"), M)
+    assert list(t) == sched and x.shape == (len(sched), M)
+    last = x[-1].reshape(4, G)
+    for g, b in enumerate([0.5, 1.0, 2.0, 4.0]):
+        s = 1 / math.sqrt(2 * b)
+        assert abs(last[g].mean()) < 3 * s / math.sqrt(G)
+        assert abs(last[g].std() - s) < 3 * s / math.sqrt(2 * G)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-GPU: the Simulation path under torchrun + NCCL (skipped on single-GPU boxes)
+# ---------------------------------------------------------------------------------------------------------
+_NCCL_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+rank = int(os.environ["RANK"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+import montecarlo_b200 as mb
+from montecarlo_b200 import policy_guided as PG
+M, steps = 100003, 60
+chains = mb.ParticleEnsemble(n_chains=M, beta=2.0, arith="exact")
+pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.3), 0.5),
+        mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.05), 0.5))
+sched = mb.build_schedule(steps, 10, 10)
+sim = mb.Simulation(chains, (dict(algorithm=mb.Metropolis, pool=pool, seed=7),
+                             dict(algorithm=PG.PolicyGradientEstimator, dependencies=(mb.Metropolis,),
+                                  optimisers=(PG.Static(), PG.VPG(0.05)), q_batch_size=3),
+                             dict(algorithm=PG.PolicyGradientUpdate, dependencies=(PG.PolicyGradientEstimator,),
+                                  scheduler=mb.build_schedule(steps, 10, 4)),
+                             dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance),
+                                  scheduler=sched)), steps, path={path!r})
+mb.run(sim)
+np.save(os.path.join({path!r}, f"x_rank{{rank}}.npy"), chains.x)
+if rank == 0:
+    np.save(os.path.join({path!r}, "sigma.npy"), np.array([m.parameters.σ for m in pool]))
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_two_gpu_nccl_simulation_matches_one_gpu(tmp_path):
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for n in (1, 2):
+        d = tmp_path / f"n{n}"
+        d.mkdir()
+        script = d / "worker.py"
+        script.write_text(_NCCL_WORKER.format(root=root, path=str(d)))
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                            "--master-addr", "127.0.0.1", "--master-port", str(29600 + n), str(script)],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[n] = (np.concatenate([np.load(d / f"x_rank{k}.npy") for k in range(n)]), np.load(d / "sigma.npy"),
+                   np.loadtxt(d / "energy.dat"))
+    np.testing.assert_allclose(outs[2][0], outs[1][0], rtol=0, atol=1e-12)     # per-chain results independent of sharding
+    np.testing.assert_allclose(outs[2][1], outs[1][1], rtol=1e-12)
+    np.testing.assert_allclose(outs[2][2], outs[1][2], rtol=1e-12)
+    assert outs[1][1][0] == 0.3 and outs[1][1][1] != 0.05

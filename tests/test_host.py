@@ -265,13 +265,20 @@ chains = mb.ParticleEnsemble(x0, 2.0)
 pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.3), 0.5),
         mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.05), 0.5))
 sched = mb.build_schedule(steps, 10, 10)
+from montecarlo_b200 import policy_guided as PG
 sim = mb.Simulation(chains, (dict(algorithm=mb.Metropolis, pool=pool, seed=7),
+                             dict(algorithm=PG.PolicyGradientEstimator, dependencies=(mb.Metropolis,),
+                                  optimisers=(PG.Static(), PG.VPG(0.05)), q_batch_size=3),
+                             dict(algorithm=PG.PolicyGradientUpdate, dependencies=(PG.PolicyGradientEstimator,),
+                                  scheduler=mb.build_schedule(steps, 10, 4)),
                              dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance),
                                   scheduler=sched),
+                             dict(algorithm=mb.StoreParameters, dependencies=(mb.Metropolis,), scheduler=sched),
                              dict(algorithm=mb.StoreTrajectories, scheduler=[steps], store_first=False)),
                     steps, path={path!r})
 mb.run(sim)
 np.save(os.path.join({path!r}, f"x_rank{{chains.rank}}.npy"), chains.x)
+np.save(os.path.join({path!r}, f"sigma_rank{{chains.rank}}.npy"), np.array([m.parameters.σ for m in pool]))
 dist.barrier(); dist.destroy_process_group()
 """
 
@@ -284,23 +291,35 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
              for r in range(2)]
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
-    # single-process oracle over the WHOLE ensemble
+    # single-process oracle over the WHOLE ensemble, incl. the estimator (every step) and the VPG update (every 4)
     M, steps = 101, 60
     x0 = O.init_synthetic(7, 0, M)
     ref = O.Ensemble(x0, 2.0, [0.3, 0.05], [0.5, 0.5])
     sched = A.build_schedule(steps, 10, 10)
+    upd = set(A.build_schedule(steps, 10, 4))
     rows_e = open(tmp_path / "energy.dat").read().split("\n")[:-1]
     rows_a = open(tmp_path / "acceptance.dat").read().split("\n")[:-1]
-    done = 0
-    for i, t in enumerate(sched):
-        uc, z, ua = O.draws_philox(7, 0, M, done, t - done)
+    gd, q = np.zeros(5), 0
+    obs = {}
+    for t in range(1, steps + 1):
+        uc, z, ua = O.draws_philox(7, 0, M, t - 1, 1)
         ref.sweep_replay(uc, z, ua)
-        done = t
+        gd += ref.pgmc_replay(3, [1], O.draws_pgmc_philox(7, 0, M, q, 3).reshape(1, 3, M))[0]
+        q += 3
+        if t in upd:
+            ref.sigma[1] = O.learning_step(O.OPT_VPG, 0.05, 0.0, gd[:4] / gd[4], ref.sigma[1])
+            gd[:] = 0
+        if t in sched:
+            obs[t] = (ref.callback_energy(), ref.callback_acceptance())
+    for i, t in enumerate(sched):
         te, ve = rows_e[1 + i].split(" ", 1)
-        assert int(te) == t and abs(float(ve) - ref.callback_energy()) < 1e-13
+        assert int(te) == t and abs(float(ve) - obs[t][0]) < 1e-12
         got = np.array([float(v.replace("NaN", "nan")) for v in rows_a[1 + i].split(" ", 1)[1].strip("[]").split(", ")])
-        np.testing.assert_allclose(got, ref.callback_acceptance(), rtol=1e-13, equal_nan=True)
+        np.testing.assert_allclose(got, obs[t][1], rtol=1e-12, equal_nan=True)
     # per-chain results are invariant to the sharding (global chain id keys the stream)
     x = np.concatenate([np.load(tmp_path / f"x_rank{r}.npy") for r in range(2)])
-    assert np.array_equal(x, ref.x)
+    np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-12)   # σ differs in the last bits (sum order of the all-reduce)
+    sig = [np.load(tmp_path / f"sigma_rank{r}.npy") for r in range(2)]
+    assert np.array_equal(sig[0], sig[1])                      # every rank applies the same update
+    assert sig[0][0] == 0.3 and abs(sig[0][1] - ref.sigma[1]) < 1e-12 and sig[0][1] != 0.05
     assert os.path.exists(tmp_path / "trajectories" / "rank1.bin")

@@ -55,6 +55,9 @@ def test_neg2log_accuracy(lib):
     ref = -2 * np.log(k.astype(LD) * LD(2) ** -53)
     assert ulp_err(out, ref).max() <= 2.5
     assert out.min() > 0                         # odd lattice: u1 < 1, the radius never collapses to 0
+    out2 = np.empty(k.size)
+    lib.m64_neg2log_words(P(k), P(out2), C.c_long(k.size))
+    assert np.array_equal(out, out2)             # the DADD-normalised variant is the same function, bit for bit
 
 
 def test_sqrt_is_correctly_rounded(lib):
