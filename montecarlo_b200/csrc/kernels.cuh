@@ -140,11 +140,14 @@ template <int POT, class ExactU>
 __device__ __forceinline__ bool mc_step_fast(double &x, double &e, double beta, double sigma, double z, float ulo,
                                              float cell, ExactU exact_u, const double *exp2_j)
 {
+    // e is re-derived from x (one DMUL on the idle FP64 pipe) instead of being carried through two more selects on
+    // the ALU pipe, which is the busiest pipe of the sweep
+    const double e0 = potential<POT, ARITH_FAST>(x);
     const double xn = fma(sigma, z, x);
     const double en = potential<POT, ARITH_FAST>(xn);
-    const bool a = m64::exp_accept(beta * (e - en), ulo, ulo + cell, exact_u, exp2_j);   // ulo + cell is exact
+    const bool a = m64::exp_accept(beta * (e0 - en), ulo, ulo + cell, exact_u, exp2_j);   // ulo + cell is exact
     x = a ? xn : x;
-    e = a ? en : e;
+    (void)e;  // FAST never carries e: callers that need it (the fused reduction) evaluate potential(x)
     return a;
 }
 
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         } else {
             p.acc[c] = acc;
             if (p.reduce) {
-                sum_e += e;          // callback_energy: Σ system.e
+                sum_e += potential<POT, ARITH>(x);   // callback_energy: Σ system.e, e == potential(x) always
                 sum_acc += acc;      // callback_acceptance: Σ_c acc_c/tot with tot == tend for every chain
                 ++cnt;
             }

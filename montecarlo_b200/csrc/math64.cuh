@@ -243,19 +243,23 @@ AM_FN float uint_as_float(uint32_t b)
 template <class ExactU>
 AM_FN bool exp_accept(double x, float ulo, float uhi, ExactU exact_u, const double *exp2_j)
 {
-    const uint32_t t = double2hi(x) - 0x7ff00000u;
-    const bool always = t >= 0x80100000u;                                   // x ≥ +0, finite
-    const bool core = (t - 0x00100000u) < (0x40962000u - 0x00100000u);      // x ∈ [−708, −0]
     const float a = (float)x;
     const float E = ex2_approx(a * 1.44269504f);
     const float eps = fmaf(fabsf(a), 4.76837158e-07f, 4.76837158e-07f);      // 2^-21·(|a| + 1)
     const float Elo = fmaf(-E, eps, E), Ehi = fmaf(E, eps, E);
-    bool acc = Elo >= uhi;                                                   // u ∈ [ulo, uhi]; the ε bound is strict
+    // x ≥ 0 (incl. −0 and +inf): min(1, exp(x)) = 1 > u.  Otherwise u ∈ [ulo, uhi] and the ε bound is strict.
+    bool acc = (a >= 0.0f) || (Elo >= uhi);
     // strict: when E underflowed to 0 in FP32 the relative bound is void, but then α < 2^-125 < any non-zero u_lo;
     // with u_lo == 0 the comparison is false and the exact path decides (α > 0 = u accepts).
     const bool rej = Ehi < ulo;
-    if (!(always || acc || rej)) acc = exp_core(x, exp2_j) > exact_u();      // rare: full FP64 decision
-    return always || (core && acc);
+    if (!(acc || rej)) {
+        // rare: full FP64 decision.  NaN lands here too (every FP32 comparison is false) and rejects via `core`.
+        const uint32_t t = double2hi(x) - 0x7ff00000u;
+        const bool core = (t - 0x00100000u) < (0x40962000u - 0x00100000u);  // x ∈ [−708, −0]
+        const bool tiny_pos = t >= 0x80100000u;                             // 0 ≤ x, finite (float(x) rounded to −0… never)
+        acc = tiny_pos || (core && (exp_core(x, exp2_j) > exact_u()));
+    }
+    return acc;
 }
 
 // Filter cell from the top 23 bits of a raw 64-bit word whose u is (w >> 11)·2^-53 (XOSHIRO mode).
