@@ -155,6 +155,19 @@ def workload_config(args, world):
     }
 
 
+def ncu_traffic(m_local, mc_steps):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep kernel from the committed `ncu --set full`
+    capture (profiles/traffic.json, written by scripts/summarise_profile.py); only valid for the captured shape."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if t["chains"] == m_local and t["mc_steps"] == mc_steps:
+            return {"bytes_per_launch": t["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": 24 * m_local,
+                    "source": t["source"]}
+    except Exception:
+        pass
+    return None
+
+
 def chains_per_rank(args, world):
     total = 1 << args.log2_chains
     return total if args.scaling == "weak" else total // world
@@ -281,7 +294,7 @@ def run_ours(args):
             "peak_source": "DFMA microbenchmark in this run (arianna_measure_fp64_peak; MEASURED_PEAKS.json has no "
                            "FP64 entry); nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2",
             "flops_per_chain_step": FLOPS_PER_CHAIN_STEP, "kernel_ms": kern_ms,
-            "traffic": None,
+            "traffic": ncu_traffic(m_local, S),
             "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                     "bytes_per_chain_step": BYTES_PER_CHAIN_PER_LAUNCH / S,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},

@@ -58,6 +58,14 @@ lines += ["", "## SASS opcode mix of the launch (source page, --import-source on
 for op, s in by.most_common(16):
     lines.append(f"| {op} | {100 * s / tot:.1f} | {100 * ex[op] / tex:.1f} |")
 open(os.path.join(out_dir, f"{tag}_sweep_ncu_summary.md"), "w").write("\n".join(lines) + "\n")
+import json
+def _val(name):
+    i = hdr.index(name)
+    v = float(data[0][i].replace(",", ""))
+    return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[i]]
+json.dump({"chains": 1 << 27, "mc_steps": 10, "dram_bytes_per_launch": _val("dram__bytes_read.sum") + _val("dram__bytes_write.sum"),
+           "source": f"profiles/{tag}_sweep_ncu_summary.md (ncu --set full, bench.py default shape)"},
+          open(os.path.join(out_dir, "traffic.json"), "w"))
 
 # launch list: per-kernel totals and shares
 lc = os.path.join(ROOT, "gpurun_out", "launches.csv")

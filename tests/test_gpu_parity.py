@@ -543,3 +543,40 @@ def test_two_gpu_nccl_simulation_matches_one_gpu(tmp_path):
     np.testing.assert_allclose(outs[2][1], outs[1][1], rtol=1e-12)
     np.testing.assert_allclose(outs[2][2], outs[1][2], rtol=1e-12)
     assert outs[1][1][0] == 0.3 and outs[1][1][1] != 0.05
+
+
+def test_config1_verbatim(tmp_path):
+    """BASELINE config 1 = example/particle_1d/harmonic_oscillator/MC_harmonic_oscillator.jl verbatim: β = 2, M = 10,
+    10^5 steps, burn 1000, σ = 0.1, Metropolis + StoreCallbacks energy/acceptance + StoreTrajectories + StoreLastFrames
+    on build_schedule(steps, burn, [0, 10]).  Every one of the 9 902 records must match the stepwise oracle."""
+    seed, beta, M, steps, burn = 42, 2.0, 10, 10 ** 5, 1000
+    x0 = O.init_synthetic(seed, 0, M)
+    chains = [mb.System(x, beta) for x in x0]                      # the reference's `chains` vector
+    pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.1), 1.0),)
+    sampletimes = mb.build_schedule(steps, burn, [0, 10])
+    algorithm_list = (
+        dict(algorithm=mb.Metropolis, pool=pool, seed=seed, parallel=False),
+        dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance), scheduler=sampletimes),
+        dict(algorithm=mb.StoreTrajectories, scheduler=sampletimes),
+        dict(algorithm=mb.StoreLastFrames, scheduler=[steps]),
+        dict(algorithm=mb.PrintTimeSteps, scheduler=mb.build_schedule(steps, burn, steps // 10)),
+    )
+    simulation = mb.Simulation(chains, algorithm_list, steps, path=str(tmp_path), verbose=False)
+    mb.run(simulation)
+    energies = np.loadtxt(tmp_path / "energy.dat")
+    assert energies.shape == (1 + len(sampletimes), 2) and len(sampletimes) == 9901
+    ref = O.Ensemble(x0, beta, [0.1])
+    want, done = [ref.callback_energy()], 0
+    for t in sampletimes:
+        _, z, ua = O.draws_philox(seed, 0, M, done, t - done, with_cat=False)
+        ref.sweep_replay(None, z, ua)
+        done = t
+        want.append(ref.callback_energy())
+    np.testing.assert_allclose(energies[:, 1], want, rtol=1e-10)
+    assert list(energies[:, 0]) == [0] + sampletimes
+    trj = np.loadtxt(tmp_path / "trajectories" / "10" / "trajectory.dat")
+    assert trj.shape == (1 + len(sampletimes), 2) and abs(trj[-1, 1] - ref.x[9]) < 1e-12
+    # the example's own sanity print: mean(energies) ≈ 1/(2β) (10 chains x 9 901 correlated samples: loose window)
+    assert abs(energies[1:, 1].mean() - 0.25) < 0.03
+    acc = open(tmp_path / "acceptance.dat").read().split("\n")
+    assert acc[0] == "0 [NaN]" and abs(float(acc[-2].split("[")[1][:-1]) - ref.callback_acceptance()[0]) < 1e-12
