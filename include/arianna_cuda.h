@@ -44,7 +44,8 @@ enum arianna_status {
     ARIANNA_ERR_CUDA = 2,        /* a CUDA runtime call failed; message holds cudaGetErrorString          */
     ARIANNA_ERR_NOMEM = 3,       /* device or host allocation failed                                      */
     ARIANNA_ERR_UNSUPPORTED = 4, /* valid request this build cannot serve (e.g. replay with XOSHIRO rng)  */
-    ARIANNA_ERR_NO_DEVICE = 5    /* no CUDA device: there is NO CPU fallback                              */
+    ARIANNA_ERR_NO_DEVICE = 5,   /* no CUDA device: there is NO CPU fallback                              */
+    ARIANNA_ERR_NCCL = 6         /* libnccl could not be loaded or an NCCL call failed                    */
 };
 
 /* potential(x): the script-level global of the examples (MC_harmonic_oscillator.jl:4, test/runtests). */
@@ -187,6 +188,17 @@ ARIANNA_API int32_t arianna_device_info(arianna_handle *h, int32_t *sm_count, in
 /* FP64 pipe peak of the handle's device by a dependent-chain-free DFMA microbenchmark (flop/s); used as the
  * FP64 roofline denominator because MEASURED_PEAKS.json holds none. */
 ARIANNA_API int32_t arianna_measure_fp64_peak(arianna_handle *h, double *flops_per_s);
+
+/* Multi-GPU for hosts without their own collective library (the Julia shim): one handle per rank, chains sharded
+ * by (chain_offset, n_chains, n_chains_total).  Rank 0 obtains a 128-byte NCCL unique id, the host distributes it
+ * (MPI, sockets, a file ...) and every rank calls arianna_comm_init.  libnccl.so.2 is resolved with dlopen at the
+ * first call (override with ARIANNA_NCCL_LIB), so single-GPU users never need it.  The *_global calls all-reduce
+ * the 2 + n_moves callback sums / the 5 n_learn estimator sums over NVLink on the engine's stream and return
+ * ensemble-wide values on every rank; without a communicator they equal the local calls. */
+ARIANNA_API int32_t arianna_nccl_unique_id(void *id128);
+ARIANNA_API int32_t arianna_comm_init(arianna_handle *h, const void *id128, int32_t rank, int32_t n_ranks);
+ARIANNA_API int32_t arianna_callbacks_global(arianna_handle *h, double *mean_energy, double *acc_per_move);
+ARIANNA_API int32_t arianna_pgmc_read_global(arianna_handle *h, arianna_gradient_data *out, int32_t n_learn);
 
 /* Diagnostic: evaluates the device FP64 math layer (csrc/math64.cuh) on host arrays so that tests can compare
  * the device code paths with extended-precision references.  kind: 0 min(1,exp(a)) | 1 -2 ln(b 2^-53) | 2 sqrt(a) |

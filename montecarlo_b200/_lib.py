@@ -9,7 +9,7 @@ from ._build import LIB_PATH
 
 MAX_MOVES = 16
 
-OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_NO_DEVICE = range(6)
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_NCCL = range(7)
 POT_HARMONIC, POT_QUARTIC, POT_DOUBLE_WELL = 0, 1, 2
 RNG_PHILOX, RNG_XOSHIRO = 0, 1
 ARITH_EXACT, ARITH_FAST = 0, 1
@@ -88,6 +88,10 @@ SYMBOLS = {
     "arianna_device_info": (C.c_int32, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int64)]),
     "arianna_measure_fp64_peak": (C.c_int32, [_H, _D]),
+    "arianna_nccl_unique_id": (C.c_int32, [C.c_void_p]),
+    "arianna_comm_init": (C.c_int32, [_H, C.c_void_p, C.c_int32, C.c_int32]),
+    "arianna_callbacks_global": (C.c_int32, [_H, _D, _D]),
+    "arianna_pgmc_read_global": (C.c_int32, [_H, C.POINTER(GradientData), C.c_int32]),
     "arianna_debug_math": (C.c_int32, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
 }
 

@@ -6,17 +6,58 @@
 // arianna_create fails with ARIANNA_ERR_NO_DEVICE.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include "../../include/arianna_cuda.h"
 #include "kernels.cuh"
 
 using namespace arianna;
+
+// ---- NCCL, resolved at run time (dlopen) so the library has no link-time dependency on it ------------------------
+// Only the five entry points below are used; ABI of NCCL 2.x: ncclUniqueId is a 128-byte POD passed BY VALUE,
+// ncclDouble == 8, ncclSum == 0.
+namespace nccl {
+struct UniqueId { char internal[128]; };
+using Comm = void *;
+struct Api {
+    void *lib = nullptr;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static Api g_api;
+static const char *load(std::string &err)
+{
+    if (g_api.lib) return nullptr;
+    const char *names[] = {getenv("ARIANNA_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *n : names)
+        if (n && (lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!lib) { err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return err.c_str(); }
+    Api a;
+    a.lib = lib;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(lib, "ncclAllReduce");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy || !a.GetErrorString) {
+        err = "libnccl is missing a required symbol";
+        return err.c_str();
+    }
+    g_api = a;
+    return nullptr;
+}
+}  // namespace nccl
 
 static_assert(ARIANNA_MAX_MOVES == kMaxMoves, "header / kernel pool size mismatch");
 static_assert(sizeof(arianna_gradient_data) == 5 * sizeof(double), "gradient record layout");
@@ -49,6 +90,10 @@ struct arianna_handle {
     m64::MathTables *d_tables = nullptr;   // exp/log tables of csrc/math64.cuh
     double *d_scratch = nullptr;    // e[] staging for get_state / dfma out
     size_t scratch_bytes = 0;
+
+    nccl::Comm comm = nullptr;      // optional: set by arianna_comm_init
+    int comm_rank = 0, comm_size = 1;
+    double *d_coll = nullptr;       // [kMaxMoves * 5] staging of the tiny all-reduces
 
     PoolParams pool{};
     int64_t steps_done = 0;         // MC steps done per chain == draw index base == total_calls (single move)
@@ -302,6 +347,8 @@ int32_t arianna_destroy(arianna_handle *h)
     cudaFree(h->d_x); cudaFree(h->d_acc); cudaFree(h->d_tot); cudaFree(h->d_betas); cudaFree(h->d_rng);
     cudaFree(h->d_ki); cudaFree(h->d_wi); cudaFree(h->d_fi); cudaFree(h->d_partials); cudaFree(h->d_ticket);
     cudaFree(h->d_sums); cudaFree(h->d_gd); cudaFree(h->d_csum); cudaFree(h->d_scratch); cudaFree(h->d_tables);
+    if (h->comm) { nccl::g_api.CommDestroy(h->comm); h->comm = nullptr; }
+    cudaFree(h->d_coll);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
@@ -630,6 +677,82 @@ int32_t arianna_callbacks(arianna_handle *h, double *mean_energy, double *acc_pe
     if (acc_per_move)
         for (int k = 0; k < nm; ++k) acc_per_move[k] = sums[1 + k] / cnt;
     return ARIANNA_OK;
+}
+
+// ---- multi-GPU without a Python host: NCCL all-reduce of the tiny sum vectors inside the library ------------------
+#define NCCL_TRY(h, expr)                                                                                     \
+    do {                                                                                                      \
+        int _r = (expr);                                                                                      \
+        if (_r != 0) return fail((h), ARIANNA_ERR_NCCL, std::string(#expr) + ": " + nccl::g_api.GetErrorString(_r)); \
+    } while (0)
+
+int32_t arianna_nccl_unique_id(void *id128)
+{
+    if (!id128) return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_nccl_unique_id: NULL output");
+    std::string err;
+    if (nccl::load(err)) return fail(nullptr, ARIANNA_ERR_NCCL, err);
+    nccl::UniqueId id;
+    int r = nccl::g_api.GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, ARIANNA_ERR_NCCL, std::string("ncclGetUniqueId: ") + nccl::g_api.GetErrorString(r));
+    std::memcpy(id128, &id, sizeof id);
+    return ARIANNA_OK;
+}
+
+int32_t arianna_comm_init(arianna_handle *h, const void *id128, int32_t rank, int32_t n_ranks)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, id128 != nullptr && n_ranks >= 1 && rank >= 0 && rank < n_ranks, "arianna_comm_init: bad arguments");
+    REQUIRE(h, h->comm == nullptr, "arianna_comm_init: communicator already initialised");
+    std::string err;
+    if (nccl::load(err)) return fail(h, ARIANNA_ERR_NCCL, err);
+    DeviceGuard guard(h->device);
+    nccl::UniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    NCCL_TRY(h, nccl::g_api.CommInitRank(&h->comm, n_ranks, id, rank));
+    h->comm_rank = rank;
+    h->comm_size = n_ranks;
+    if (!h->d_coll) CU_TRY(h, cudaMalloc(&h->d_coll, sizeof(double) * kMaxMoves * 5));
+    return ARIANNA_OK;
+}
+
+static int32_t allreduce_small(arianna_handle *h, const double *d_src, int n, double *host_out)
+{
+    CU_TRY(h, cudaMemcpyAsync(h->d_coll, d_src, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->comm)
+        NCCL_TRY(h, nccl::g_api.AllReduce(h->d_coll, h->d_coll, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->comm, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(host_out, h->d_coll, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_callbacks_global(arianna_handle *h, double *mean_energy, double *acc_per_move)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (!h->d_coll) CU_TRY(h, cudaMalloc(&h->d_coll, sizeof(double) * kMaxMoves * 5));
+    double *d = nullptr;
+    int32_t n = 0;
+    int32_t rc = arianna_callback_sums_device(h, &d, &n);
+    if (rc) return rc;
+    double sums[kMaxOut];
+    rc = allreduce_small(h, d, n, sums);
+    if (rc) return rc;
+    const int nm = h->pool.n_moves;
+    const double cnt = sums[1 + nm];
+    if (mean_energy) *mean_energy = sums[0] / cnt;
+    if (acc_per_move)
+        for (int k = 0; k < nm; ++k) acc_per_move[k] = sums[1 + k] / cnt;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_pgmc_read_global(arianna_handle *h, arianna_gradient_data *out, int32_t n_learn)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, out != nullptr && n_learn >= 0 && n_learn <= kMaxMoves, "arianna_pgmc_read_global: bad arguments");
+    if (n_learn == 0) return ARIANNA_OK;
+    DeviceGuard guard(h->device);
+    if (!h->d_coll) CU_TRY(h, cudaMalloc(&h->d_coll, sizeof(double) * kMaxMoves * 5));
+    return allreduce_small(h, h->d_gd, 5 * n_learn, reinterpret_cast<double *>(out));
 }
 
 int32_t arianna_get_counters(arianna_handle *h, int64_t *accepted, int64_t *total)

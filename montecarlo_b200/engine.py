@@ -251,6 +251,28 @@ class CudaEnsemble:
         self._ck(self._lib.arianna_pgmc_sums_device(self._h, C.byref(p), C.byref(n)))
         return torch.as_tensor(_DeviceBuffer(p.value, n.value, self.stream_ptr), device="cuda")
 
+    # -- NCCL inside the library (hosts without torch.distributed) -------------------------------------------
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        L.check(None, L.load().arianna_nccl_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self._lib.arianna_comm_init(self._h, buf, int(rank), int(n_ranks)))
+
+    def callbacks_global(self):
+        me = C.c_double()
+        acc = (C.c_double * self.n_moves)()
+        self._ck(self._lib.arianna_callbacks_global(self._h, C.byref(me), acc))
+        return me.value, np.array(acc[:], dtype=np.float64)
+
+    def pgmc_read_global(self, n_learn: int):
+        out = (L.GradientData * n_learn)()
+        self._ck(self._lib.arianna_pgmc_read_global(self._h, out, n_learn))
+        return np.array([[r.j, r.dj, r.dlogq_forward, r.g, r.n] for r in out], dtype=np.float64).reshape(n_learn, 5)
+
     # -- plumbing -----------------------------------------------------------------------------------------
     @property
     def stream_ptr(self) -> int:

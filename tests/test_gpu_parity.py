@@ -580,3 +580,55 @@ def test_config1_verbatim(tmp_path):
     assert abs(energies[1:, 1].mean() - 0.25) < 0.03
     acc = open(tmp_path / "acceptance.dat").read().split("\n")
     assert acc[0] == "0 [NaN]" and abs(float(acc[-2].split("[")[1][:-1]) - ref.callback_acceptance()[0]) < 1e-12
+
+
+_LIBNCCL_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("gloo")                      # only used to hand the 128-byte NCCL id around
+import montecarlo_b200 as mb
+from montecarlo_b200.arianna import shard_bounds
+M = 100003
+off, n = shard_bounds(M, rank, world)
+ids = [mb.CudaEnsemble.nccl_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+eng = mb.CudaEnsemble(n, 2.0, [0.2, 0.6], [0.5, 0.5], seed=11, chain_offset=off, n_chains_total=M, arith="exact",
+                      device=int(os.environ["LOCAL_RANK"]))
+eng.comm_init(ids[0], rank, world)
+eng.init_synthetic()
+eng.sweep(25, reduce=True)
+me, ma = eng.callbacks_global()                      # NCCL all-reduce inside libarianna_cuda.so
+eng.pgmc_estimate(3, [0, 1])
+gd = eng.pgmc_read_global(2)
+np.save(os.path.join({path!r}, f"out_rank{{rank}}.npy"), np.concatenate([[me], ma, gd.ravel()]))
+eng.close(); dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_two_gpu_allreduce_inside_the_library(tmp_path):
+    """arianna_comm_init / arianna_callbacks_global / arianna_pgmc_read_global: the NCCL path a Julia host would use."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_LIBNCCL_WORKER.format(root=root, path=str(tmp_path)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29650", str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    a, b = (np.load(tmp_path / f"out_rank{k}.npy") for k in range(2))
+    assert np.array_equal(a, b)                                   # every rank holds the ensemble-wide values
+    M = 100003
+    with mb.CudaEnsemble(M, 2.0, [0.2, 0.6], [0.5, 0.5], seed=11, arith="exact") as eng:   # one GPU, whole ensemble
+        eng.init_synthetic()
+        eng.sweep(25, reduce=True)
+        me, ma = eng.callbacks_global()                           # no communicator: equals the local call
+        eng.pgmc_estimate(3, [0, 1])
+        want = np.concatenate([[me], ma, eng.pgmc_read(2).ravel()])
+    np.testing.assert_allclose(a, want, rtol=1e-12)
