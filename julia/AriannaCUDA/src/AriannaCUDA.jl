@@ -17,7 +17,7 @@ using ComponentArrays
 using Libdl
 using Random
 
-export CudaEnsemble, callback_energy, callback_acceptance_cuda, flush!, device_positions
+export CudaEnsemble, callback_acceptance_cuda, flush!, device_positions, nccl_unique_id, comm_init!
 
 const MAX_MOVES = 16
 const libarianna = Ref{String}(get(ENV, "ARIANNA_CUDA_LIB", "libarianna_cuda.so"))
@@ -89,6 +89,21 @@ function CudaEnsemble(x0::Vector{Float64}, β::Float64, pool; seed::Int=1, poten
     return ens
 end
 
+"""
+    nccl_unique_id() -> Vector{UInt8}          (rank 0; broadcast it with MPI.jl / Distributed / a file)
+    comm_init!(ens, id, rank, nranks)          (every rank, ens built with chain_offset / n_total of its shard)
+
+Multi-GPU: one Julia process per GPU; the callback and estimator sums are all-reduced inside libarianna_cuda.so.
+"""
+function nccl_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(C_NULL, ccall((:arianna_nccl_unique_id, libarianna[]), Int32, (Ptr{UInt8},), id))
+    return id
+end
+comm_init!(ens, id::Vector{UInt8}, rank::Int, nranks::Int) =
+    check(ens.handle, ccall((:arianna_comm_init, libarianna[]), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32),
+                            ens.handle, id, rank, nranks))
+
 # Metropolis(chains; pool) deep-copies the pool per chain and the estimator deep-copies the chains
 # (metropolis.jl:289, estimator.jl:86): a raw handle must never be duplicated.
 Base.deepcopy_internal(e::CudaEnsemble, ::IdDict) = e
@@ -123,7 +138,8 @@ function reduce_callbacks!(ens::CudaEnsemble)
     check(ens.handle, ccall((:arianna_steps_done, libarianna[]), Int32, (Ptr{Cvoid}, Ref{Int64}), ens.handle, t))
     if ens.cache_t != t[]
         e = Ref{Float64}(0.0)
-        check(ens.handle, ccall((:arianna_callbacks, libarianna[]), Int32, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}),
+        # *_global == the local call on one GPU; with a communicator (comm_init!) it all-reduces over NVLink first
+        check(ens.handle, ccall((:arianna_callbacks_global, libarianna[]), Int32, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}),
                                 ens.handle, e, ens.acceptance))
         ens.energy, ens.cache_t = e[], t[]
     end
@@ -175,7 +191,7 @@ function Arianna.make_step!(simulation::Simulation{<:CudaEnsemble}, algorithm::P
     check(ens.handle, ccall((:arianna_pgmc_estimate, libarianna[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32),
                             ens.handle, algorithm.q_batch_size, ids, length(ids)))
     recs = Vector{GradientRecord}(undef, length(ids))
-    check(ens.handle, ccall((:arianna_pgmc_read, libarianna[]), Int32, (Ptr{Cvoid}, Ptr{GradientRecord}, Int32),
+    check(ens.handle, ccall((:arianna_pgmc_read_global, libarianna[]), Int32, (Ptr{Cvoid}, Ptr{GradientRecord}, Int32),
                             ens.handle, recs, length(ids)))
     for (k, r) in enumerate(recs)
         gd = Arianna.PolicyGuided.GradientData(r.j, ComponentArray(σ=r.dj), ComponentArray(σ=r.dlogq_forward),
