@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) k(double *out, uint32_t seed, double a, d
     double d0 = threadIdx.x, d1 = d0 + 1, d2 = d0 + 2, d3 = d0 + 3;
     uint32_t i0 = threadIdx.x + seed, i1 = i0 * 3u, i2 = i0 * 5u, i3 = i0 * 7u;
     uint32_t l0 = i0 ^ 0x1234, l1 = i1 ^ 0x777, l2 = i2, l3 = i3;
+    uint64_t w0 = i0, w1 = i1 + 11, w2 = i2 + 13, w3 = i3 + 17;
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
@@ -48,6 +49,13 @@ __global__ void __launch_bounds__(256) k(double *out, uint32_t seed, double a, d
             if (MODE & 256) {  // IMAD.HI.U32 x4
                 i0 = __umulhi(i0, 0xD2511F53u) + 1u; i1 = __umulhi(i1, 0xCD9E8D57u) + 3u; i2 = __umulhi(i2, 0xD2511F53u) + 5u; i3 = __umulhi(i3, 0xCD9E8D57u) + 7u;
             }
+            if (MODE & 512) {  // pure IMAD.WIDE.U32 with 64-bit accumulate: one instruction per chain step
+                w0 = (uint64_t)(uint32_t)w0 * 0xD2511F53u + w0; w1 = (uint64_t)(uint32_t)w1 * 0xCD9E8D57u + w1;
+                w2 = (uint64_t)(uint32_t)w2 * 0xD2511F53u + w2; w3 = (uint64_t)(uint32_t)w3 * 0xCD9E8D57u + w3;
+            }
+            if (MODE & 1024) {  // DADD x4
+                d0 = d0 + a; d1 = d1 + a; d2 = d2 + a; d3 = d3 + a;
+            }
             if (MODE & 16) {  // FFMA x4 (fp32)
                 float f0 = __uint_as_float(l0), f1 = __uint_as_float(l1), f2 = __uint_as_float(l2), f3 = __uint_as_float(l3);
                 f0 = fmaf(f0, 1.0001f, 0.5f); f1 = fmaf(f1, 1.0001f, 0.5f); f2 = fmaf(f2, 1.0001f, 0.5f); f3 = fmaf(f3, 1.0001f, 0.5f);
@@ -55,7 +63,7 @@ __global__ void __launch_bounds__(256) k(double *out, uint32_t seed, double a, d
             }
         }
     }
-    out[blockIdx.x * 256 + threadIdx.x] = d0 + d1 + d2 + d3 + (double)(i0 ^ i1 ^ i2 ^ i3 ^ l0 ^ l1 ^ l2 ^ l3);
+    out[blockIdx.x * 256 + threadIdx.x] = d0 + d1 + d2 + d3 + (double)(i0 ^ i1 ^ i2 ^ i3 ^ l0 ^ l1 ^ l2 ^ l3) + (double)(w0 ^ w1 ^ w2 ^ w3);
 }
 
 template <int MODE>
@@ -103,5 +111,15 @@ int main()
     run<1 | 256>("DFMA + IMAD.HI", 8, out, p.multiProcessorCount, ghz);
     run<2 | 64>("IMAD.WIDE(+xor) + MUFU.EX2", 12, out, p.multiProcessorCount, ghz);
     run<8 | 2>("IMAD lo + IMAD.WIDE(+xor)", 12, out, p.multiProcessorCount, ghz);
+    run<512>("IMAD.WIDE (pure, 64-bit acc)", 4, out, p.multiProcessorCount, ghz);
+    run<512 | 4>("IMAD.WIDE pure + LOP3", 8, out, p.multiProcessorCount, ghz);
+    run<512 | 16>("IMAD.WIDE pure + FFMA", 8, out, p.multiProcessorCount, ghz);
+    run<512 | 1>("IMAD.WIDE pure + DFMA", 8, out, p.multiProcessorCount, ghz);
+    run<512 | 8>("IMAD.WIDE pure + IMAD lo", 8, out, p.multiProcessorCount, ghz);
+    run<512 | 64>("IMAD.WIDE pure + MUFU.EX2", 8, out, p.multiProcessorCount, ghz);
+    run<512 | 4 | 16>("IMAD.WIDE pure + LOP3 + FFMA", 12, out, p.multiProcessorCount, ghz);
+    run<1024>("DADD", 4, out, p.multiProcessorCount, ghz);
+    run<4 | 16>("LOP3 + FFMA", 8, out, p.multiProcessorCount, ghz);
+    run<4 | 16 | 1>("LOP3 + FFMA + DFMA", 12, out, p.multiProcessorCount, ghz);
     return 0;
 }

@@ -1,0 +1,27 @@
+#!/bin/bash
+# compute-sanitizer evidence: memcheck + racecheck + synccheck over a small end-to-end pass of every kernel family.
+mkdir -p gpurun_out
+cat > /tmp/san.py <<'PY'
+import sys, numpy as np
+sys.path.insert(0, ".")
+import montecarlo_b200 as mb
+from oracle import oracle as O
+M = 3001
+for arith in ("fast", "exact"):
+    for sig, w in (([0.1], [1.0]), ([0.2, 0.5, 0.9], [0.5, 0.25, 0.25])):
+        with mb.CudaEnsemble(M, 2.0, sig, w, seed=3, arith=arith) as e:
+            e.init_synthetic(); e.sweep(7, reduce=True); e.sweep(4); e.callbacks(); e.counters()
+            e.pgmc_estimate(3, [0]); e.pgmc_read(1); e.get_state(with_energy=True)
+            x0 = e.get_state()
+            uc, z, ua = O.draws_philox(3, 0, M, 0, 5)
+            e.sweep_replay(uc, z, ua, want_decisions=True)
+with mb.CudaEnsemble(M, 2.0, [0.1], seed=3, rng="xoshiro", arith="exact") as e:
+    e.init_synthetic(); st = np.random.default_rng(0).integers(1, 2**63, size=(M, 4), dtype=np.uint64)
+    e.set_rng_state(st); e.sweep(50); e.get_rng_state()
+print("sanitize pass ok")
+PY
+for tool in memcheck racecheck synccheck; do
+  echo "== compute-sanitizer --tool $tool"
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san.py 2>&1 | tail -6
+  echo "exit=$?"
+done 2>&1 | tee gpurun_out/sanitizer.log

@@ -12,6 +12,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # A fresh checkout has no built artefacts (*.so is git-ignored): build the CUDA library (nvcc cross-compiles
+    # without a GPU) and the CPU oracle once, in-tree, before any test imports them.
+    from montecarlo_b200._build import build_library, is_stale
+    if is_stale():
+        build_library()
+    from oracle import oracle as O
+    O.build()
 
 
 def _have_gpu():
