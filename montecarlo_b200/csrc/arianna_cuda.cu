@@ -571,7 +571,9 @@ int32_t arianna_sweep_replay(arianna_handle *h, int64_t K, const double *u_cat, 
     } else {
         // stage host draws through a bounded device buffer, chunked over steps (<= 1 GiB per array)
         const size_t per_step = sizeof(double) * (size_t)h->M;
-        int64_t kc = (int64_t)((size_t(1) << 30) / per_step);
+        size_t stage = size_t(1) << 30;
+        if (const char *env = getenv("ARIANNA_REPLAY_STAGE_BYTES")) stage = (size_t)strtoull(env, nullptr, 10);
+        int64_t kc = (int64_t)(stage / per_step);
         if (kc < 1) kc = 1;
         if (kc > K) kc = K;
         const size_t narr = multi ? 3 : 2;

@@ -632,3 +632,20 @@ def test_two_gpu_allreduce_inside_the_library(tmp_path):
         eng.pgmc_estimate(3, [0, 1])
         want = np.concatenate([[me], ma, eng.pgmc_read(2).ravel()])
     np.testing.assert_allclose(a, want, rtol=1e-12)
+
+
+def test_replay_host_staging_is_chunked_over_steps(monkeypatch):
+    """Host-pointer replay streams the draws through a bounded device buffer: force 3-step chunks."""
+    M, K = 2049, 20
+    monkeypatch.setenv("ARIANNA_REPLAY_STAGE_BYTES", str(3 * 8 * M))
+    x0 = O.init_synthetic(4, 0, M)
+    uc, z, ua = _xoshiro_draws(x0, 2.0, [0.2, 0.7], [0.3, 0.7], K)
+    ref = O.Ensemble(x0, 2.0, [0.2, 0.7], [0.3, 0.7])
+    dref, _, _ = ref.sweep_replay(uc, z, ua, want_decisions=True)
+    with mb.CudaEnsemble(M, 2.0, [0.2, 0.7], [0.3, 0.7], arith="exact") as eng:
+        eng.set_state(x0)
+        l0 = eng.launch_count
+        dec = eng.sweep_replay(uc, z, ua, want_decisions=True)
+        assert eng.launch_count - l0 == 7                          # ceil(20 / 3) launches
+        assert np.array_equal(dec, dref) and np.array_equal(eng.get_state(), ref.x)
+        assert np.array_equal(eng.chain_counters()[1].astype(np.int64), ref.tot)
