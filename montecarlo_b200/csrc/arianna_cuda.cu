@@ -72,8 +72,7 @@ struct arianna_handle {
     double *d_snap = nullptr;             // device snapshot of x the copy stream reads from
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t hbm_bytes = 0;
-    int grid = 0;        // persistent grid of the light kernels: 8 resident CTAs per SM x SM count
-    int grid_sweep = 0;  // persistent grid of the fused sweep: exactly one resident wave (occupancy API)
+    int grid = 0;        // grid of the light streaming kernels: 8 CTAs per SM x SM count
 
     int64_t M = 0;
     double *d_x = nullptr;
@@ -178,6 +177,28 @@ void make_zig_tables(uint64_t *ki, double *wi, double *fi)
     ki[1] = 0;
 }
 
+// Grid of the grid-stride kernels: an integer number of FULL resident waves (occupancy API x SM count x kGridWaves).
+// One wave is the worst choice for these kernels: all CTAs start together, their warps run the Philox phase and the
+// FP64 phase in lockstep (bursts of contention on one pipe at a time) and the SM drains unevenly at the end.  With
+// 16 waves the hardware CTA scheduler staggers the phases and balances the tail; measured on M = 2^27, K = 10:
+// 1 / 2 / 4 / 8 / 16 / 32 / 64 / 256 waves -> 5.57 / 5.28 / 5.15 / 5.09 / 5.06 / 5.07 / 5.11 / 5.36 ms.
+constexpr int kGridWaves = 16;
+constexpr int kMaxGridWaves = 32;
+template <typename K>
+int wave_grid(const arianna_handle *h, K kernel, size_t smem, int64_t M)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 2;
+    }
+    if (per_sm > 8) per_sm = 8;
+    static const int env_waves = getenv("ARIANNA_GRID_WAVES") ? atoi(getenv("ARIANNA_GRID_WAVES")) : 0;
+    int waves = env_waves > 0 ? env_waves : kGridWaves;
+    if (waves > kMaxGridWaves) waves = kMaxGridWaves;
+    return grid_for(h, M, per_sm * waves);
+}
+
 template <typename F>
 int32_t dispatch_pot(int pot, F &&f)
 {
@@ -266,18 +287,6 @@ int32_t arianna_create(const arianna_config *cfg, arianna_handle **out)
         return bail(ARIANNA_ERR_UNSUPPORTED, "arianna_create: this library is built for sm_100a (B200) only");
     // persistent-style grid: 8 resident CTAs of 256 threads per SM cover the 64-warp SM limit
     h->grid = grid_for(h, h->M, 8);
-    {
-        // one CTA wave that is fully resident: a grid-stride loop over more CTAs than fit leaves a partial last wave
-        int per_sm = 0;
-        const bool multi = cfg->n_moves > 1;
-        const size_t smem = multi ? sizeof(uint32_t) * 2 * cfg->n_moves * kBlock : 0;
-        cudaError_t e = multi
-            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_philox_kernel<POT_HARMONIC, ARITH_FAST, true>, kBlock, smem)
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_philox_kernel<POT_HARMONIC, ARITH_FAST, false>, kBlock, smem);
-        if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }
-        h->grid_sweep = grid_for(h, h->M, per_sm);
-    }
-
     if (cfg->stream) {
         h->stream = (cudaStream_t)cfg->stream;
     } else {
@@ -301,7 +310,7 @@ int32_t arianna_create(const arianna_config *cfg, arianna_handle **out)
         CU_CREATE(cudaMemsetAsync(h->d_tot, 0, sizeof(uint32_t) * h->M * nm, h->stream));
     }
     CU_CREATE(cudaMemsetAsync(h->d_x, 0, sizeof(double) * h->M, h->stream));
-    const int max_grid = h->sm_count * 8;
+    const int max_grid = h->sm_count * 8 * kMaxGridWaves;  // partials of the largest grid wave_grid() can return
     CU_CREATE(cudaMalloc(&h->d_partials, sizeof(double) * (size_t)max_grid * kMaxOut));
     CU_CREATE(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
     CU_CREATE(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
@@ -498,11 +507,11 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
         dispatch_pot(h->cfg.potential, [&](auto pot) {
             constexpr int POT = decltype(pot)::value;
             if (exact) {
-                if (multi) sweep_philox_kernel<POT, ARITH_EXACT, true><<<h->grid_sweep, kBlock, smem, h->stream>>>(sp);
-                else sweep_philox_kernel<POT, ARITH_EXACT, false><<<h->grid_sweep, kBlock, 0, h->stream>>>(sp);
+                if (multi) sweep_philox_kernel<POT, ARITH_EXACT, true><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_EXACT, true>, smem, h->M), kBlock, smem, h->stream>>>(sp);
+                else sweep_philox_kernel<POT, ARITH_EXACT, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_EXACT, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
             } else {
-                if (multi) sweep_philox_kernel<POT, ARITH_FAST, true><<<h->grid_sweep, kBlock, smem, h->stream>>>(sp);
-                else sweep_philox_kernel<POT, ARITH_FAST, false><<<h->grid_sweep, kBlock, 0, h->stream>>>(sp);
+                if (multi) sweep_philox_kernel<POT, ARITH_FAST, true><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_FAST, true>, smem, h->M), kBlock, smem, h->stream>>>(sp);
+                else sweep_philox_kernel<POT, ARITH_FAST, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_FAST, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
             }
             return 0;
         });
@@ -515,11 +524,11 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
         dispatch_pot(h->cfg.potential, [&](auto pot) {
             constexpr int POT = decltype(pot)::value;
             if (exact) {
-                if (multi) sweep_xoshiro_kernel<POT, ARITH_EXACT, true><<<h->grid, kBlock, smem, h->stream>>>(xp);
-                else sweep_xoshiro_kernel<POT, ARITH_EXACT, false><<<h->grid, kBlock, 0, h->stream>>>(xp);
+                if (multi) sweep_xoshiro_kernel<POT, ARITH_EXACT, true><<<wave_grid(h, sweep_xoshiro_kernel<POT, ARITH_EXACT, true>, smem, h->M), kBlock, smem, h->stream>>>(xp);
+                else sweep_xoshiro_kernel<POT, ARITH_EXACT, false><<<wave_grid(h, sweep_xoshiro_kernel<POT, ARITH_EXACT, false>, 0, h->M), kBlock, 0, h->stream>>>(xp);
             } else {
-                if (multi) sweep_xoshiro_kernel<POT, ARITH_FAST, true><<<h->grid, kBlock, smem, h->stream>>>(xp);
-                else sweep_xoshiro_kernel<POT, ARITH_FAST, false><<<h->grid, kBlock, 0, h->stream>>>(xp);
+                if (multi) sweep_xoshiro_kernel<POT, ARITH_FAST, true><<<wave_grid(h, sweep_xoshiro_kernel<POT, ARITH_FAST, true>, smem, h->M), kBlock, smem, h->stream>>>(xp);
+                else sweep_xoshiro_kernel<POT, ARITH_FAST, false><<<wave_grid(h, sweep_xoshiro_kernel<POT, ARITH_FAST, false>, 0, h->M), kBlock, 0, h->stream>>>(xp);
             }
             return 0;
         });
@@ -556,8 +565,10 @@ int32_t arianna_sweep_replay(arianna_handle *h, int64_t K, const double *u_cat, 
         rp.pool = h->pool;
         dispatch_pot(h->cfg.potential, [&](auto pot) {
             constexpr int POT = decltype(pot)::value;
-            if (multi) sweep_replay_kernel<POT, true><<<h->grid, kBlock, smem, h->stream>>>(rp);
-            else sweep_replay_kernel<POT, false><<<h->grid, kBlock, 0, h->stream>>>(rp);
+            if (multi)
+                sweep_replay_kernel<POT, true><<<wave_grid(h, sweep_replay_kernel<POT, true>, smem, h->M), kBlock, smem, h->stream>>>(rp);
+            else
+                sweep_replay_kernel<POT, false><<<wave_grid(h, sweep_replay_kernel<POT, false>, 0, h->M), kBlock, 0, h->stream>>>(rp);
             return 0;
         });
         CU_TRY(h, cudaGetLastError());
@@ -820,9 +831,12 @@ static int32_t pgmc_impl(arianna_handle *h, int32_t q_batch, const int32_t *lear
         pp.tables = h->d_tables;
         dispatch_pot(h->cfg.potential, [&](auto pot) {
             constexpr int POT = decltype(pot)::value;
-            if (replay) pgmc_kernel<POT, ARITH_EXACT, true><<<h->grid, kBlock, 0, h->stream>>>(pp);
-            else if (exact) pgmc_kernel<POT, ARITH_EXACT, false><<<h->grid, kBlock, 0, h->stream>>>(pp);
-            else pgmc_kernel<POT, ARITH_FAST, false><<<h->grid, kBlock, 0, h->stream>>>(pp);
+            if (replay)
+                pgmc_kernel<POT, ARITH_EXACT, true><<<wave_grid(h, pgmc_kernel<POT, ARITH_EXACT, true>, 0, h->M), kBlock, 0, h->stream>>>(pp);
+            else if (exact)
+                pgmc_kernel<POT, ARITH_EXACT, false><<<wave_grid(h, pgmc_kernel<POT, ARITH_EXACT, false>, 0, h->M), kBlock, 0, h->stream>>>(pp);
+            else
+                pgmc_kernel<POT, ARITH_FAST, false><<<wave_grid(h, pgmc_kernel<POT, ARITH_FAST, false>, 0, h->M), kBlock, 0, h->stream>>>(pp);
             return 0;
         });
         CU_TRY(h, cudaGetLastError());
