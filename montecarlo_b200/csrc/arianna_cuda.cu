@@ -810,6 +810,8 @@ static int32_t pgmc_impl(arianna_handle *h, int32_t q_batch, const int32_t *lear
     for (int l = 0; l < n_learn; ++l)
         REQUIRE(h, learn_ids[l] >= 0 && learn_ids[l] < h->pool.n_moves, "arianna_pgmc_estimate: learn id out of range");
     if (n_learn == 0) return ARIANNA_OK;
+    REQUIRE(h, replay || h->pgmc_samples + (int64_t)n_learn * q_batch < (int64_t(1) << 33),
+            "arianna_pgmc_estimate: the estimator stream holds 2^33 samples per chain");
     DeviceGuard guard(h->device);
     const bool exact = replay || h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
     const double *dz = z;
@@ -939,10 +941,10 @@ int32_t arianna_debug_math(arianna_handle *h, int32_t kind, const double *a, con
                            double *out, int64_t n)
 {
     if (!h) return ARIANNA_ERR_INVALID;
-    REQUIRE(h, kind >= 0 && kind <= 5 && out != nullptr && n >= 0, "arianna_debug_math: bad arguments");
+    REQUIRE(h, kind >= 0 && kind <= 7 && out != nullptr && n >= 0, "arianna_debug_math: bad arguments");
     if (n == 0) return ARIANNA_OK;
     DeviceGuard guard(h->device);
-    const int64_t nout = (kind >= 3) ? 2 * n : n;
+    const int64_t nout = (kind >= 6) ? 4 * n : (kind >= 3) ? 2 * n : n;
     const size_t bytes = sizeof(double) * (size_t)(nout + 3 * n);
     if (!ensure_scratch(h, bytes)) return fail(h, ARIANNA_ERR_NOMEM, "arianna_debug_math: scratch allocation failed");
     double *d_out = h->d_scratch;

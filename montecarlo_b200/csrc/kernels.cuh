@@ -294,10 +294,13 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
             }
         }
 
+        // chain-only halves of the first three Philox rounds (rng.cuh); the rare refinement block is generated unhoisted
+        const PhiloxChain<kTagMetropolis, 0> ph(sid);
+        const PhiloxChain<kTagMetropolis, MULTI ? 2 : 0> ph_cat(sid);   // (unused -> eliminated when !MULTI)
         // Draws of one pair of steps (a pure function of the pair index, independent of the chain state).
         // ONE Philox block feeds the pair: words B0/B1 give the two 53-bit Box-Muller uniforms (top 53 bits) and,
         // in their low 11 bits, the PREFIXES of the two accept uniforms.  The remaining 42 bits of an accept
-        // uniform come from block 4p+1 and are only generated when the FP32 filter cannot decide (lazy refinement).
+        // uniform come from sub-block 1 of the pair and are only generated when the FP32 filter cannot decide (lazy refinement).
         struct PairDraws {
             double z0, z1;
             uint32_t f0, f1;   // 11-bit prefixes of u_acc(2p), u_acc(2p+1)
@@ -306,20 +309,20 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         };
         auto gen_pair = [&](uint64_t pr) {
             PairDraws d;
-            const U64Pair b0 = philox_block<kTagMetropolis>(sid, 4 * pr + 0);
+            const U64Pair b0 = ph.block((uint32_t)pr);
             m64::box_muller_u64(u64_of(b0.a_lo, b0.a_hi), u64_of(b0.b_lo, b0.b_hi), &s_T, d.z0, d.z1);
             d.f0 = b0.a_lo & 0x7ffu;
             d.f1 = b0.b_lo & 0x7ffu;
             d.pr = pr;
             d.b2 = U64Pair{};
-            if constexpr (MULTI) d.b2 = philox_block<kTagMetropolis>(sid, 4 * pr + 2);
+            if constexpr (MULTI) d.b2 = ph_cat.block((uint32_t)pr);
             return d;
         };
         // the two (state-dependent, serial) Metropolis steps of a pair; DO0 / DO1 are compile-time
         auto do_steps = [&](const PairDraws &d, auto do0, auto do1) {
             if constexpr (decltype(do0)::value) {
                 auto exact_u = [&]() {
-                    const U64Pair r = philox_block<kTagMetropolis>(sid, 4 * d.pr + 1);
+                    const U64Pair r = philox_block<kTagMetropolis>(sid, d.pr, 1);
                     return m64::u53_prefix_refine(d.f0, r.a_lo, r.a_hi);
                 };
                 const float ulo = m64::ulo_from_prefix11(d.f0);
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
             }
             if constexpr (decltype(do1)::value) {
                 auto exact_u = [&]() {
-                    const U64Pair r = philox_block<kTagMetropolis>(sid, 4 * d.pr + 1);
+                    const U64Pair r = philox_block<kTagMetropolis>(sid, d.pr, 1);
                     return m64::u53_prefix_refine(d.f1, r.b_lo, r.b_hi);
                 };
                 const float ulo = m64::ulo_from_prefix11(d.f1);
@@ -738,8 +741,9 @@ __global__ void __launch_bounds__(kBlock) pgmc_kernel(const PgmcParams p)
                                         sgf, sg, s_T.exp2_j);
         } else {
             const uint64_t sid = p.sid0 + (uint64_t)c;
+            const PhiloxChain<kTagEstimator, 0> ph(sid);
             for (int64_t pr = p.q0 >> 1; 2 * pr < qend; ++pr) {
-                const U64Pair blk = philox_block<kTagEstimator>(sid, (uint64_t)pr);
+                const U64Pair blk = ph.block((uint32_t)pr);
                 double z0, z1;
                 m64::box_muller_u64(u64_of(blk.a_lo, blk.a_hi), u64_of(blk.b_lo, blk.b_hi), &s_T, z0, z1);
                 if (2 * pr >= p.q0)
@@ -759,7 +763,7 @@ __global__ void __launch_bounds__(kBlock) pgmc_kernel(const PgmcParams p)
 __global__ void __launch_bounds__(kBlock) init_kernel(double *x, int64_t M, uint64_t sid0)
 {
     for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < M; c += (int64_t)gridDim.x * kBlock) {
-        const U64Pair b = philox_block<kTagInit>(sid0 + (uint64_t)c, 0);
+        const U64Pair b = philox_block<kTagInit>(sid0 + (uint64_t)c, 0, 0);
         x[c] = __dsub_rn(__dmul_rn(4.0, u53(b.a_lo, b.a_hi)), 2.0);
     }
 }
@@ -777,7 +781,8 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const double *x, double 
 // Diagnostic: evaluates the device math layer (csrc/math64.cuh) on arrays so the tests can compare the DEVICE code
 // paths (MUFU.RSQ64H seed, MUFU.EX2 filter) with long-double references.  kind: 0 exp_nonpos(x) | 1 neg2log_u53(k) |
 // 2 sqrt_pos(x) | 3 sincos_turn53(k) -> out[2i], out[2i+1] | 4 box_muller_u64(a, b) -> out[2i], out[2i+1] |
-// 5 accept test (x = a, prefix word = b, refinement word = c) -> out[2i] = filtered, out[2i+1] = reference decision
+// 5 accept test (x = a, prefix word = b, refinement word = c) -> out[2i] = filtered, out[2i+1] = reference decision |
+// 6 / 7 Philox block of (sid = b, p = c[, sub = a]) through PhiloxChain / philox_block -> out[4i .. 4i+3] = the 4 words
 __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const double *a, const uint64_t *b,
                                                             const uint64_t *cc, double *out, int64_t n,
                                                             const m64::MathTables *tables)
@@ -791,7 +796,14 @@ __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const doub
         else if (kind == 2) out[i] = m64::sqrt_pos(a[i]);
         else if (kind == 3) m64::sincos_turn53(b[i], out[2 * i], out[2 * i + 1]);
         else if (kind == 4) m64::box_muller_u64(b[i], cc[i], &s_T, out[2 * i], out[2 * i + 1]);
-        else {
+        else if (kind == 6 || kind == 7) {
+            // Philox4x32-10 block (sid = b, p = c): 6 = per-chain hoisted form (sub 0), 7 = general form, sub = a
+            U64Pair r;
+            if (kind == 6) r = PhiloxChain<kTagMetropolis, 0>(b[i]).block((uint32_t)cc[i]);
+            else r = philox_block<kTagMetropolis>(b[i], cc[i], (uint32_t)a[i]);
+            out[4 * i] = (double)r.a_lo; out[4 * i + 1] = (double)r.a_hi;
+            out[4 * i + 2] = (double)r.b_lo; out[4 * i + 3] = (double)r.b_hi;
+        } else {
             const uint32_t f = (uint32_t)b[i] & 0x7ffu;
             const uint64_t r = cc[i];
             auto exact_u = [&]() { return m64::u53_prefix_refine(f, (uint32_t)r, (uint32_t)(r >> 32)); };

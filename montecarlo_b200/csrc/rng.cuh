@@ -22,25 +22,71 @@ struct U64Pair {
     uint32_t a_lo, a_hi, b_lo, b_hi;  // A = out[0] | out[1] << 32,  B = out[2] | out[3] << 32
 };
 
-// One Philox4x32-10 block.  TAG is a compile-time constant so the ten round keys fold into immediates.
-template <uint32_t TAG>
-__device__ __forceinline__ U64Pair philox_block(uint64_t sid, uint64_t n)
+// One Philox4x32-10 round on (c0, c1, c2, c3) with round keys (k0, k1).
+__device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0,
+                                             uint32_t k1)
 {
-    uint32_t c0 = (uint32_t)sid, c1 = (uint32_t)(sid >> 32), c2 = (uint32_t)n, c3 = (uint32_t)(n >> 32);
-    uint32_t k0 = TAG, k1 = kKey1;
+    const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
+    const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+}
+
+// Counter layout (v2, identical in oracle/arianna_oracle.c:philox_block):
+//   ctr = (sid_lo, p_lo, sid_hi, sub | (p_hi << 8)),  key = (TAG, 'ARIA')
+// sid = seed + global chain index, p = block index of the stream (Metropolis: step pair t >> 1; estimator: sample
+// pair q >> 1), sub = which block of the pair (0 main, 1 accept-uniform refinement, 2 categorical uniforms).
+// The VARYING word p sits in c1, a word that the first round only XORs: with (c0, c2, c3) fixed per chain, one of
+// the two 32x32->64 multiplies of each of the first three rounds depends on the chain alone (PhiloxChain below).
+
+// One Philox4x32-10 block, general form.  TAG is a compile-time constant so the ten round keys fold into immediates.
+template <uint32_t TAG>
+__device__ __forceinline__ U64Pair philox_block(uint64_t sid, uint64_t p, uint32_t sub)
+{
+    uint32_t c0 = (uint32_t)sid, c1 = (uint32_t)p, c2 = (uint32_t)(sid >> 32), c3 = sub | ((uint32_t)(p >> 32) << 8);
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
-        uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
-        c0 = hi1 ^ c1 ^ k0;
-        c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
-        c3 = lo0;
-        k0 += kPhiloxW0;
-        k1 += kPhiloxW1;
-    }
+    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, TAG + (uint32_t)r * kPhiloxW0, kKey1 + (uint32_t)r * kPhiloxW1);
     return U64Pair{c0, c1, c2, c3};
 }
+
+// The same function for ONE chain and a fixed sub-block, p < 2^32: the chain-only halves of rounds 0-2 are computed
+// once per chain (4 wide multiplies) and every block then costs 16 wide multiplies instead of 20.  On B200 an
+// IMAD.WIDE holds the issue port for ~4.5 cycles (profiles/microbench), so these are the most expensive instructions
+// of the sweep.  Bit-identical to philox_block<TAG>(sid, p, SUB) (tests/test_gpu_math.py::test_device_philox_kat).
+template <uint32_t TAG, uint32_t SUB>
+struct PhiloxChain {
+    uint32_t X, L0, B2, Q, ql;
+    __device__ __forceinline__ explicit PhiloxChain(uint64_t sid)
+    {
+        constexpr uint32_t k00 = TAG, k10 = kKey1, k01 = TAG + kPhiloxW0, k11 = kKey1 + kPhiloxW1,
+                           k02 = TAG + 2u * kPhiloxW0, k12 = kKey1 + 2u * kPhiloxW1;
+        const uint32_t s0 = (uint32_t)sid, s1 = (uint32_t)(sid >> 32);
+        const uint32_t h0 = __umulhi(kPhiloxM0, s0), l0 = kPhiloxM0 * s0;     // round 0, chain-only
+        const uint32_t h1 = __umulhi(kPhiloxM1, s1), l1 = kPhiloxM1 * s1;
+        X = h1 ^ k00;                                                         // c0 after round 0 = X ^ p
+        const uint32_t C2 = h0 ^ SUB ^ k10;                                   // c2 after round 0
+        const uint32_t gh = __umulhi(kPhiloxM1, C2), gl = kPhiloxM1 * C2;     // round 1, chain-only half
+        const uint32_t A = gh ^ l1 ^ k01;                                     // c0 after round 1
+        L0 = l0 ^ k11;                                                        // c2 after round 1 = hi(M0 c0) ^ L0
+        const uint32_t qh = __umulhi(kPhiloxM0, A);                           // round 2, chain-only half
+        ql = kPhiloxM0 * A;                                                   // c3 after round 2
+        B2 = gl ^ k02;                                                        // c0 after round 2 = hi(M1 c2) ^ B2
+        Q = qh ^ k12;                                                         // c2 after round 2 = Q ^ lo(M0 c0 of round 1)
+    }
+    __device__ __forceinline__ U64Pair block(uint32_t p) const
+    {
+        const uint32_t a = X ^ p;                                                   // round 0
+        const uint32_t ah = __umulhi(kPhiloxM0, a), al = kPhiloxM0 * a;             // round 1
+        const uint32_t b = ah ^ L0;
+        const uint32_t bh = __umulhi(kPhiloxM1, b), bl = kPhiloxM1 * b;             // round 2
+        uint32_t c0 = bh ^ B2, c1 = bl, c2 = Q ^ al, c3 = ql;
+#pragma unroll
+        for (int r = 3; r < 10; ++r) philox_round(c0, c1, c2, c3, TAG + (uint32_t)r * kPhiloxW0, kKey1 + (uint32_t)r * kPhiloxW1);
+        return U64Pair{c0, c1, c2, c3};
+    }
+};
 
 // u53(w) = (w >> 11) * 2^-53 in [0,1), EXACTLY, without an int->fp64 conversion instruction:
 //   k = w >> 11 = k_hi * 2^32 + k_lo  (k_hi: 21 bits)

@@ -55,16 +55,17 @@ AO_API void ao_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint3
 
 /* Stream layout shared with the CUDA engine's native-Philox mode (DESIGN.md "RNG stream layout").
  *   key  = (tag, 0x41524941)                     tag: 0 = initial condition, 1 = Metropolis, 2 = estimator
- *   ctr  = (sid_lo, sid_hi, n_lo, n_hi)          sid = seed + global 0-based chain index  (mirrors the
- *                                                reference's per-chain seed  seed + c - 1, metropolis.jl:262)
+ *   ctr  = (sid_lo, p_lo, sid_hi, sub | p_hi<<8) sid = seed + global 0-based chain index  (mirrors the
+ *                                                reference's per-chain seed  seed + c - 1, metropolis.jl:262);
+ *                                                p = block index of the stream, sub = sub-block of p (0..255)
  *   out  = 4 words -> A = out[0] | out[1] << 32 ; B = out[2] | out[3] << 32
  *   u53(w) = (w >> 11) * 2^-53 in [0,1)          (same map as Julia's rand(Float64) [EXT])               */
 #define AO_KEY1 0x41524941u
 enum { AO_TAG_INIT = 0, AO_TAG_METROPOLIS = 1, AO_TAG_ESTIMATOR = 2 };
 
-static inline void philox_block(uint64_t sid, uint64_t n, uint32_t tag, uint64_t *A, uint64_t *B)
+static inline void philox_block(uint64_t sid, uint64_t p, uint32_t sub, uint32_t tag, uint64_t *A, uint64_t *B)
 {
-    uint32_t ctr[4] = {(uint32_t)sid, (uint32_t)(sid >> 32), (uint32_t)n, (uint32_t)(n >> 32)};
+    uint32_t ctr[4] = {(uint32_t)sid, (uint32_t)p, (uint32_t)(sid >> 32), sub | ((uint32_t)(p >> 32) << 8)};
     uint32_t key[2] = {tag, AO_KEY1};
     uint32_t o[4];
     ao_philox4x32_10(ctr, key, o);
@@ -90,25 +91,25 @@ static inline void box_muller(uint64_t B0, uint64_t B1, double *z0, double *z1)
 }
 
 /* x0 = 4u - 2 : mirrors `System(4rand(rng) - 2, β)` (example/.../MC_harmonic_oscillator.jl:13) with the
- * engine's own counter-based stream (tag 0, block 0, word A). */
+ * engine's own counter-based stream (tag 0, block (0, 0), word A). */
 AO_API void ao_init_synthetic(int64_t seed, int64_t chain_offset, int64_t M, double *x)
 {
 #pragma omp parallel for schedule(static)
     for (int64_t c = 0; c < M; ++c) {
         uint64_t A, B;
-        philox_block((uint64_t)(seed + chain_offset + c), 0, AO_TAG_INIT, &A, &B);
+        philox_block((uint64_t)(seed + chain_offset + c), 0, 0, AO_TAG_INIT, &A, &B);
         x[c] = 4.0 * u53(A) - 2.0;
     }
 }
 
 /* Native-mode Metropolis draws for MC steps t0 .. t0+K-1 of chains [chain_offset, chain_offset+M), written
  * as step-major [K][M] arrays so that native mode == replay of these arrays.
- *   pair p = t >> 1:  block 4p+0: words (A, B): A>>11 -> Box-Muller u1 (|1), B>>11 -> Box-Muller u2;
+ *   pair p = t >> 1:  sub-block 0: words (A, B): A>>11 -> Box-Muller u1 (|1), B>>11 -> Box-Muller u2;
  *                                 A & 0x7ff -> 11-bit PREFIX of u_acc(2p), B & 0x7ff -> prefix of u_acc(2p+1)
- *                     block 4p+1: A>>22 -> 42 refinement bits of u_acc(2p), B>>22 -> of u_acc(2p+1)
+ *                     sub-block 1: A>>22 -> 42 refinement bits of u_acc(2p), B>>22 -> of u_acc(2p+1)
  *                                 u_acc = ((prefix << 42) | refinement) * 2^-53   (the engine only generates
  *                                 this block when its FP32 filter cannot decide from the prefix alone)
- *                     block 4p+2: A -> u_cat(2p), B -> u_cat(2p+1)      (only consumed when n_moves > 1)
+ *                     sub-block 2: A -> u_cat(2p), B -> u_cat(2p+1)      (only consumed when n_moves > 1)
  *   z(2p) = r cos(2π u2), z(2p+1) = r sin(2π u2).
  * u_cat may be NULL (single-move pools do not consume it in native mode). */
 AO_API void ao_draws_philox(int64_t seed, int64_t chain_offset, int64_t M, int64_t t0, int64_t K,
@@ -121,8 +122,8 @@ AO_API void ao_draws_philox(int64_t seed, int64_t chain_offset, int64_t M, int64
             uint64_t t = (uint64_t)(t0 + s);
             uint64_t p = t >> 1;
             uint64_t A0, B0, A1, B1;
-            philox_block(sid, 4 * p + 0, AO_TAG_METROPOLIS, &A0, &B0);
-            philox_block(sid, 4 * p + 1, AO_TAG_METROPOLIS, &A1, &B1);
+            philox_block(sid, p, 0, AO_TAG_METROPOLIS, &A0, &B0);
+            philox_block(sid, p, 1, AO_TAG_METROPOLIS, &A1, &B1);
             double z0, z1;
             box_muller(A0, B0, &z0, &z1);
             int odd = (int)(t & 1);
@@ -132,7 +133,7 @@ AO_API void ao_draws_philox(int64_t seed, int64_t chain_offset, int64_t M, int64
             u_acc[s * M + c] = (double)((prefix << 42) | refine) * 0x1.0p-53;
             if (u_cat) {
                 uint64_t A2, B2;
-                philox_block(sid, 4 * p + 2, AO_TAG_METROPOLIS, &A2, &B2);
+                philox_block(sid, p, 2, AO_TAG_METROPOLIS, &A2, &B2);
                 u_cat[s * M + c] = u53(odd ? B2 : A2);
             }
         }
@@ -140,7 +141,7 @@ AO_API void ao_draws_philox(int64_t seed, int64_t chain_offset, int64_t M, int64
 }
 
 /* Estimator normals: sample index q (per chain, 0-based, counted since creation), pair p = q >> 1,
- * block p with tag 2: A -> u1, B -> u2.  z laid out [n][M] for samples q0 .. q0+n-1. */
+ * block (p, sub 0) with tag 2: A -> u1, B -> u2.  z laid out [n][M] for samples q0 .. q0+n-1. */
 AO_API void ao_draws_pgmc_philox(int64_t seed, int64_t chain_offset, int64_t M, int64_t q0, int64_t n, double *z)
 {
 #pragma omp parallel for schedule(static)
@@ -149,7 +150,7 @@ AO_API void ao_draws_pgmc_philox(int64_t seed, int64_t chain_offset, int64_t M, 
         for (int64_t s = 0; s < n; ++s) {
             uint64_t q = (uint64_t)(q0 + s);
             uint64_t A, B;
-            philox_block(sid, q >> 1, AO_TAG_ESTIMATOR, &A, &B);
+            philox_block(sid, q >> 1, 0, AO_TAG_ESTIMATOR, &A, &B);
             double z0, z1;
             box_muller(A, B, &z0, &z1);
             z[s * M + c] = (q & 1) ? z1 : z0;

@@ -60,6 +60,28 @@ def test_device_box_muller(eng):
     assert np.abs(z[:, 1] - (r * np.sin(twopi * u2)).astype(np.float64)).max() < 4e-15
 
 
+def test_device_philox_kat(eng):
+    """Both device forms of the Philox4x32-10 block (general, and the per-chain hoisted PhiloxChain that the sweep
+    uses) against the oracle's Philox, which is itself pinned by the Random123 known-answer vectors."""
+    from oracle import oracle_np as N
+    rng = np.random.default_rng(11)
+    n = 20000
+    sid = np.concatenate([rng.integers(0, 2 ** 64, size=n - 4, dtype=np.uint64),
+                          np.array([0, 1, 2 ** 32 - 1, 2 ** 64 - 1], dtype=np.uint64)])
+    p = np.concatenate([rng.integers(0, 2 ** 32, size=n - 4, dtype=np.uint64),
+                        np.array([0, 1, 2 ** 31, 2 ** 32 - 1], dtype=np.uint64)])
+    lo, hi = sid & np.uint64(0xffffffff), sid >> np.uint64(32)
+    for kind, sub in ((6, 0), (7, 0), (7, 1), (7, 2)):
+        got = eng.debug_math(kind, a=np.full(n, float(sub)), b=sid, c=p).reshape(-1, 4)
+        want = np.stack(N.philox4x32_10(lo, p, hi, np.full(n, sub, dtype=np.uint64), 1, 0x41524941), axis=1)
+        assert np.array_equal(got.astype(np.uint64), want), (kind, sub)
+    # general form with a block index beyond 32 bits: p_hi lands in bits 8.. of the last counter word
+    pbig = p + (np.uint64(5) << np.uint64(32))
+    got = eng.debug_math(7, a=np.full(n, 2.0), b=sid, c=pbig).reshape(-1, 4)
+    want = np.stack(N.philox4x32_10(lo, p, hi, np.full(n, 2 | (5 << 8), dtype=np.uint64), 1, 0x41524941), axis=1)
+    assert np.array_equal(got.astype(np.uint64), want)
+
+
 def test_device_fp32_filter_never_changes_a_decision(eng):
     rng = np.random.default_rng(7)
     n = 4_000_000

@@ -67,10 +67,11 @@ def test_philox_draws_layout_and_moments():
     n = z.size
     assert abs(z.mean()) < 4 / math.sqrt(n) and abs(z.std() - 1) < 4 / math.sqrt(2 * n)
     # numpy restatement of the counter layout for chain 3, pair 0 (lazy-refinement layout):
-    # u_acc(step 0) = ((A0 & 0x7ff) << 42 | A1 >> 22) * 2^-53 with A0 from block 0, A1 from block 1
+    # u_acc(step 0) = ((A0 & 0x7ff) << 42 | A1 >> 22) * 2^-53 with A0 from sub-block 0, A1 from sub-block 1
     sid = 42 + 5 + 3
-    o0 = N.philox4x32_10(sid & 0xffffffff, sid >> 32, 0, 0, 1, 0x41524941)
-    o1 = N.philox4x32_10(sid & 0xffffffff, sid >> 32, 1, 0, 1, 0x41524941)
+    # layout v2: ctr = (sid_lo, p, sid_hi, sub), key = (tag, 'ARIA'); pair p = 0, sub-blocks 0 and 1
+    o0 = N.philox4x32_10(sid & 0xffffffff, 0, sid >> 32, 0, 1, 0x41524941)
+    o1 = N.philox4x32_10(sid & 0xffffffff, 0, sid >> 32, 1, 1, 0x41524941)
     A0 = int(o0[0]) | (int(o0[1]) << 32)
     B0 = int(o0[2]) | (int(o0[3]) << 32)
     A1 = int(o1[0]) | (int(o1[1]) << 32)
