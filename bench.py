@@ -3,9 +3,12 @@
 
 Workload (BASELINE.json configs[2], "C3"): particle_1d harmonic, β = 2, Gaussian displacement σ = 0.1, Float64,
 M = 2^27 chains per GPU, StoreCallbacks energy/acceptance every 10 MC steps.  One bench "step" = one store
-interval = ONE fused launch of 10 Metropolis steps over every local chain with the callback sums reduced at its
-tail, followed (N > 1) by the NCCL all-reduce of the 3 sums.  Chains are independent, so they shard over ranks
-with no data-path collective: weak scaling, per-GPU work fixed (`--scaling strong` keeps the total at 2^27).
+interval = 10 Metropolis steps over every local chain + its callback record (Σe, Σacc/tot, count).  By default
+`--series 16` store intervals are fused into ONE launch (arianna_sweep_series: chains stay in registers across the
+16 intervals, the 16 records are reduced on the device and all-reduced (N > 1) / copied to the host together);
+`--series 1` is the one-launch-per-store path (arianna_sweep with the reduction fused at its tail).  Chains are
+independent, so they shard over ranks with no data-path collective: weak scaling, per-GPU work fixed
+(`--scaling strong` keeps the total at 2^27).
 
   python bench.py [--gpus N --steps K --warmup W]                  # our arm (one process per GPU under torchrun)
   python bench.py --impl reference [...]                           # the CPU restatement of the reference path
@@ -39,7 +42,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-chains", type=int, default=27, help="chains per GPU (weak) or in total (strong), log2")
-    ap.add_argument("--mc-steps", type=int, default=10, help="Metropolis steps fused per launch (store interval)")
+    ap.add_argument("--mc-steps", type=int, default=10, help="Metropolis steps per store interval")
+    ap.add_argument("--series", type=int, default=16, help="store intervals fused per launch (1 = one launch per store)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -148,19 +152,21 @@ def workload_config(args, world):
     return {
         "workload": "C3: particle_1d harmonic beta=2, Gaussian Displacement sigma=0.1, Metropolis + StoreCallbacks "
                     "energy/acceptance every 10 steps (BASELINE.json configs[2])",
-        "chains_per_gpu": m_local, "chains_total": m_local * world, "mc_steps_per_launch": args.mc_steps,
+        "chains_per_gpu": m_local, "chains_total": m_local * world, "mc_steps_per_store": args.mc_steps,
+        "stores_per_launch": args.series, "mc_steps_per_launch": args.mc_steps * args.series,
         "rng": "philox4x32-10 + box-muller (native mode)", "arith": args.arith,
         "l2_policy": "inputs larger than L2 (x + counters = %.0f MiB per GPU vs 126 MB L2)" % (m_local * 12 / 2 ** 20),
-        "parallelism": f"chains sharded x{world}, NCCL all-reduce of 3 doubles per store",
+        "parallelism": f"chains sharded x{world}, NCCL all-reduce of 3 doubles per store"
+                       + (f", {args.series} stores per all-reduce" if args.series > 1 else ""),
     }
 
 
-def ncu_traffic(m_local, mc_steps):
+def ncu_traffic(m_local, mc_steps, series=1):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep kernel from the committed `ncu --set full`
     capture (profiles/traffic.json, written by scripts/summarise_profile.py); only valid for the captured shape."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if t["chains"] == m_local and t["mc_steps"] == mc_steps:
+        if t["chains"] == m_local and t["mc_steps"] == mc_steps and t.get("series", 1) == series:
             return {"bytes_per_launch": t["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": 24 * m_local,
                     "source": t["source"]}
     except Exception:
@@ -193,30 +199,37 @@ def run_ours(args):
 
     m_local = chains_per_rank(args, world)
     K, W, S = args.steps, max(3, args.warmup), args.mc_steps
+    G = max(1, min(args.series, 64))                   # store intervals fused per launch
     stream = torch.cuda.Stream(device=local_rank)      # torch owns the stream; the engine launches on it
     eng = mb.CudaEnsemble(m_local, 2.0, [0.1], [1.0], seed=42, chain_offset=rank * m_local,
                           n_chains_total=m_local * world, arith=args.arith, device=local_rank,
                           stream=stream.cuda_stream)
-    sums_host = torch.empty(3, dtype=torch.float64).pin_memory()
+    sums_host = torch.empty(3 * G, dtype=torch.float64).pin_memory()
 
-    def one_step(timed_events=None):
-        """one store interval: fused sweep + tail reduction, all-reduce (N > 1), async D2H of the 3 sums."""
+    def one_launch(n, timed_events=None):
+        """n store intervals: one fused launch (+ the record fold), all-reduce (N > 1), async D2H of the 3n sums."""
         if timed_events is not None:
             timed_events[0].record(stream)
-        eng.sweep(S, reduce=True)
+        if G == 1:
+            eng.sweep(S, reduce=True)
+        else:
+            eng.sweep_series([S] * n, read=False)
         if timed_events is not None:
             timed_events[1].record(stream)
-        t = eng.callback_sums_tensor()
+        t = eng.callback_sums_tensor() if G == 1 else eng.series_tensor()
         if world > 1:
             t = t.clone()
             dist.all_reduce(t)
-        sums_host.copy_(t, non_blocking=True)
+        sums_host[:3 * n].copy_(t, non_blocking=True)
+
+    def groups(total):
+        return [min(G, total - g) for g in range(0, total, G)]
 
     with torch.cuda.stream(stream):
         eng.init_synthetic()
         fp64_peak = eng.measure_fp64_peak()
-        for _ in range(W):
-            one_step()
+        for n in groups(W):
+            one_launch(n)
         stream.synchronize()
         if world > 1:
             dist.barrier()
@@ -224,11 +237,12 @@ def run_ours(args):
         launches0 = eng.launch_count
         sampler = ClockSampler(local_rank)
         sampler.start()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        plan = groups(K)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in plan]
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record(stream)
-        for k in range(K):
-            one_step(ev[k])
+        for n, e in zip(plan, ev):
+            one_launch(n, e)
         stop.record(stream)
         stop.synchronize()
         torch.cuda.synchronize()
@@ -237,12 +251,15 @@ def run_ours(args):
             dist.barrier()
         launches = eng.launch_count - launches0
         ms_total = start.elapsed_time(stop)
-        kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        # average duration of a FULL launch (G stores) and the MC steps it covers; a ragged last group is left out
+        full = [a.elapsed_time(b) for n, (a, b) in zip(plan, ev) if n == min(G, K)]
+        kern_ms = float(np.mean(full))
+        steps_per_launch = S * min(G, K)
         tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms_total = float(tmax.item())
-        energy = float(sums_host[0] / sums_host[2])
+        energy = float(sums_host[3 * plan[-1] - 3] / sums_host[3 * plan[-1] - 1])
 
         # ---- e2e: the same job through the C ABI with HOST buffers inside the timed region --------------------
         e2e = None
@@ -256,15 +273,23 @@ def run_ours(args):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             eng.set_state_from_ptr(x_in.data_ptr())                # H2D: the job's chains, pinned host -> HBM
-            for k in range(K):
-                eng.set_params(0, 0.1)                             # the step's input: policy parameters θ = (σ)
-                eng.sweep(S, reduce=True)
-                if world > 1:
-                    t = eng.callback_sums_tensor().clone()
+            for n in plan:
+                eng.set_params(0, 0.1)                             # the launch's input: policy parameters θ = (σ)
+                if G == 1:
+                    eng.sweep(S, reduce=True)
+                    if world > 1:
+                        t = eng.callback_sums_tensor().clone()
+                        dist.all_reduce(t)
+                        vals = t.cpu().numpy()                     # D2H: the step's result (3 doubles)
+                    else:
+                        vals = eng.callback_sums()                 # D2H through arianna_callback_sums
+                elif world > 1:
+                    eng.sweep_series([S] * n, read=False)
+                    t = eng.series_tensor().clone()
                     dist.all_reduce(t)
-                    vals = t.cpu().numpy()                         # D2H: the step's result (3 doubles)
+                    vals = t.cpu().numpy()[-3:]                    # D2H: n records of 3 doubles
                 else:
-                    vals = eng.callback_sums()                     # D2H through arianna_callback_sums
+                    vals = eng.sweep_series([S] * n)[-1]           # D2H through arianna_sweep_series
             eng.get_state_to_ptr(x_out.data_ptr())                 # D2H: final chains (StoreLastFrames)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
@@ -286,17 +311,18 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        ach_tf = FLOPS_PER_CHAIN_STEP * m_local * S / (kern_ms * 1e-3) / 1e12
+        ach_tf = FLOPS_PER_CHAIN_STEP * m_local * steps_per_launch / (kern_ms * 1e-3) / 1e12
         ach_gb = BYTES_PER_CHAIN_PER_LAUNCH * m_local / (kern_ms * 1e-3) / 1e9
         roofline = {
-            "bound": "fp64", "kernel": "sweep_philox_kernel<HARMONIC,%s,single-move>" % args.arith.upper(),
+            "bound": "fp64", "kernel": "sweep_philox_kernel<HARMONIC,%s,single-move%s>" % (
+                args.arith.upper(), ",series" if G > 1 else ""),
             "achieved": ach_tf, "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": ach_tf / (fp64_peak / 1e12),
             "peak_source": "DFMA microbenchmark in this run (arianna_measure_fp64_peak; MEASURED_PEAKS.json has no "
                            "FP64 entry); nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2",
-            "flops_per_chain_step": FLOPS_PER_CHAIN_STEP, "kernel_ms": kern_ms,
-            "traffic": ncu_traffic(m_local, S),
+            "flops_per_chain_step": FLOPS_PER_CHAIN_STEP, "kernel_ms": kern_ms, "mc_steps_per_launch": steps_per_launch,
+            "traffic": ncu_traffic(m_local, S, G),
             "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
-                    "bytes_per_chain_step": BYTES_PER_CHAIN_PER_LAUNCH / S,
+                    "bytes_per_chain_step": BYTES_PER_CHAIN_PER_LAUNCH / steps_per_launch,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         }
         line = {

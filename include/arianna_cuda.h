@@ -134,6 +134,20 @@ ARIANNA_API int32_t arianna_get_params(arianna_handle *h, int32_t move_id, doubl
  * mc_step! :176-190).  Asynchronous. */
 ARIANNA_API int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags);
 
+/* A whole stretch of the schedule in one call: n_stores consecutive store intervals of K[i] Metropolis steps each,
+ * with the StoreCallbacks record (algorithms.jl:97-102: callback_energy, callback_acceptance) taken after every
+ * interval ON THE DEVICE.  Equivalent to  for i: arianna_sweep(h, K[i], ARIANNA_SWEEP_REDUCE); arianna_callback_sums
+ * but the chains stay in registers across up to ARIANNA_MAX_SERIES intervals per launch, nothing is copied to the
+ * host between stores and the multi-GPU host all-reduces the whole series at once.  records (optional, host):
+ * [n_stores][3] = (Σ e, Σ_c acc_c/tot_c, local chain count) per store, local shard; NULL = leave them on the device
+ * (arianna_series_device; asynchronous).  arianna_series_global all-reduces the device records of the LAST
+ * arianna_sweep_series call over the communicator (arianna_comm_init) and returns ensemble-wide records.
+ * Single-move pools with the native Philox stream only (ARIANNA_ERR_UNSUPPORTED otherwise: use arianna_sweep). */
+#define ARIANNA_MAX_SERIES 64
+ARIANNA_API int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t *K, double *records);
+ARIANNA_API int32_t arianna_series_device(arianna_handle *h, double **dptr, int32_t *n_doubles);
+ARIANNA_API int32_t arianna_series_global(arianna_handle *h, int32_t n_stores, double *records);
+
 /* Replay mode: the same K steps consuming caller-supplied draws instead of the native RNG, always in EXACT
  * arithmetic.  u_cat / z / u_acc are step-major [K][n_chains] (u_cat may be NULL when n_moves == 1);
  * `on_device` != 0 means the three pointers (and decisions_out) are device pointers.  decisions_out

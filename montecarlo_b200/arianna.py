@@ -198,6 +198,13 @@ class ParticleEnsemble(AriannaSystem):
         self.pool: Optional[Sequence[Move]] = None
         self.pending = 0
         self._cb_cache = None  # (steps_done, energy, acceptance)
+        # look-ahead (set by run()): the engine may execute a whole stretch of callback-only store intervals in one
+        # arianna_sweep_series call; `_ahead` = MC steps already executed beyond the driver's current time, and
+        # `_series_cache` maps "MC steps done" -> (energy, acceptance) for the stores inside that stretch
+        self._lookahead = None
+        self._ahead = 0
+        self._series_cache = {}
+        self.max_lookahead = 4096
 
     def __len__(self):
         return self.n_total
@@ -226,13 +233,62 @@ class ParticleEnsemble(AriannaSystem):
         """Run the pending Metropolis steps as one fused launch."""
         if self.engine is None:
             raise RuntimeError("no Metropolis algorithm is attached to these chains")
+        if self._ahead > 0:
+            raise RuntimeError("the device ensemble ran ahead of the schedule (look-ahead over callback-only stores) "
+                               "and something not in the plan observed or changed the chains")
         if self.pending > 0:
             self._push_params()
             self.engine.sweep(self.pending, reduce=reduce)
             self.pending = 0
             self._cb_cache = None
 
+    def _advance(self, n: int):
+        """n more Metropolis steps requested by the driver: queue them, or consume steps already run ahead."""
+        if self._ahead > 0:
+            if n > self._ahead:
+                raise RuntimeError("look-ahead plan violated: more Metropolis steps than planned")
+            self._ahead -= n
+        else:
+            self.pending += n
+
+    def _series_supported(self):
+        return (self._lookahead is not None and len(self.pool) == 1 and self.rng == "philox"
+                and hasattr(self.engine, "sweep_series"))
+
+    def _run_series(self, Ks):
+        """One arianna_sweep_series call for [pending, K_1, K_2, ...]; every record lands in the cache."""
+        self._push_params()
+        dist = _dist()
+        nm = len(self.pool)
+        if dist is not None and dist.get_world_size() > 1 and dist.get_backend() == "nccl":
+            import torch
+            self.engine.sweep_series(Ks, read=False)
+            with torch.cuda.stream(self.engine.torch_stream()):
+                rec = allreduce_sums(None, self.engine.series_tensor()).reshape(len(Ks), 3)   # ONE all-reduce
+        else:
+            rec = allreduce_sums(self.engine.sweep_series(Ks).reshape(-1)).reshape(len(Ks), 3)
+        done = self.engine.steps_done - int(sum(Ks))
+        self._series_cache = {}
+        for K, r in zip(Ks, rec):
+            done += int(K)
+            e, a = means_from_sums(r, nm)
+            self._series_cache[done] = (float(e), a)
+        self.pending = 0
+        self._ahead = int(sum(Ks[1:]))
+        self._cb_cache = None
+
     def _callbacks(self):
+        if self._ahead > 0 or (self.pending == 0 and self._series_cache):
+            hit = self._series_cache.get(self.engine.steps_done - self._ahead) if self.pending == 0 else None
+            if hit is not None:
+                return hit
+            if self._ahead > 0:
+                raise RuntimeError("look-ahead plan violated: callbacks requested at an unplanned time")
+        if self.pending > 0 and self._series_supported():
+            ahead = self._lookahead()
+            if ahead:
+                self._run_series([self.pending] + ahead)
+                return self._series_cache[self.engine.steps_done - self._ahead]
         self.flush(reduce=True)
         sd = self.engine.steps_done
         if self._cb_cache is None or self._cb_cache[0] != sd:
@@ -325,7 +381,7 @@ class AriannaAlgorithm:
 
 def mc_sweep(system: ParticleEnsemble, pool, rng=None, *, mc_steps: int = 1):
     """mc_sweep!(system, pool, rng; mc_steps) (metropolis.jl:203-212) for device-resident chains: lazy."""
-    system.pending += int(mc_steps)
+    system._advance(int(mc_steps))
 
 
 class Metropolis(AriannaAlgorithm):
@@ -608,9 +664,49 @@ class Simulation:
             f.write("\n")
 
 
+def _make_lookahead(sim: "Simulation"):
+    """Look-ahead over callback-only stores.  The schedule is known up front (sim.schedulers), so when StoreCallbacks
+    fires at time t the ensemble can run every following store interval up to the next event that observes or
+    changes the chains in any other way (trajectory frames, the PGMC estimator/update, parameter stores, ...) as ONE
+    arianna_sweep_series call.  Returns a function () -> [K_1, K_2, ...] (MC steps between the coming callback-only
+    store times, as of sim.t), or None when the algorithm list does not allow it."""
+    import bisect
+    algs = sim.algorithms
+    met = [k for k, a in enumerate(algs) if isinstance(a, Metropolis)]
+    cbs = [k for k, a in enumerate(algs) if isinstance(a, StoreCallbacks)
+           and all(cb in (callback_energy, callback_acceptance) for cb in a.callbacks)]
+    if len(met) != 1 or not cbs or min(cbs) < met[0]:
+        return None                      # callbacks listed before Metropolis see the state BEFORE the step at t
+    m = met[0]
+    passive = (Metropolis, PrintTimeSteps)
+    barriers = sorted({t for k, a in enumerate(algs) if k not in cbs and not isinstance(a, passive)
+                       for t in sim.schedulers[k]})
+    stores = sorted({t for k in cbs for t in sim.schedulers[k]})
+    msched = sorted(sim.schedulers[m])
+    step = algs[m].sweepstep
+    chains = sim.chains
+
+    def lookahead():
+        t = sim.t
+        ib = bisect.bisect_left(barriers, t)
+        tb = barriers[ib] if ib < len(barriers) else sim.steps + 1     # first barrier at or after now
+        i0 = bisect.bisect_right(stores, t)
+        out, prev = [], t
+        for ts in stores[i0:i0 + chains.max_lookahead]:
+            if ts > tb:
+                break
+            out.append(step * (bisect.bisect_right(msched, ts) - bisect.bisect_right(msched, prev)))
+            prev = ts
+        # an algorithm with store_last fires once more in finalise(), at t = steps: the stretch must not pass the end
+        return out
+
+    return lookahead
+
+
 def run(simulation: Simulation):
     """run!(simulation) (simulation.jl:175-204): initialise all, t-loop in list order, finalise in `finally`."""
     sim = simulation
+    sim.chains._lookahead = _make_lookahead(sim) if getattr(sim, "lookahead", True) else None
     try:
         for a in sim.algorithms:
             a.initialise(sim)

@@ -60,6 +60,7 @@ static const char *load(std::string &err)
 }  // namespace nccl
 
 static_assert(ARIANNA_MAX_MOVES == kMaxMoves, "header / kernel pool size mismatch");
+static_assert(ARIANNA_MAX_SERIES == kMaxSeries, "header / kernel series size mismatch");
 static_assert(sizeof(arianna_gradient_data) == 5 * sizeof(double), "gradient record layout");
 
 struct arianna_handle {
@@ -89,6 +90,10 @@ struct arianna_handle {
     m64::MathTables *d_tables = nullptr;   // exp/log tables of csrc/math64.cuh
     double *d_scratch = nullptr;    // e[] staging for get_state / dfma out
     size_t scratch_bytes = 0;
+
+    double *d_series = nullptr;     // [series_cap][3] callback records of the last arianna_sweep_series call
+    int64_t series_cap = 0, series_n = 0;
+    double *d_series_partials = nullptr;   // [max grid][kMaxSeries + 1][2]
 
     nccl::Comm comm = nullptr;      // optional: set by arianna_comm_init
     int comm_rank = 0, comm_size = 1;
@@ -356,6 +361,7 @@ int32_t arianna_destroy(arianna_handle *h)
     cudaFree(h->d_x); cudaFree(h->d_acc); cudaFree(h->d_tot); cudaFree(h->d_betas); cudaFree(h->d_rng);
     cudaFree(h->d_ki); cudaFree(h->d_wi); cudaFree(h->d_fi); cudaFree(h->d_partials); cudaFree(h->d_ticket);
     cudaFree(h->d_sums); cudaFree(h->d_gd); cudaFree(h->d_csum); cudaFree(h->d_scratch); cudaFree(h->d_tables);
+    cudaFree(h->d_series); cudaFree(h->d_series_partials);
     if (h->comm) { nccl::g_api.CommDestroy(h->comm); h->comm = nullptr; }
     cudaFree(h->d_coll);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
@@ -541,6 +547,107 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
         if (!multi && h->cfg.rng_mode == ARIANNA_RNG_PHILOX) h->sums_valid = true;  // fused at the sweep's tail
         else return launch_callback_reduce(h);
     }
+    return ARIANNA_OK;
+}
+
+// Store intervals fused per series launch.  Each interval costs kSeriesBytesPerStore (3 KB) of shared memory per CTA:
+// 16 intervals (48 KB + 6 KB) keep the sweep's 4 resident CTAs per SM; an ensemble that fits one CTA per SM anyway
+// (M <= 256 x SM count: the reference's own small-M configurations) fuses up to ARIANNA_MAX_SERIES per launch.
+static int series_per_launch(const arianna_handle *h)
+{
+    const char *e = getenv("ARIANNA_SERIES_PER_LAUNCH");   // test / tuning override
+    const int env = e ? atoi(e) : 0;
+    if (env > 0) return env < kMaxSeries ? env : kMaxSeries;
+    return h->M <= (int64_t)kBlock * h->sm_count ? kMaxSeries : 16;
+}
+
+int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t *K, double *records)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, n_stores >= 0 && (n_stores == 0 || K != nullptr), "arianna_sweep_series: bad arguments");
+    if (h->pool.n_moves != 1 || h->cfg.rng_mode != ARIANNA_RNG_PHILOX)
+        return fail(h, ARIANNA_ERR_UNSUPPORTED,
+                    "arianna_sweep_series: single-move pools with the native Philox stream only (use arianna_sweep)");
+    int64_t total = 0;
+    for (int32_t i = 0; i < n_stores; ++i) {
+        REQUIRE(h, K[i] >= 0 && K[i] < (int64_t(1) << 31), "arianna_sweep_series: K[i] must be in [0, 2^31)");
+        total += K[i];
+    }
+    REQUIRE(h, h->steps_done + total <= 0xFFFFFFFFll, "arianna_sweep_series: per-chain counters are 32-bit (2^32-1 steps max)");
+    h->series_n = 0;
+    if (n_stores == 0) return ARIANNA_OK;
+    DeviceGuard guard(h->device);
+    if (h->series_cap < n_stores) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_series);
+        h->d_series = nullptr;
+        h->series_cap = 0;
+        const int64_t cap = n_stores < 1024 ? 1024 : n_stores;
+        CU_TRY(h, cudaMalloc(&h->d_series, sizeof(double) * 3 * cap));
+        h->series_cap = cap;
+    }
+    if (!h->d_series_partials)
+        CU_TRY(h, cudaMalloc(&h->d_series_partials,
+                             sizeof(double) * 2 * (kMaxSeries + 1) * (size_t)h->sm_count * 8 * kMaxGridWaves));
+    const bool exact = h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
+    const int per_launch = series_per_launch(h);
+    for (int32_t s0 = 0; s0 < n_stores; s0 += per_launch) {
+        const int ns = n_stores - s0 < per_launch ? n_stores - s0 : per_launch;
+        SweepParams sp{};
+        sp.x = h->d_x; sp.acc = h->d_acc; sp.tot = nullptr; sp.betas = h->d_betas; sp.beta = h->cfg.beta;
+        sp.M = h->M; sp.t0 = h->steps_done;
+        sp.sid0 = (uint64_t)(h->cfg.seed + h->cfg.chain_offset);
+        sp.tables = h->d_tables;
+        sp.pool = h->pool;
+        sp.n_series = ns;
+        sp.series_partials = h->d_series_partials;
+        SeriesK sk{};
+        int64_t k_launch = 0;
+        bool even = (h->steps_done & 1) == 0;
+        for (int i = 0; i < ns; ++i) {
+            sp.series_K[i] = sk.k[i] = (int)K[s0 + i];
+            k_launch += K[s0 + i];
+            even = even && K[s0 + i] > 0 && (K[s0 + i] & 1) == 0;
+        }
+        sp.series_K[ns] = 0;
+        sp.series_even = even ? 1 : 0;
+        sp.K = k_launch;
+        const size_t smem = (size_t)ns * kSeriesBytesPerStore + sizeof(unsigned long long) * kBlock;
+        int grid = 0;
+        int32_t rc = dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
+            constexpr int POT = decltype(pot)::value;
+            auto go = [&](auto kernel) -> int32_t {
+                CU_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                grid = wave_grid(h, kernel, smem, h->M);
+                kernel<<<grid, kBlock, smem, h->stream>>>(sp);
+                return ARIANNA_OK;
+            };
+            return exact ? go(sweep_philox_kernel<POT, ARITH_EXACT, false, true>)
+                         : go(sweep_philox_kernel<POT, ARITH_FAST, false, true>);
+        });
+        if (rc) return rc;
+        CU_TRY(h, cudaGetLastError());
+        series_fold_kernel<<<ns, kBlock, 0, h->stream>>>(h->d_series_partials, grid, ns, h->steps_done, sk, h->M,
+                                                       h->d_series + 3 * (size_t)s0, h->d_sums);
+        CU_TRY(h, cudaGetLastError());
+        h->launches += 2;
+        h->steps_done += k_launch;
+    }
+    h->series_n = n_stores;
+    h->sums_valid = true;   // the last record doubles as the callback sums of the current state
+    if (records) {
+        CU_TRY(h, cudaMemcpyAsync(records, h->d_series, sizeof(double) * 3 * n_stores, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return ARIANNA_OK;
+}
+
+int32_t arianna_series_device(arianna_handle *h, double **dptr, int32_t *n_doubles)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, dptr && n_doubles, "arianna_series_device: NULL output");
+    *dptr = h->d_series;
+    *n_doubles = (int32_t)(3 * h->series_n);
     return ARIANNA_OK;
 }
 
@@ -755,6 +862,22 @@ int32_t arianna_callbacks_global(arianna_handle *h, double *mean_energy, double 
     if (mean_energy) *mean_energy = sums[0] / cnt;
     if (acc_per_move)
         for (int k = 0; k < nm; ++k) acc_per_move[k] = sums[1 + k] / cnt;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_series_global(arianna_handle *h, int32_t n_stores, double *records)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, records != nullptr && n_stores >= 0 && n_stores <= h->series_n,
+            "arianna_series_global: n_stores exceeds the last arianna_sweep_series call");
+    if (n_stores == 0) return ARIANNA_OK;
+    DeviceGuard guard(h->device);
+    // in place on the series buffer: ONE all-reduce for the whole stretch of the schedule
+    if (h->comm)
+        NCCL_TRY(h, nccl::g_api.AllReduce(h->d_series, h->d_series, (size_t)3 * n_stores, /*ncclDouble*/ 8,
+                                          /*ncclSum*/ 0, h->comm, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(records, h->d_series, sizeof(double) * 3 * n_stores, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
     return ARIANNA_OK;
 }
 

@@ -35,6 +35,8 @@ namespace arianna {
 
 constexpr int kBlock = 256;
 constexpr int kMaxMoves = 16;
+constexpr int kMaxSeries = 64;              // store intervals one series launch can fuse (host picks <= this)
+constexpr int kSeriesBytesPerStore = kBlock * (8 + 4);   // shared memory per fused interval: Σe f64 + ΣΔacc u32 per thread
 constexpr int kWarpsPerBlock = kBlock / 32;
 
 enum { POT_HARMONIC = 0, POT_QUARTIC = 1, POT_DOUBLE_WELL = 2 };
@@ -63,6 +65,11 @@ struct SweepParams {
     double *sums;           // [2 + n_moves]
     const m64::MathTables *tables;  // exp/log tables in global memory (copied to shared by every CTA)
     PoolParams pool;
+    // series mode (sweep_philox_kernel<..., SERIES = true>): n_series store intervals fused into ONE launch
+    int n_series;
+    int series_even;                // every interval is a positive even number of steps starting on an even step
+    int series_K[kMaxSeries + 1];   // MC steps of each interval (one spare slot: read past the last interval)
+    double *series_partials;        // [gridDim.x][n_series + 1][2]: (Σe, ΣΔacc) per interval, then (Σacc at entry, 0)
 };
 
 constexpr int kMaxOut = 2 + kMaxMoves;
@@ -239,13 +246,32 @@ __device__ __forceinline__ void block_reduce_and_finish(const double *vals, int 
 // K1: fused sweep, native Philox.  MULTI = pool with more than one move (categorical pick, per-move counters in
 // shared memory so that the dynamically indexed counters never spill to local memory).
 // ---------------------------------------------------------------------------------------------------------
-template <int POT, int ARITH, bool MULTI>
+//
+// SERIES (single-move pools): the launch covers n_series consecutive store intervals.  The chain stays in registers
+// across ALL of them (HBM traffic 24/(ΣK) B per chain-step, per-chain prologue paid once) and the callback sums of
+// every interval are accumulated per thread in shared memory -- Σe as f64, the accepted-count INCREMENT of the
+// interval as u32 -- then block-reduced once at the end of the launch into series_partials; series_fold_kernel
+// turns the partials into one [Σe, Σacc/t, count] record per store.  No host round trip and no second launch per
+// store: StoreCallbacks at every 10th step costs the same as one K = 10·n_series sweep.
+template <int POT, int ARITH, bool MULTI, bool SERIES = false>
 __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(const SweepParams p)
 {
-    extern __shared__ unsigned char smem_raw[];
+    static_assert(!(MULTI && SERIES), "series mode is implemented for single-move pools");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     // MULTI: [n_moves][kBlock] acc, [n_moves][kBlock] tot (u32), then sigma/weight/lognorm tables
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *s_tot = s_acc + (MULTI ? p.pool.n_moves * kBlock : 0);
+    // SERIES: [n_series][kBlock] f64 Σe, [n_series][kBlock] u32 ΣΔacc, [kBlock] u64 Σacc at entry
+    double *s_se = reinterpret_cast<double *>(smem_raw);
+    uint32_t *s_da = reinterpret_cast<uint32_t *>(s_se + (SERIES ? p.n_series * kBlock : 0));
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_da + (SERIES ? p.n_series * kBlock : 0));
+    if constexpr (SERIES) {
+        for (int s = 0; s < p.n_series; ++s) {
+            s_se[s * kBlock + threadIdx.x] = 0.0;
+            s_da[s * kBlock + threadIdx.x] = 0u;
+        }
+        s_base[threadIdx.x] = 0ull;
+    }
     __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves];
     __shared__ m64::MathTables s_T;
     if (threadIdx.x < kMaxMoves) {
@@ -262,14 +288,9 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
     unsigned long long sum_acc = 0ull;   // Σ accepted_calls: exact in integers; every chain shares tot = tend
     uint32_t cnt = 0;
     const double sigma0 = p.pool.sigma[0], lognorm0 = p.pool.lognorm[0];
-    // Steps are consumed in Box-Muller pairs (pair index = step >> 1).  A launch that starts on an odd step uses
-    // only the sine half of its first pair and one that ends on an even step only the cosine half of its last, so
-    // the result does not depend on how the steps are chunked into launches.
-    const bool lead = (p.t0 & 1) != 0;
-    const int64_t tfull = p.t0 + (lead ? 1 : 0);
-    const int npairs = (int)((tend - tfull) >> 1);
-    const bool trail = ((tend - tfull) & 1) != 0;
-    const uint64_t pair0 = (uint64_t)(p.t0 >> 1);
+    // Steps are consumed in Box-Muller pairs (pair index = step >> 1).  A run of steps [ta, tb) that starts on an odd
+    // step uses only the sine half of its first pair and one that ends on an even step only the cosine half of its
+    // last, so the result does not depend on how the steps are chunked into launches or store intervals.
 
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -357,7 +378,12 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         };
         using T_ = std::true_type;
         using F_ = std::false_type;
-        uint64_t pr = pair0;
+        auto run_steps = [&](uint32_t ta, uint32_t tb) {     // MC steps [ta, tb) of this chain; t < 2^32 (host check)
+        const bool lead = (ta & 1u) != 0;
+        const uint32_t tfull = ta + (lead ? 1u : 0u);
+        const int npairs = (int)((tb - tfull) >> 1);
+        const bool trail = ((tb - tfull) & 1u) != 0;
+        uint64_t pr = (uint64_t)(ta >> 1);
         if (lead) { do_steps(gen_pair(pr), F_{}, T_{}); ++pr; }
 #if ARIANNA_PIPE
         // Software pipeline: the draws of pair p+1 are generated while the serial accept chain of pair p runs, so
@@ -378,6 +404,44 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         for (int i = 0; i < npairs; ++i, ++pr) do_steps(gen_pair(pr), T_{}, T_{});
 #endif
         if (trail) do_steps(gen_pair(pr), T_{}, F_{});
+        };
+        if constexpr (SERIES) {
+            s_base[threadIdx.x] += acc;
+            uint32_t acc_prev = acc, ta = (uint32_t)p.t0;
+            if (p.series_even) {
+                // whole pairs only: ONE flat loop over the pairs of all intervals; a countdown marks the store points
+                // (a nested interval/pair loop makes the compiler rebuild the per-chain Philox constants in every
+                // interval's preheader: measured 6 % slower than this form)
+                double *pe = s_se + threadIdx.x;
+                uint32_t *pa = s_da + threadIdx.x;
+                const int *pk = p.series_K;
+                int left = pk[0] >> 1;
+                const uint32_t pr1 = (uint32_t)(tend >> 1);
+#pragma unroll 1
+                for (uint32_t pr = ta >> 1; pr < pr1; ++pr) {
+                    do_steps(gen_pair((uint64_t)pr), T_{}, T_{});
+                    if (--left == 0) {
+                        *pe += potential<POT, ARITH>(x);
+                        *pa += acc - acc_prev;
+                        acc_prev = acc;
+                        pe += kBlock;
+                        pa += kBlock;
+                        left = *++pk >> 1;
+                    }
+                }
+            } else
+#pragma unroll 1
+            for (int s = 0; s < p.n_series; ++s) {
+                const uint32_t tb = ta + (uint32_t)p.series_K[s];
+                run_steps(ta, tb);
+                s_se[s * kBlock + threadIdx.x] += potential<POT, ARITH>(x);   // callback_energy: e == potential(x)
+                s_da[s * kBlock + threadIdx.x] += acc - acc_prev;             // accepted within this interval
+                acc_prev = acc;
+                ta = tb;
+            }
+        } else {
+            run_steps((uint32_t)p.t0, (uint32_t)tend);
+        }
 
         p.x[c] = x;
         if constexpr (MULTI) {
@@ -395,6 +459,34 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         }
     }
 
+    if constexpr (SERIES) {
+        // one block reduction per interval, in a fixed order (deterministic for a given grid); integer-valued sums
+        // are exact in binary64 (< 2^53)
+        __shared__ double s_w[kWarpsPerBlock][2];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int s = 0; s <= p.n_series; ++s) {
+            double v0, v1;
+            if (s < p.n_series) {
+                v0 = s_se[s * kBlock + threadIdx.x];
+                v1 = (double)s_da[s * kBlock + threadIdx.x];
+            } else {
+                v0 = (double)s_base[threadIdx.x];
+                v1 = 0.0;
+            }
+            v0 = warp_sum(v0);
+            v1 = warp_sum(v1);
+            __syncthreads();
+            if (lane == 0) { s_w[warp][0] = v0; s_w[warp][1] = v1; }
+            __syncthreads();
+            if (threadIdx.x < 2) {
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < kWarpsPerBlock; ++w) t += s_w[w][threadIdx.x];
+                p.series_partials[((size_t)blockIdx.x * (p.n_series + 1) + s) * 2 + threadIdx.x] = t;
+            }
+        }
+        return;
+    }
     if constexpr (!MULTI) {
         if (p.reduce) {
             // Σ acc_c / tot == (Σ acc_c) / tot exactly in real arithmetic; the integer sum is exact in binary64 (< 2^53)
@@ -402,6 +494,44 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
             double vals[3] = {sum_e, (double)sum_acc / (double)tend, (double)cnt};
             block_reduce_and_finish<3>(vals, 3, p.partials, p.ticket, p.sums, false);
         }
+    }
+}
+
+// Series fold: CTA s turns the per-CTA partials of a series launch into the callback record of store s,
+//   out[s] = [Σ_c e_c(t_s), (Σ_c acc_c(t_s)) / t_s, M]   with  Σ acc(t_s) = Σ acc(entry) + Σ_{s' <= s} ΣΔacc(s')
+// (same definition as the fused reduction of the plain sweep: Σ_c acc_c/tot with tot == t_s for every chain).
+// The last CTA's record is also copied to `sums` so that arianna_callbacks() after a series needs no extra pass.
+struct SeriesK { int k[kMaxSeries]; };
+__global__ void __launch_bounds__(kBlock) series_fold_kernel(const double *partials, int n_ctas, int n_series,
+                                                             int64_t t0, const SeriesK series_K, int64_t M,
+                                                             double *out, double *sums)
+{
+    __shared__ double s_w[kWarpsPerBlock][2];
+    __shared__ int64_t s_t;
+    const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        int64_t t = t0;
+        for (int i = 0; i <= s; ++i) t += series_K.k[i];
+        s_t = t;
+    }
+    double e = 0.0, a = 0.0;
+    for (int b = threadIdx.x; b < n_ctas; b += kBlock) {
+        const double *row = partials + (size_t)b * (n_series + 1) * 2;
+        e += row[2 * s];
+        a += row[2 * n_series];                       // Σacc at entry
+        for (int i = 0; i <= s; ++i) a += row[2 * i + 1];
+    }
+    e = warp_sum(e);
+    a = warp_sum(a);
+    if (lane == 0) { s_w[warp][0] = e; s_w[warp][1] = a; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double te = 0.0, ta = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; ++w) { te += s_w[w][0]; ta += s_w[w][1]; }
+        const double r1 = ta / (double)s_t;
+        out[3 * s] = te; out[3 * s + 1] = r1; out[3 * s + 2] = (double)M;
+        if (s == n_series - 1 && sums) { sums[0] = te; sums[1] = r1; sums[2] = (double)M; }
     }
 }
 

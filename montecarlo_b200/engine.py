@@ -148,6 +148,30 @@ class CudaEnsemble:
         """K fused mc steps per chain (asynchronous)."""
         self._ck(self._lib.arianna_sweep(self._h, int(K), L.SWEEP_REDUCE if reduce else 0))
 
+    def sweep_series(self, Ks: Sequence[int], read: bool = True):
+        """len(Ks) consecutive store intervals of Ks[i] mc steps, the callback record taken after each ON THE DEVICE
+        (arianna_sweep_series).  read=True returns the local-shard records [n][3] = (Σe, Σ acc/tot, count);
+        read=False leaves them on the device (series_tensor / series_global)."""
+        ks = np.ascontiguousarray(Ks, dtype=np.int64)
+        rec = np.empty((ks.size, 3), dtype=np.float64) if read else None
+        self._ck(self._lib.arianna_sweep_series(self._h, int(ks.size), ks.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                _ptr(rec)))
+        return rec
+
+    def series_tensor(self):
+        """torch view (no copy) of the device records of the last sweep_series call, for ONE in-place all_reduce."""
+        import torch
+        p = C.c_void_p()
+        n = C.c_int32()
+        self._ck(self._lib.arianna_series_device(self._h, C.byref(p), C.byref(n)))
+        return torch.as_tensor(_DeviceBuffer(p.value, n.value, self.stream_ptr), device="cuda")
+
+    def series_global(self, n_stores: int):
+        """Records of the last sweep_series call all-reduced inside the library (arianna_comm_init)."""
+        rec = np.empty((int(n_stores), 3), dtype=np.float64)
+        self._ck(self._lib.arianna_series_global(self._h, int(n_stores), _ptr(rec)))
+        return rec
+
     def sweep_replay(self, u_cat, z, u_acc, want_decisions: bool = False):
         z = np.ascontiguousarray(z, dtype=np.float64)
         u_acc = np.ascontiguousarray(u_acc, dtype=np.float64)

@@ -63,7 +63,8 @@ def _val(name):
     i = hdr.index(name)
     v = float(data[0][i].replace(",", ""))
     return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[i]]
-json.dump({"chains": 1 << 27, "mc_steps": 10, "dram_bytes_per_launch": _val("dram__bytes_read.sum") + _val("dram__bytes_write.sum"),
+series = int(sys.argv[2]) if len(sys.argv) > 2 else 16   # store intervals per launch of the profiled bench.py run
+json.dump({"chains": 1 << 27, "mc_steps": 10, "series": series, "dram_bytes_per_launch": _val("dram__bytes_read.sum") + _val("dram__bytes_write.sum"),
            "source": f"profiles/{tag}_sweep_ncu_summary.md (ncu --set full, bench.py default shape)"},
           open(os.path.join(out_dir, "traffic.json"), "w"))
 
@@ -82,7 +83,7 @@ if os.path.exists(lc):
             agg[name][0] += 1
             agg[name][1] += v
     total = sum(v[1] for v in agg.values())
-    out = [f"# launch list ({tag}): ncu --metrics gpu__time_duration.sum --clock-control none over `bench.py --steps 12 --warmup 3`", "",
+    out = [f"# launch list ({tag}): ncu --metrics gpu__time_duration.sum --clock-control none over `bench.py --steps 32 --warmup 16`", "",
            "Per-launch times are cold-cache and serialised under the profiler: compare SHARES, not absolutes.", "",
            "| kernel | launches | total ms | share |", "|---|---|---|---|"]
     for k, (n, ms) in sorted(agg.items(), key=lambda t: -t[1][1]):

@@ -56,6 +56,19 @@ class OracleEngine:
             self.steps_done += K
             self.launch_count += 1
 
+    def sweep_series(self, Ks, read=True):
+        """arianna_sweep_series: len(Ks) store intervals in ONE call (counted as one launch), a record after each."""
+        if self.n_moves != 1:
+            raise RuntimeError("sweep_series: single-move pools only")
+        n0 = self.launch_count
+        rec = np.empty((len(Ks), 3))
+        for i, K in enumerate(Ks):
+            self.sweep(int(K))
+            rec[i] = self.callback_sums()
+        self.launch_count = n0 + 1
+        self.series_calls = getattr(self, "series_calls", 0) + 1
+        return rec
+
     def callback_sums(self):
         with np.errstate(all="ignore"):
             r = (self.ens.acc / self.ens.tot).sum(axis=1)

@@ -228,6 +228,84 @@ def test_callbacks_fused_and_standalone_match_oracle():
             assert abs(ma[0] / ref.callback_acceptance()[0] - 1) < 1e-12
 
 
+@pytest.mark.parametrize("arith", ["exact", "fast"])
+@pytest.mark.parametrize("per_launch", [0, 3])
+@pytest.mark.parametrize("even", [False, True])
+def test_series_equals_per_store_sweeps(arith, per_launch, even, monkeypatch):
+    """arianna_sweep_series == the loop [arianna_sweep(K_i, REDUCE); arianna_callback_sums] it replaces: identical
+    chain states and counters (the draws are a pure function of (chain, step)), records equal up to the summation
+    order, and equal to the oracle's callback_energy / callback_acceptance after every interval.  Odd interval
+    lengths exercise store boundaries that split a Box-Muller pair."""
+    if per_launch:
+        monkeypatch.setenv("ARIANNA_SERIES_PER_LAUNCH", str(per_launch))
+    M, seed = 70001, 11
+    Ks = [10, 1, 7, 10, 10, 3, 0, 12, 5, 10, 10, 10, 9, 10, 11, 10, 10, 2, 10, 10]      # 20 stores > 16 per launch
+    pre = 3                                                         # the series starts on an odd step
+    if even:                                                        # whole-pair intervals: the flat-loop fast path
+        Ks, pre = [10, 2, 8, 10, 10, 4, 6, 12, 4, 10, 10, 10, 8, 10, 12, 10, 10, 2, 10, 10], 4
+    x0 = O.init_synthetic(seed, 0, M)
+    ref = O.Ensemble(x0, 2.0, [0.1])
+    with mb.CudaEnsemble(M, 2.0, [0.1], seed=seed, arith=arith) as a, \
+            mb.CudaEnsemble(M, 2.0, [0.1], seed=seed, arith=arith) as b:
+        a.init_synthetic(); b.init_synthetic()
+        a.sweep(pre); b.sweep(pre)
+        rec = a.sweep_series(Ks)
+        assert rec.shape == (len(Ks), 3) and a.steps_done == pre + sum(Ks)
+        _, z, ua = O.draws_philox(seed, 0, M, 0, pre, with_cat=False)
+        ref.sweep_replay(None, z, ua)
+        done = pre
+        for i, K in enumerate(Ks):
+            b.sweep(K, reduce=True)
+            sb = b.callback_sums()
+            np.testing.assert_allclose(rec[i], sb, rtol=1e-13, err_msg=f"store {i}")
+            assert rec[i, 2] == M
+            if K:
+                _, z, ua = O.draws_philox(seed, 0, M, done, K, with_cat=False)
+                ref.sweep_replay(None, z, ua)
+                done += K
+            assert abs(rec[i, 0] / M / ref.callback_energy() - 1) < 1e-12
+            assert abs(rec[i, 1] / M / ref.callback_acceptance()[0] - 1) < 1e-12
+        assert np.array_equal(a.get_state(), b.get_state())
+        assert np.array_equal(a.chain_counters()[0], b.chain_counters()[0])
+        assert np.max(np.abs(a.get_state() - ref.x)) < 1e-12
+        assert np.array_equal(a.chain_counters()[0][0].astype(np.int64), ref.acc[0])
+        # the last record doubles as the current callback sums
+        np.testing.assert_array_equal(a.callback_sums(), rec[-1])
+        me, ma = a.callbacks()
+        assert abs(me / ref.callback_energy() - 1) < 1e-12
+        # records can stay on the device (one all-reduce for the whole stretch) and be fetched later
+        a.sweep_series([4, 4], read=False)
+        b.sweep(4, reduce=True); s1 = b.callback_sums(); b.sweep(4, reduce=True); s2 = b.callback_sums()
+        np.testing.assert_allclose(a.series_global(2), np.stack([s1, s2]), rtol=1e-13)
+
+
+def test_series_small_ensemble_and_errors():
+    """M = 10 (BASELINE config 1's width): up to ARIANNA_MAX_SERIES stores per launch; multi-move pools refuse."""
+    M, seed = 10, 42
+    x0 = O.init_synthetic(seed, 0, M)
+    ref = O.Ensemble(x0, 2.0, [0.1])
+    Ks = [1000] + [10] * 150
+    with mb.CudaEnsemble(M, 2.0, [0.1], seed=seed, arith="fast") as eng:
+        eng.init_synthetic()
+        n0 = eng.launch_count
+        rec = eng.sweep_series(Ks)
+        assert eng.launch_count - n0 == 2 * math.ceil(len(Ks) / 64)
+        done = 0
+        for i, K in enumerate(Ks):
+            _, z, ua = O.draws_philox(seed, 0, M, done, K, with_cat=False)
+            ref.sweep_replay(None, z, ua)
+            done += K
+            assert abs(rec[i, 0] / M / ref.callback_energy() - 1) < 1e-11
+            assert abs(rec[i, 1] / M / ref.callback_acceptance()[0] - 1) < 1e-12
+        assert eng.sweep_series([]).shape == (0, 3)
+        with pytest.raises(mb.AriannaError):
+            eng.sweep_series([-1])
+    with mb.CudaEnsemble(M, 2.0, [0.1, 0.2], seed=seed) as eng:
+        with pytest.raises(mb.AriannaError) as ei:
+            eng.sweep_series([10])
+        assert ei.value.code == 4                                   # ARIANNA_ERR_UNSUPPORTED
+
+
 def test_multi_move_acceptance_is_mean_of_ratios_with_nan():
     M, seed, K = 5000, 8, 3                                       # after 3 steps some chain has never tried move 7
     sigma, weight = [0.2] * 7, [0.4] + [0.1] * 6

@@ -201,6 +201,86 @@ def test_run_matches_stepwise_oracle_and_fuses_steps(tmp_path, fake_engine):
     assert "Metropolis" in open(tmp_path / "summary.log").read()
 
 
+def _callbacks_only_setup(path, M=48, steps=400, burn=100, traj_every=None):
+    seed = 42
+    chains = mb.ParticleEnsemble(O.init_synthetic(seed, 0, M), 2.0)
+    pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.1), 1.0),)
+    sampletimes = mb.build_schedule(steps, burn, 10)
+    algorithm_list = [
+        dict(algorithm=mb.Metropolis, pool=pool, seed=seed, parallel=False),
+        dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance), scheduler=sampletimes),
+        dict(algorithm=mb.PrintTimeSteps, scheduler=mb.build_schedule(steps, burn, steps // 10)),
+    ]
+    if traj_every:
+        algorithm_list.append(dict(algorithm=mb.StoreTrajectories, scheduler=mb.build_schedule(steps, burn, traj_every)))
+    return chains, sampletimes, mb.Simulation(chains, tuple(algorithm_list), steps, path=str(path))
+
+
+def test_lookahead_fuses_callback_only_stores(tmp_path, fake_engine):
+    """The schedule is known up front: run() lets the ensemble execute every callback-only store interval up to the
+    next event that needs the chains themselves as ONE arianna_sweep_series call.  Output files are byte-identical
+    to the one-launch-per-store path; trajectory frames act as barriers and still see the state at THEIR time."""
+    for traj_every in (None, 70):
+        a, b = tmp_path / f"look{traj_every}", tmp_path / f"plain{traj_every}"
+        ca, st, sa = _callbacks_only_setup(a, traj_every=traj_every)
+        mb.run(sa)
+        cb, _, sb = _callbacks_only_setup(b, traj_every=traj_every)
+        sb.lookahead = False
+        mb.run(sb)
+        assert cb.engine.launch_count >= len(st) and not hasattr(cb.engine, "series_calls")
+        for name in ("energy.dat", "acceptance.dat"):
+            assert open(a / name).read() == open(b / name).read()
+        assert np.array_equal(ca.engine.get_state(), cb.engine.get_state())
+        assert ca.engine.steps_done == cb.engine.steps_done == 400
+        if traj_every is None:
+            assert ca.engine.series_calls == 1 and ca.engine.launch_count == 1     # the whole run in one call
+        else:
+            ta = mb.StoreTrajectories.read_binary(str(a / "trajectories" / "rank0.bin"), 48)
+            tb = mb.StoreTrajectories.read_binary(str(b / "trajectories" / "rank0.bin"), 48)
+            assert np.array_equal(ta[0], tb[0]) and np.array_equal(ta[1], tb[1])
+            assert 1 < ca.engine.series_calls <= len(ta[0]) + 1 and ca.engine.launch_count < cb.engine.launch_count / 3
+    # a bounded look-ahead window chunks the stretch
+    ca, st, sa = _callbacks_only_setup(tmp_path / "win")
+    ca.max_lookahead = 7
+    mb.run(sa)
+    assert ca.engine.series_calls == math.ceil(len(st) / 8)
+    assert open(tmp_path / "win" / "energy.dat").read() == open(tmp_path / "lookNone" / "energy.dat").read()
+
+
+def test_lookahead_refuses_unplanned_observation(tmp_path, fake_engine):
+    chains, st, sim = _callbacks_only_setup(tmp_path)
+    seen = []
+
+    class Peek(A.AriannaAlgorithm):                        # an algorithm run() knows nothing about: a barrier
+        def __init__(self, chains, **extras):
+            pass
+
+        def make_step(self, simulation):
+            seen.append(simulation.chains.x.copy())
+
+    sim2 = mb.Simulation(chains.__class__(O.init_synthetic(42, 0, 48), 2.0), (
+        dict(algorithm=mb.Metropolis, pool=(mb.Move(mb.Displacement(0.0), mb.StandardGaussian(),
+                                                    mb.ComponentArray(σ=0.1), 1.0),), seed=42),
+        dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy,), scheduler=st),
+        dict(algorithm=Peek, scheduler=[155, 300]),
+    ), 400, path=str(tmp_path / "peek"))
+    mb.run(sim2)
+    assert len(seen) == 2 and sim2.chains.engine.steps_done == 400
+    ref = O.Ensemble(O.init_synthetic(42, 0, 48), 2.0, [0.1])
+    _, z, ua = O.draws_philox(42, 0, 48, 0, 155, with_cat=False)
+    ref.sweep_replay(None, z, ua)
+    assert np.array_equal(seen[0], ref.x)                 # the barrier saw the chains at t = 155, not run ahead
+    # an observation that is NOT in the schedule while the device is ahead fails loudly instead of lying
+    chains3, st3, sim3 = _callbacks_only_setup(tmp_path / "bad")
+    chains3._lookahead = A._make_lookahead(sim3)
+    sim3.t = st3[0]
+    chains3._advance(st3[0])
+    mb.callback_energy(sim3)
+    assert chains3._ahead > 0
+    with pytest.raises(RuntimeError):
+        chains3.x
+
+
 def test_simulation_constructor_contract(tmp_path, fake_engine):
     chains = mb.ParticleEnsemble(np.zeros(4), 2.0)
     pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.1), 1.0),)
