@@ -4,8 +4,9 @@
 Workload (BASELINE.json configs[2], "C3"): particle_1d harmonic, β = 2, Gaussian displacement σ = 0.1, Float64,
 M = 2^27 chains per GPU, StoreCallbacks energy/acceptance every 10 MC steps.  One bench "step" = one store
 interval = 10 Metropolis steps over every local chain + its callback record (Σe, Σacc/tot, count).  By default
-`--series 16` store intervals are fused into ONE launch (arianna_sweep_series: chains stay in registers across the
-16 intervals, the 16 records are reduced on the device and all-reduced (N > 1) / copied to the host together);
+the engine's preferred number of store intervals (11 on B200) is fused into ONE launch (arianna_sweep_series: chains
+stay in registers across the intervals, the records are reduced on the device and all-reduced (N > 1) / copied to
+the host together);
 `--series 1` is the one-launch-per-store path (arianna_sweep with the reduction fused at its tail).  Chains are
 independent, so they shard over ranks with no data-path collective: weak scaling, per-GPU work fixed
 (`--scaling strong` keeps the total at 2^27).
@@ -38,12 +39,13 @@ BYTES_PER_CHAIN_PER_LAUNCH = 24.0     # x f64 read+write, acc u32 read+write
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=110)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-chains", type=int, default=27, help="chains per GPU (weak) or in total (strong), log2")
     ap.add_argument("--mc-steps", type=int, default=10, help="Metropolis steps per store interval")
-    ap.add_argument("--series", type=int, default=16, help="store intervals fused per launch (1 = one launch per store)")
+    ap.add_argument("--series", type=int, default=0,
+                    help="store intervals fused per launch (0 = the engine's preferred count, 1 = one launch per store)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -199,11 +201,13 @@ def run_ours(args):
 
     m_local = chains_per_rank(args, world)
     K, W, S = args.steps, max(3, args.warmup), args.mc_steps
-    G = max(1, min(args.series, 64))                   # store intervals fused per launch
     stream = torch.cuda.Stream(device=local_rank)      # torch owns the stream; the engine launches on it
     eng = mb.CudaEnsemble(m_local, 2.0, [0.1], [1.0], seed=42, chain_offset=rank * m_local,
                           n_chains_total=m_local * world, arith=args.arith, device=local_rank,
                           stream=stream.cuda_stream)
+    G = args.series if args.series > 0 else eng.series_per_launch    # store intervals fused per launch
+    G = max(1, min(G, 64))
+    args.series = G
     sums_host = torch.empty(3 * G, dtype=torch.float64).pin_memory()
 
     def one_launch(n, timed_events=None):

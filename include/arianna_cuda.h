@@ -147,6 +147,9 @@ ARIANNA_API int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags);
 ARIANNA_API int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t *K, double *records);
 ARIANNA_API int32_t arianna_series_device(arianna_handle *h, double **dptr, int32_t *n_doubles);
 ARIANNA_API int32_t arianna_series_global(arianna_handle *h, int32_t n_stores, double *records);
+/* How many store intervals one launch of arianna_sweep_series fuses for this ensemble (longer series are chunked):
+ * callers that can choose the length of a stretch should use a multiple of it. */
+ARIANNA_API int32_t arianna_series_per_launch(arianna_handle *h, int32_t *n);
 
 /* Replay mode: the same K steps consuming caller-supplied draws instead of the native RNG, always in EXACT
  * arithmetic.  u_cat / z / u_acc are step-major [K][n_chains] (u_cat may be NULL when n_moves == 1);

@@ -73,6 +73,7 @@ struct arianna_handle {
     double *d_snap = nullptr;             // device snapshot of x the copy stream reads from
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t hbm_bytes = 0;
+    size_t smem_per_sm = 0;
     int grid = 0;        // grid of the light streaming kernels: 8 CTAs per SM x SM count
 
     int64_t M = 0;
@@ -288,6 +289,7 @@ int32_t arianna_create(const arianna_config *cfg, arianna_handle **out)
     h->cc_major = prop.major;
     h->cc_minor = prop.minor;
     h->hbm_bytes = prop.totalGlobalMem;
+    h->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (prop.major != 10)
         return bail(ARIANNA_ERR_UNSUPPORTED, "arianna_create: this library is built for sm_100a (B200) only");
     // persistent-style grid: 8 resident CTAs of 256 threads per SM cover the 64-warp SM limit
@@ -550,15 +552,36 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
     return ARIANNA_OK;
 }
 
-// Store intervals fused per series launch.  Each interval costs kSeriesBytesPerStore (3 KB) of shared memory per CTA:
-// 16 intervals (48 KB + 6 KB) keep the sweep's 4 resident CTAs per SM; an ensemble that fits one CTA per SM anyway
-// (M <= 256 x SM count: the reference's own small-M configurations) fuses up to ARIANNA_MAX_SERIES per launch.
+// Store intervals fused per series launch.  Each interval costs kSeriesBytesPerStore (3 KB) of shared memory per CTA
+// on top of the kernel's static tables (~19 KB, mostly the sin/cos directions): as many intervals as keep the
+// sweep's 4 resident CTAs per SM (11 on B200's 228 KB); an ensemble that fits one CTA per SM anyway (M <= 256 x SM
+// count: the reference's own small-M configurations) fuses up to ARIANNA_MAX_SERIES per launch.
 static int series_per_launch(const arianna_handle *h)
 {
     const char *e = getenv("ARIANNA_SERIES_PER_LAUNCH");   // test / tuning override
     const int env = e ? atoi(e) : 0;
     if (env > 0) return env < kMaxSeries ? env : kMaxSeries;
-    return h->M <= (int64_t)kBlock * h->sm_count ? kMaxSeries : 16;
+    if (h->M <= (int64_t)kBlock * h->sm_count) return kMaxSeries;
+    cudaFuncAttributes fa{};
+    size_t stat = 20 * 1024;
+    if (cudaFuncGetAttributes(&fa, sweep_philox_kernel<POT_HARMONIC, ARITH_FAST, false, true>) == cudaSuccess)
+        stat = fa.sharedSizeBytes;
+    else
+        cudaGetLastError();
+    const long per_cta = (long)(h->smem_per_sm / ARIANNA_MINB) - 1024 - (long)stat - (long)(sizeof(unsigned long long) * kBlock);
+    long n = per_cta / kSeriesBytesPerStore;
+    if (n < 1) n = 1;
+    if (n > 16) n = 16;
+    return (int)n;
+}
+
+int32_t arianna_series_per_launch(arianna_handle *h, int32_t *n)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, n != nullptr, "arianna_series_per_launch: NULL output");
+    DeviceGuard guard(h->device);
+    *n = series_per_launch(h);
+    return ARIANNA_OK;
 }
 
 int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t *K, double *records)

@@ -924,7 +924,7 @@ __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const doub
         if (kind == 0) out[i] = m64::exp_nonpos(a[i], s_T.exp2_j);
         else if (kind == 1) out[i] = m64::neg2log_u53(b[i], s_T.log_rc, s_T.log_m2lc, s_T.e_m2ln2);
         else if (kind == 2) out[i] = m64::sqrt_pos(a[i]);
-        else if (kind == 3) m64::sincos_turn53(b[i], out[2 * i], out[2 * i + 1]);
+        else if (kind == 3) m64::sincos_turn53_tab((uint32_t)(b[i] >> 32), (uint32_t)b[i], s_T.sincos, out[2 * i], out[2 * i + 1]);
         else if (kind == 4) m64::box_muller_u64(b[i], cc[i], &s_T, out[2 * i], out[2 * i + 1]);
         else if (kind == 6 || kind == 7) {
             // Philox4x32-10 block (sid = b, p = c): 6 = per-chain hoisted form (sub 0), 7 = general form, sub = a

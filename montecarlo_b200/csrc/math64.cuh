@@ -7,7 +7,7 @@
 //   exp_core / exp_accept / exp_nonpos   exp for the accept test / PGMC α      11 FP64, 1 table load, integer range checks
 //   neg2log_u53(n)       −2·ln(n·2^-53), n ∈ [1, 2^53)  (Box-Muller radius²)   10 FP64, 3 table loads
 //   sqrt_pos(w)          √w, w > 0 normal                                       6 FP64 + 1 MUFU.RSQ64H
-//   sincos_turn53(k,…)   sin/cos(2π·k·2^-53), k ∈ [0, 2^53)                    18 FP64, integer quadrant reduction
+//   sincos_turn53_tab    sin/cos(2π·k·2^-53), k ∈ [0, 2^53)                    12 FP64, one 16-byte table load (1024 directions)
 //
 // Accuracy target: ≤ 2 ulp (validated against long-double references on the host, tests/test_math64.py, and on
 // the device through arianna_debug_math, tests/test_gpu_math.py).  Every function is also compilable for the host
@@ -123,16 +123,19 @@ AM_CONST double kSinK[6] = {1.58969099521155010221e-10, -2.50507602534068634195e
                             -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};
 AM_CONST double kCosK[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
                             2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+AM_CONST double kTrigK[3] = {1.0 / 120.0, -1.0 / 6.0, 1.0 / 24.0};
 AM_CONST double kTurnK[2] = {0x1.921fb54442d18p-51,  // 2π·2^-53
                              6755399441055744.0};    // 1.5·2^52
 
 // ---- tables (filled on the host once, copied to shared memory by each CTA) ---------------------------------
+constexpr int kTrigTab = 1024; // directions of the full circle held as (sin, cos) pairs
 constexpr int kLogTab = 128;  // mantissa intervals of [√½, √2)
 constexpr int kExpTab = 32;   // 2^(j/32)
 constexpr int kETab = 64;     // −2·E·ln2 for E = 0 … −53
 constexpr uint32_t kHxBase = 0x3fe6a09eu;  // high word of √½ (fdlibm's log reduction constant)
 
-struct MathTables {
+struct alignas(16) MathTables {
+    double sincos[kTrigTab][2]; // (sin, cos)(2π·i/1024), correctly rounded; exact 0 / ±1 on the axes
     double log_rc[kLogTab];    // 1 / c_i (c_i: centre of mantissa interval i; exactly 1.0 for the interval holding 1)
     double log_m2lc[kLogTab];  // −2·ln(c_i) == +2·ln(rc_i), computed from the ROUNDED rc_i
     double e_m2ln2[kETab];     // −2·E·ln2, index −E
@@ -153,6 +156,17 @@ static inline void build_math_tables(MathTables &T)
         const double rc = (double)(1.0L / (long double)c);
         T.log_rc[i] = rc;
         T.log_m2lc[i] = (c == 1.0) ? 0.0 : (double)(2.0L * __builtin_logl((long double)rc));
+    }
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int j = 0; j < kTrigTab / 4; ++j) {
+        // first quadrant from the library, the other three by exact rotation (so the axes hold exact 0 / ±1)
+        const double sj = j == 0 ? 0.0 : (double)__builtin_sinl(two_pi * j / kTrigTab);
+        const double cj = j == 0 ? 1.0 : (double)__builtin_cosl(two_pi * j / kTrigTab);
+        const int q = kTrigTab / 4;
+        T.sincos[j][0] = sj;          T.sincos[j][1] = cj;
+        T.sincos[j + q][0] = cj;      T.sincos[j + q][1] = -sj;
+        T.sincos[j + 2 * q][0] = -sj; T.sincos[j + 2 * q][1] = -cj;
+        T.sincos[j + 3 * q][0] = -cj; T.sincos[j + 3 * q][1] = sj;
     }
     for (int e = 0; e < kETab; ++e) T.e_m2ln2[e] = (double)(2.0L * e * 0.693147180559945309417232121458176568L);
     for (int j = 0; j < kExpTab; ++j) T.exp2_j[j] = (double)__builtin_exp2l((long double)j / 32.0L);
@@ -394,6 +408,35 @@ AM_FN void sincos_turn53(uint64_t k, double &sn, double &cs)
     sn = hilo2double(double2hi(ss) ^ (neg_s << 31), double2lo(ss));
 }
 
+// Table form used by the sweep: the circle is cut into 1024 directions a_i = 2π·i/1024 held as correctly rounded
+// (sin, cos) pairs in shared memory; k = i·2^43 + rem with |rem| ≤ 2^42, φ = 2π·rem·2^-53, |φ| ≤ π/1024, so
+//   sin φ = φ + φ³(−1/6 + φ²/120)              (truncation φ⁶/5040 ≈ 2·10^-19 relative)
+//   cos φ − 1 = φ²(−1/2 + φ²/24)               (truncation φ⁶/720 ≈ 10^-18)
+//   sin(a+φ) = fma(C, sin φ, fma(S, cos φ − 1, S)),  cos(a+φ) = fma(−S, sin φ, fma(C, cos φ − 1, C)).
+// 12 FP64 instructions + one 16-byte shared load instead of 18 FP64 + ~20 integer/select instructions of the
+// quadrant-reduced polynomial form above (no quadrant swap, no sign fix-up, four polynomial constants instead of
+// twelve).  Error ≤ 0.5 ulp (table) + 0.5 ulp (inner fma) + 0.5 ulp (outer fma); exact on the axes (S or C = 0, ±1).
+AM_FN void sincos_turn53_tab(uint32_t k_hi, uint32_t k_lo, const double (*tab)[2], double &sn, double &cs)
+{
+    const uint32_t kk = k_hi + (1u << 10);                 // k + 2^42: round to the nearest direction
+    const uint32_t i = (kk >> 11) & (uint32_t)(kTrigTab - 1);
+    // rem = ((kk & 0x7ff) − 0x400)·2^32 + k_lo, converted exactly: bits(1.5·2^52) + rem, minus 1.5·2^52
+    const double d = hilo2double(0x43380000u - 0x400u + (kk & 0x7ffu), k_lo) - kTurnK[1];
+    const double phi = d * kTurnK[0];
+    const double z = phi * phi;
+    const double ps = fma64(z, kTrigK[0], kTrigK[1]);      // 1/120, −1/6
+    const double sphi = fma64(z * phi, ps, phi);
+    const double cm1 = fma64(z, kTrigK[2], -0.5) * z;      // 1/24
+#if AM_DEV
+    const double2 t = *reinterpret_cast<const double2 *>(tab[i]);
+    const double S = t.x, C = t.y;
+#else
+    const double S = tab[i][0], C = tab[i][1];
+#endif
+    sn = fma64(C, sphi, fma64(S, cm1, S));
+    cs = fma64(-S, sphi, fma64(C, cm1, C));
+}
+
 // Box-Muller from two raw 64-bit Philox words (B0 -> radius, B1 -> angle); same definition as the oracle:
 //   u1 = ((B0 >> 11) | 1)·2^-53 ∈ (0,1) (odd lattice: never 0 or 1, so −2 ln u1 > 0 without a special case),
 //   u2 = (B1 >> 11)·2^-53, z0 = √(−2 ln u1)·cos(2π u2), z1 = …·sin(2π u2).
@@ -403,7 +446,8 @@ AM_FN void box_muller_u64(uint64_t B0, uint64_t B1, const MathTables *T, double 
     const double w = neg2log_words(a_hi >> 11, ((a_hi << 21) | (a_lo >> 11)) | 1u, T->log_rc, T->log_m2lc, T->e_m2ln2);
     const double r = sqrt_pos(w);
     double s, c;
-    sincos_turn53(B1 >> 11, s, c);
+    const uint32_t b_lo = (uint32_t)B1, b_hi = (uint32_t)(B1 >> 32);
+    sincos_turn53_tab(b_hi >> 11, (b_hi << 21) | (b_lo >> 11), T->sincos, s, c);
     z0 = r * c;
     z1 = r * s;
 }

@@ -158,6 +158,13 @@ class CudaEnsemble:
                                                 _ptr(rec)))
         return rec
 
+    @property
+    def series_per_launch(self) -> int:
+        """Store intervals one sweep_series launch fuses for this ensemble (arianna_series_per_launch)."""
+        n = C.c_int32()
+        self._ck(self._lib.arianna_series_per_launch(self._h, C.byref(n)))
+        return n.value
+
     def series_tensor(self):
         """torch view (no copy) of the device records of the last sweep_series call, for ONE in-place all_reduce."""
         import torch

@@ -12,7 +12,8 @@ void m64_exp(const double *x, double *out, long n) { init(); for (long i = 0; i 
 void m64_neg2log(const uint64_t *k, double *out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = neg2log_u53(k[i], T.log_rc, T.log_m2lc, T.e_m2ln2); }
 void m64_neg2log_words(const uint64_t *k, double *out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = neg2log_words((uint32_t)(k[i] >> 32), (uint32_t)k[i], T.log_rc, T.log_m2lc, T.e_m2ln2); }
 void m64_sqrt(const double *x, double *out, long n) { for (long i = 0; i < n; ++i) out[i] = sqrt_pos(x[i]); }
-void m64_sincos(const uint64_t *k, double *s, double *c, long n) { for (long i = 0; i < n; ++i) sincos_turn53(k[i], s[i], c[i]); }
+void m64_sincos(const uint64_t *k, double *s, double *c, long n) { init(); for (long i = 0; i < n; ++i) sincos_turn53_tab((uint32_t)(k[i] >> 32), (uint32_t)k[i], T.sincos, s[i], c[i]); }
+void m64_sincos_poly(const uint64_t *k, double *s, double *c, long n) { for (long i = 0; i < n; ++i) sincos_turn53(k[i], s[i], c[i]); }
 void m64_box_muller(const uint64_t *b0, const uint64_t *b1, double *z0, double *z1, long n) { init(); for (long i = 0; i < n; ++i) box_muller_u64(b0[i], b1[i], &T, z0[i], z1[i]); }
 // mode 0: XOSHIRO-style word (23-bit cell, u = (w >> 11) 2^-53); mode 1: native (11-bit prefix f = w & 0x7ff,
 // refinement word r given separately)

@@ -81,6 +81,16 @@ def test_sincos_turn_accuracy(lib):
     assert np.abs(s * s + c * c - 1).max() < 5e-16
 
 
+def test_sincos_table_form_agrees_with_polynomial_form(lib):
+    """Two independent evaluations (1024-direction table + short Taylor vs quadrant reduction + fdlibm kernels)."""
+    rng = np.random.default_rng(14)
+    k = rng.integers(0, 2 ** 53, size=500000, dtype=np.uint64)
+    s, c, s2, c2 = (np.empty(k.size) for _ in range(4))
+    lib.m64_sincos(P(k), P(s), P(c), C.c_long(k.size))
+    lib.m64_sincos_poly(P(k), P(s2), P(c2), C.c_long(k.size))
+    assert np.abs(s - s2).max() <= 3.4e-16 and np.abs(c - c2).max() <= 3.4e-16
+
+
 def test_box_muller_matches_oracle_definition(lib):
     from oracle import oracle as O
     rng = np.random.default_rng(5)
