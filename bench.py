@@ -163,6 +163,23 @@ def workload_config(args, world):
     }
 
 
+def ncu_issue(m_local, mc_steps, series, chain_steps_per_s, sm_count=148, smsp=4, ghz=1.965):
+    """Issue-slot view of the same launch: warp instructions per warp-step from the committed ncu capture x the
+    measured step rate, against one instruction per SMSP per clock.  (The sweep is issue-bound: an IMAD.WIDE holds
+    the dispatch port for ~4.5 cycles, profiles/microbench.)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if t["chains"] == m_local and t["mc_steps"] == mc_steps and t.get("series", 1) == series:
+            ach = t["warp_inst_per_warp_step"] * chain_steps_per_s / 32.0
+            peak = sm_count * smsp * ghz * 1e9
+            return {"achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": ach / peak,
+                    "warp_inst_per_warp_step": t["warp_inst_per_warp_step"],
+                    "ncu_issue_active_pct": t.get("issue_active_pct"), "source": t["source"]}
+    except Exception:
+        pass
+    return None
+
+
 def ncu_traffic(m_local, mc_steps, series=1):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep kernel from the committed `ncu --set full`
     capture (profiles/traffic.json, written by scripts/summarise_profile.py); only valid for the captured shape."""
@@ -325,6 +342,7 @@ def run_ours(args):
                            "FP64 entry); nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2",
             "flops_per_chain_step": FLOPS_PER_CHAIN_STEP, "kernel_ms": kern_ms, "mc_steps_per_launch": steps_per_launch,
             "traffic": ncu_traffic(m_local, S, G),
+            "issue": ncu_issue(m_local, S, G, m_local * steps_per_launch / (kern_ms * 1e-3)),
             "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                     "bytes_per_chain_step": BYTES_PER_CHAIN_PER_LAUNCH / steps_per_launch,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},

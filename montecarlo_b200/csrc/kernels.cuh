@@ -842,19 +842,21 @@ __device__ __forceinline__ void pgmc_sample(double &x, double &e, double beta, d
         double dj = __dmul_rn(j, (alpha == 1.0) ? gf : gb);                                    // :106
         sj += j; sdj += dj; sgf += gf; sg += __dmul_rn(gf, gf);                                // :107, :68-76
     } else {
-        double delta = sigma * z;
-        double inv_s = 1.0 / sigma;
-        double gf = fma(z, z, -1.0) * inv_s;   // δ²/σ³ − 1/σ = (z² − 1)/σ
-        double xn = x + delta;
-        double en = potential<POT, ARITH_FAST>(xn);
-        double alpha = m64::exp_nonpos(beta * (e - en), exp2_j);   // = min(1, exp(·))
-        double j = delta * delta * alpha;
-        sj += j; sdj = fma(j, gf, sdj); sgf += gf; sg = fma(gf, gf, sg);
+        // FAST accumulates the σ-free quantities; pgmc_kernel applies the powers of σ once per thread:
+        //   j = δ²α = σ²·(z²α),  ∂σ log q = (z² − 1)/σ,  ∇j = j·∂σ log q = σ·(z²α)(z² − 1),  g = (z² − 1)²/σ²
+        (void)lognorm;
+        const double z2 = z * z;
+        const double w = fma(z, z, -1.0);
+        const double xn = fma(sigma, z, x);
+        const double en = potential<POT, ARITH_FAST>(xn);
+        const double alpha = m64::exp_nonpos(beta * (e - en), exp2_j);   // = min(1, exp(·))
+        const double ja = z2 * alpha;
+        sj += ja; sdj = fma(ja, w, sdj); sgf += w; sg = fma(w, w, sg);
     }
 }
 
 template <int POT, int ARITH, bool REPLAY>
-__global__ void __launch_bounds__(kBlock) pgmc_kernel(const PgmcParams p)
+__global__ void __launch_bounds__(kBlock, ARIANNA_MINB) pgmc_kernel(const PgmcParams p)
 {
     __shared__ m64::MathTables s_T;
     load_tables(&s_T, p.tables);
@@ -872,18 +874,29 @@ __global__ void __launch_bounds__(kBlock) pgmc_kernel(const PgmcParams p)
         } else {
             const uint64_t sid = p.sid0 + (uint64_t)c;
             const PhiloxChain<kTagEstimator, 0> ph(sid);
-            for (int64_t pr = p.q0 >> 1; 2 * pr < qend; ++pr) {
-                const U64Pair blk = ph.block((uint32_t)pr);
+            // samples [q0, q1) of this chain's estimator stream, two per Box-Muller pair; only the first / last pair
+            // of a launch can be split (q < 2^33, host check)
+            auto pair = [&](uint32_t pr, bool do0, bool do1) {
+                const U64Pair blk = ph.block(pr);
                 double z0, z1;
                 m64::box_muller_u64(u64_of(blk.a_lo, blk.a_hi), u64_of(blk.b_lo, blk.b_hi), &s_T, z0, z1);
-                if (2 * pr >= p.q0)
-                    pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z0, sj, sdj, sgf, sg, s_T.exp2_j);
-                if (2 * pr + 1 < qend)
-                    pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z1, sj, sdj, sgf, sg, s_T.exp2_j);
-            }
+                if (do0) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z0, sj, sdj, sgf, sg, s_T.exp2_j);
+                if (do1) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z1, sj, sdj, sgf, sg, s_T.exp2_j);
+            };
+            const bool lead = (p.q0 & 1) != 0, trail = (qend & 1) != 0;
+            uint32_t pr = (uint32_t)(p.q0 >> 1);
+            const uint32_t pr_end = (uint32_t)(qend >> 1);      // first pair that is not complete
+            if (lead) { pair(pr, false, true); ++pr; }
+#pragma unroll 1
+            for (; pr < pr_end; ++pr) pair(pr, true, true);
+            if (trail) pair(pr, true, false);
         }
         sn += (double)p.q_batch;
         if constexpr (ARITH == ARITH_EXACT) p.x[c] = x;  // perform/undo rounding drift is part of the reference
+    }
+    if constexpr (ARITH == ARITH_FAST) {   // the powers of σ factored out of pgmc_sample
+        const double s1 = p.sigma, i1 = 1.0 / p.sigma;
+        sj *= s1 * s1; sdj *= s1; sgf *= i1; sg *= i1 * i1;
     }
     double vals[5] = {sj, sdj, sgf, sg, sn};
     block_reduce_and_finish<5>(vals, 5, p.partials, p.ticket, p.gd, true);

@@ -64,7 +64,11 @@ def _val(name):
     v = float(data[0][i].replace(",", ""))
     return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[i]]
 series = int(sys.argv[2]) if len(sys.argv) > 2 else 16   # store intervals per launch of the profiled bench.py run
-json.dump({"chains": 1 << 27, "mc_steps": 10, "series": series, "dram_bytes_per_launch": _val("dram__bytes_read.sum") + _val("dram__bytes_write.sum"),
+inst = float(data[0][hdr.index("smsp__inst_executed.sum")].replace(",", ""))
+json.dump({"chains": 1 << 27, "mc_steps": 10, "series": series,
+           "warp_inst_per_warp_step": inst / ((1 << 27) / 32 * 10 * series),
+           "issue_active_pct": float(data[0][hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")]),
+           "dram_bytes_per_launch": _val("dram__bytes_read.sum") + _val("dram__bytes_write.sum"),
            "source": f"profiles/{tag}_sweep_ncu_summary.md (ncu --set full, bench.py default shape)"},
           open(os.path.join(out_dir, "traffic.json"), "w"))
 
