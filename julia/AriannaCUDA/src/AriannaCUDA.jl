@@ -17,7 +17,7 @@ using ComponentArrays
 using Libdl
 using Random
 
-export CudaEnsemble, callback_acceptance_cuda, flush!, device_positions, nccl_unique_id, comm_init!
+export CudaEnsemble, callback_acceptance_cuda, flush!, device_positions, nccl_unique_id, comm_init!, plan!
 
 const MAX_MOVES = 16
 const libarianna = Ref{String}(get(ENV, "ARIANNA_CUDA_LIB", "libarianna_cuda.so"))
@@ -71,6 +71,11 @@ mutable struct CudaEnsemble{T<:AbstractFloat} <: AriannaSystem
     cache_t::Int            # steps_done at which (energy, acceptance) were last reduced
     energy::Float64
     acceptance::Vector{Float64}
+    # look-ahead over callback-only stores (plan!): MC steps already executed beyond the driver's time, the records
+    # of the stores inside that stretch keyed by "MC steps done", and the planner closure installed by plan!
+    ahead::Int
+    series::Dict{Int,Tuple{Float64,Float64}}
+    lookahead::Any
 end
 
 function CudaEnsemble(x0::Vector{Float64}, β::Float64, pool; seed::Int=1, potential::Symbol=:harmonic,
@@ -83,7 +88,8 @@ function CudaEnsemble(x0::Vector{Float64}, β::Float64, pool; seed::Int=1, poten
                         Int32(0), Int32(arith == :exact ? 0 : 1), C_NULL)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(C_NULL, ccall((:arianna_create, libarianna[]), Int32, (Ref{AriannaConfig}, Ref{Ptr{Cvoid}}), cfg, h))
-    ens = CudaEnsemble{Float64}(h[], length(x0), β, pool, 0, -1, NaN, fill(NaN, nm))
+    ens = CudaEnsemble{Float64}(h[], length(x0), β, pool, 0, -1, NaN, fill(NaN, nm), 0,
+                                Dict{Int,Tuple{Float64,Float64}}(), nothing)
     check(ens.handle, ccall((:arianna_set_state, libarianna[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), ens.handle, x0))
     finalizer(e -> ccall((:arianna_destroy, libarianna[]), Int32, (Ptr{Cvoid},), e.handle), ens)
     return ens
@@ -111,18 +117,84 @@ Base.deepcopy_internal(e::CudaEnsemble, ::IdDict) = e
 # --- the hot path --------------------------------------------------------------------------------------------
 # mc_sweep!(system, pool, rng; mc_steps) (metropolis.jl:203-212), exported and overloadable (src/Arianna.jl:36)
 function Arianna.mc_sweep!(ens::CudaEnsemble, pool, rng; mc_steps=1)
-    ens.pending += mc_steps
+    if ens.ahead > 0                               # steps already run by a series launch (look-ahead)
+        mc_steps <= ens.ahead || error("look-ahead plan violated: more Metropolis steps than planned")
+        ens.ahead -= mc_steps
+    else
+        ens.pending += mc_steps
+    end
     return nothing
 end
 
-"Launch the pending Metropolis steps as ONE fused kernel (K = steps since the last observation)."
-function flush!(ens::CudaEnsemble; reduce::Bool=false)
+"""
+    plan!(simulation)
+
+Call once before `run!(simulation)`.  The schedule is known up front (`simulation.schedulers`), so when
+`StoreCallbacks` fires the ensemble can execute every following callback-only store interval, up to the next event
+that observes or changes the chains in any other way, as ONE `arianna_sweep_series` call (chains stay in registers
+across the intervals; one record per store is reduced on the device; one all-reduce per stretch).  Mirrors
+`montecarlo_b200/arianna.py:_make_lookahead`.  Without `plan!` every store is one fused launch (still correct).
+"""
+function plan!(simulation::Simulation)
+    ens = simulation.chains[1]
+    algs = simulation.algorithms
+    met = findall(a -> a isa Metropolis, algs)
+    cbs = findall(a -> a isa StoreCallbacks && all(cb -> nameof(cb) in (:callback_energy, :callback_acceptance_cuda), a.callbacks), algs)
+    (length(met) == 1 && !isempty(cbs) && minimum(cbs) > met[1] && length(ens.pool) == 1) || return nothing
+    passive(a) = a isa Metropolis || a isa Arianna.PrintTimeSteps
+    barriers = sort(unique(vcat([simulation.schedulers[k] for k in eachindex(algs) if !(k in cbs) && !passive(algs[k])]..., Int[])))
+    stores = sort(unique(vcat([simulation.schedulers[k] for k in cbs]...)))
+    msched = sort(simulation.schedulers[met[1]])
+    step = algs[met[1]].sweepstep
+    ens.lookahead = function ()
+        t = simulation.t
+        ib = searchsortedfirst(barriers, t)
+        tb = ib <= length(barriers) ? barriers[ib] : simulation.steps + 1
+        out, prev = Int64[], t
+        for ts in stores[searchsortedlast(stores, t)+1:end]
+            (ts > tb || length(out) >= 4096) && break
+            push!(out, step * (searchsortedlast(msched, ts) - searchsortedlast(msched, prev)))
+            prev = ts
+        end
+        return out
+    end
+    return nothing
+end
+
+"One arianna_sweep_series call for [pending, K_1, K_2, ...]; every record lands in ens.series."
+function run_series!(ens::CudaEnsemble, Ks::Vector{Int64})
+    push_params!(ens)
+    n = length(Ks)
+    rec = Matrix{Float64}(undef, 3, n)
+    check(ens.handle, ccall((:arianna_sweep_series, libarianna[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Float64}),
+                            ens.handle, n, Ks, C_NULL))
+    check(ens.handle, ccall((:arianna_series_global, libarianna[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}),
+                            ens.handle, n, rec))                      # all-reduced when a communicator is attached
+    t = Ref{Int64}(0)
+    check(ens.handle, ccall((:arianna_steps_done, libarianna[]), Int32, (Ptr{Cvoid}, Ref{Int64}), ens.handle, t))
+    done = t[] - sum(Ks)
+    empty!(ens.series)
+    for i in 1:n
+        done += Ks[i]
+        ens.series[done] = (rec[1, i] / rec[3, i], rec[2, i] / rec[3, i])
+    end
+    ens.pending, ens.ahead, ens.cache_t = 0, sum(Ks[2:end]), -1
+    return nothing
+end
+
+function push_params!(ens::CudaEnsemble)
     for (k, move) in enumerate(ens.pool)          # σ may have been mutated in place by learning_step! (learning.jl:33)
         θ = Ref(Float64(move.parameters.σ))
         lognorm = Ref(log(2π * move.parameters.σ^2) / 2)   # particle_1d.jl:53, Julia's own `log` for replay parity
         check(ens.handle, ccall((:arianna_set_params, libarianna[]), Int32,
                                 (Ptr{Cvoid}, Int32, Ref{Float64}, Int32, Ref{Float64}), ens.handle, k - 1, θ, 1, lognorm))
     end
+end
+
+"Launch the pending Metropolis steps as ONE fused kernel (K = steps since the last observation)."
+function flush!(ens::CudaEnsemble; reduce::Bool=false)
+    ens.ahead == 0 || error("the device ensemble ran ahead of the schedule and something outside the plan observed it")
+    push_params!(ens)
     if ens.pending > 0
         check(ens.handle, ccall((:arianna_sweep, libarianna[]), Int32, (Ptr{Cvoid}, Int64, UInt32),
                                 ens.handle, ens.pending, reduce ? 1 : 0))
@@ -133,8 +205,24 @@ function flush!(ens::CudaEnsemble; reduce::Bool=false)
 end
 
 function reduce_callbacks!(ens::CudaEnsemble)
-    flush!(ens; reduce=true)
     t = Ref{Int64}(0)
+    if ens.pending == 0 && !isempty(ens.series)           # a store inside a stretch that already ran
+        check(ens.handle, ccall((:arianna_steps_done, libarianna[]), Int32, (Ptr{Cvoid}, Ref{Int64}), ens.handle, t))
+        hit = get(ens.series, t[] - ens.ahead, nothing)
+        if hit !== nothing
+            ens.energy, ens.acceptance[1], ens.cache_t = hit[1], hit[2], ens.ahead == 0 ? t[] : -1
+            return nothing
+        end
+        ens.ahead == 0 || error("look-ahead plan violated: callbacks requested at an unplanned time")
+    end
+    if ens.pending > 0 && ens.lookahead !== nothing
+        Ks = ens.lookahead()
+        if !isempty(Ks)
+            run_series!(ens, vcat(Int64[ens.pending], Ks))
+            return reduce_callbacks!(ens)
+        end
+    end
+    flush!(ens; reduce=true)
     check(ens.handle, ccall((:arianna_steps_done, libarianna[]), Int32, (Ptr{Cvoid}, Ref{Int64}), ens.handle, t))
     if ens.cache_t != t[]
         e = Ref{Float64}(0.0)
