@@ -516,10 +516,12 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
             constexpr int POT = decltype(pot)::value;
             if (exact) {
                 if (multi) sweep_philox_kernel<POT, ARITH_EXACT, true><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_EXACT, true>, smem, h->M), kBlock, smem, h->stream>>>(sp);
-                else sweep_philox_kernel<POT, ARITH_EXACT, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_EXACT, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
+                else if (h->d_betas) sweep_philox_kernel<POT, ARITH_EXACT, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_EXACT, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
+                else sweep_philox_kernel<POT, ARITH_EXACT, false, false, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_EXACT, false, false, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
             } else {
                 if (multi) sweep_philox_kernel<POT, ARITH_FAST, true><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_FAST, true>, smem, h->M), kBlock, smem, h->stream>>>(sp);
-                else sweep_philox_kernel<POT, ARITH_FAST, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_FAST, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
+                else if (h->d_betas) sweep_philox_kernel<POT, ARITH_FAST, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_FAST, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
+                else sweep_philox_kernel<POT, ARITH_FAST, false, false, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_FAST, false, false, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
             }
             return 0;
         });
@@ -564,7 +566,7 @@ static int series_per_launch(const arianna_handle *h)
     if (h->M <= (int64_t)kBlock * h->sm_count) return kMaxSeries;
     cudaFuncAttributes fa{};
     size_t stat = 20 * 1024;
-    if (cudaFuncGetAttributes(&fa, sweep_philox_kernel<POT_HARMONIC, ARITH_FAST, false, true>) == cudaSuccess)
+    if (cudaFuncGetAttributes(&fa, sweep_philox_kernel<POT_HARMONIC, ARITH_FAST, false, true, false>) == cudaSuccess)
         stat = fa.sharedSizeBytes;
     else
         cudaGetLastError();
@@ -645,8 +647,11 @@ int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t 
                 kernel<<<grid, kBlock, smem, h->stream>>>(sp);
                 return ARIANNA_OK;
             };
-            return exact ? go(sweep_philox_kernel<POT, ARITH_EXACT, false, true>)
-                         : go(sweep_philox_kernel<POT, ARITH_FAST, false, true>);
+            if (h->d_betas)
+                return exact ? go(sweep_philox_kernel<POT, ARITH_EXACT, false, true, true>)
+                             : go(sweep_philox_kernel<POT, ARITH_FAST, false, true, true>);
+            return exact ? go(sweep_philox_kernel<POT, ARITH_EXACT, false, true, false>)
+                         : go(sweep_philox_kernel<POT, ARITH_FAST, false, true, false>);
         });
         if (rc) return rc;
         CU_TRY(h, cudaGetLastError());

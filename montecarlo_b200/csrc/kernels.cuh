@@ -253,7 +253,7 @@ __device__ __forceinline__ void block_reduce_and_finish(const double *vals, int 
 // interval as u32 -- then block-reduced once at the end of the launch into series_partials; series_fold_kernel
 // turns the partials into one [Σe, Σacc/t, count] record per store.  No host round trip and no second launch per
 // store: StoreCallbacks at every 10th step costs the same as one K = 10·n_series sweep.
-template <int POT, int ARITH, bool MULTI, bool SERIES = false>
+template <int POT, int ARITH, bool MULTI, bool SERIES = false, bool BETAS = true>
 __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(const SweepParams p)
 {
     static_assert(!(MULTI && SERIES), "series mode is implemented for single-move pools");
@@ -296,17 +296,28 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
     int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     // the next chain's state is fetched while the current chain runs its K serial steps (hides the HBM latency
     // that would otherwise be exposed once per chain at the top of the loop)
-    double x_next = (c < p.M) ? p.x[c] : 0.0;
-    uint32_t acc_next = (!MULTI && c < p.M) ? p.acc[c] : 0u;
+    // (a series launch runs >= 100 steps per chain: there the load latency is noise and the three prefetch registers
+    // are worth more to the loop body)
+    constexpr bool PREFETCH = !SERIES;
+    double x_next = (PREFETCH && c < p.M) ? p.x[c] : 0.0;
+    uint32_t acc_next = (PREFETCH && !MULTI && c < p.M) ? p.acc[c] : 0u;
     for (; c < p.M; c += stride) {
-        double x = x_next;
-        uint32_t acc = acc_next;
-        if (c + stride < p.M) {
-            x_next = p.x[c + stride];
-            if constexpr (!MULTI) acc_next = p.acc[c + stride];
+        double x;
+        uint32_t acc;
+        if constexpr (PREFETCH) {
+            x = x_next;
+            acc = acc_next;
+            if (c + stride < p.M) {
+                x_next = p.x[c + stride];
+                if constexpr (!MULTI) acc_next = p.acc[c + stride];
+            }
+        } else {
+            x = p.x[c];
+            acc = MULTI ? 0u : p.acc[c];
         }
         double e = potential<POT, ARITH>(x);
-        const double beta = p.betas ? p.betas[c] : p.beta;
+        // BETAS = false: β is a kernel-parameter constant (a constant-bank operand, no registers)
+        const double beta = BETAS ? (p.betas ? p.betas[c] : p.beta) : p.beta;
         const uint64_t sid = p.sid0 + (uint64_t)c;
         if constexpr (MULTI) {
             for (int k = 0; k < nm; ++k) {
@@ -412,21 +423,17 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                 // whole pairs only: ONE flat loop over the pairs of all intervals; a countdown marks the store points
                 // (a nested interval/pair loop makes the compiler rebuild the per-chain Philox constants in every
                 // interval's preheader: measured 6 % slower than this form)
-                double *pe = s_se + threadIdx.x;
-                uint32_t *pa = s_da + threadIdx.x;
-                const int *pk = p.series_K;
-                int left = pk[0] >> 1;
+                int s = 0;
+                int left = p.series_K[0] >> 1;
                 const uint32_t pr1 = (uint32_t)(tend >> 1);
 #pragma unroll 1
                 for (uint32_t pr = ta >> 1; pr < pr1; ++pr) {
                     do_steps(gen_pair((uint64_t)pr), T_{}, T_{});
                     if (--left == 0) {
-                        *pe += potential<POT, ARITH>(x);
-                        *pa += acc - acc_prev;
+                        s_se[s * kBlock + threadIdx.x] += potential<POT, ARITH>(x);
+                        s_da[s * kBlock + threadIdx.x] += acc - acc_prev;
                         acc_prev = acc;
-                        pe += kBlock;
-                        pa += kBlock;
-                        left = *++pk >> 1;
+                        left = p.series_K[++s] >> 1;
                     }
                 }
             } else
