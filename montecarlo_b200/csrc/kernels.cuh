@@ -25,6 +25,7 @@ namespace arianna {
 
 // Tuning knobs of the fused sweep (overridable for A/B builds, see scripts/ab_variants.sh):
 //   ARIANNA_MINB  resident CTAs per SM requested through __launch_bounds__ (register cap = 65536 / (256·MINB))
+//   ARIANNA_BLOCK threads per CTA (multiple of 32)
 //   ARIANNA_PIPE  1 = software-pipeline the Box-Muller/Philox work of pair p+1 over the two steps of pair p
 #ifndef ARIANNA_MINB
 #define ARIANNA_MINB 4
@@ -33,7 +34,10 @@ namespace arianna {
 #define ARIANNA_PIPE 0
 #endif
 
-constexpr int kBlock = 256;
+#ifndef ARIANNA_BLOCK
+#define ARIANNA_BLOCK 256
+#endif
+constexpr int kBlock = ARIANNA_BLOCK;
 constexpr int kMaxMoves = 16;
 constexpr int kMaxSeries = 64;              // store intervals one series launch can fuse (host picks <= this)
 constexpr int kSeriesBytesPerStore = kBlock * (8 + 4);   // shared memory per fused interval: Σe f64 + ΣΔacc u32 per thread

@@ -4,11 +4,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from montecarlo_b200._build import build_library, _HERE
 from concurrent.futures import ThreadPoolExecutor
 
-variants = [(m, p) for m in (2, 3, 4) for p in (0, 1)]
+variants = [(256, 4), (224, 4), (192, 5), (128, 7), (160, 6), (256, 3)]   # (threads per CTA, resident CTAs per SM)
+os.makedirs(os.path.join(_HERE, "ab"), exist_ok=True)
 def one(v):
-    m, p = v
-    out = os.path.join(_HERE, "ab", f"lib_m{m}_p{p}.so")
-    build_library(defines=(f"ARIANNA_MINB={m}", f"ARIANNA_PIPE={p}"), out=out)
+    b, m = v
+    out = os.path.join(_HERE, "ab", f"lib_b{b}_m{m}.so")
+    build_library(defines=(f"ARIANNA_BLOCK={b}", f"ARIANNA_MINB={m}"), out=out)
     return out
 with ThreadPoolExecutor(8) as ex:
     for o in ex.map(one, variants):

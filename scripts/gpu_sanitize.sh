@@ -11,6 +11,8 @@ for arith in ("fast", "exact"):
     for sig, w in (([0.1], [1.0]), ([0.2, 0.5, 0.9], [0.5, 0.25, 0.25])):
         with mb.CudaEnsemble(M, 2.0, sig, w, seed=3, arith=arith) as e:
             e.init_synthetic(); e.sweep(7, reduce=True); e.sweep(4); e.callbacks(); e.counters()
+            if len(sig) == 1:
+                e.sweep_series([4, 3, 6, 1]); e.sweep_series([2] * 20); e.callbacks()
             e.pgmc_estimate(3, [0]); e.pgmc_read(1); e.get_state(with_energy=True)
             x0 = e.get_state()
             uc, z, ua = O.draws_philox(3, 0, M, 0, 5)
