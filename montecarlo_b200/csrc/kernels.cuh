@@ -147,29 +147,44 @@ __device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, 
 // FAST: symmetric proposal => log q terms cancel; α > u  <=>  exp(β(e - e')) > u  because u < 1; reject restores x.
 // The accept uniform arrives as (ulo, cell, exact_u): a float cell [ulo, ulo + cell) that contains u and a callable
 // producing the exact 53-bit u on demand (see m64::exp_accept).
-template <int POT, class ExactU>
-__device__ __forceinline__ bool mc_step_fast(double &x, double &e, double beta, double sigma, double z, float ulo,
-                                             float cell, ExactU exact_u, const double *exp2_j)
+// A cell with cell < 0 carries the 11-bit prefix of the native stream in `ulo`'s bits (integer-domain filter).
+struct CellP11 { uint32_t f; };
+struct CellF { float ulo, cell; };
+
+template <class ExactU>
+__device__ __forceinline__ bool accept_in_cell(double arg, CellP11 c, ExactU exact_u, const double *exp2_j)
+{
+    return m64::exp_accept_prefix11(arg, c.f, exact_u, exp2_j);
+}
+template <class ExactU>
+__device__ __forceinline__ bool accept_in_cell(double arg, CellF c, ExactU exact_u, const double *exp2_j)
+{
+    return m64::exp_accept(arg, c.ulo, c.ulo + c.cell, exact_u, exp2_j);   // ulo + cell is exact
+}
+
+template <int POT, class Cell, class ExactU>
+__device__ __forceinline__ bool mc_step_fast(double &x, double &e, double beta, double sigma, double z, Cell cell,
+                                             ExactU exact_u, const double *exp2_j)
 {
     // e is re-derived from x (one DMUL on the idle FP64 pipe) instead of being carried through two more selects on
     // the ALU pipe, which is the busiest pipe of the sweep
     const double e0 = potential<POT, ARITH_FAST>(x);
     const double xn = fma(sigma, z, x);
     const double en = potential<POT, ARITH_FAST>(xn);
-    const bool a = m64::exp_accept(beta * (e0 - en), ulo, ulo + cell, exact_u, exp2_j);   // ulo + cell is exact
+    const bool a = accept_in_cell(beta * (e0 - en), cell, exact_u, exp2_j);
     x = a ? xn : x;
     (void)e;  // FAST never carries e: callers that need it (the fused reduction) evaluate potential(x)
     return a;
 }
 
-template <int POT, int ARITH, class ExactU>
+template <int POT, int ARITH, class Cell, class ExactU>
 __device__ __forceinline__ bool mc_step(double &x, double &e, double beta, double sigma, double lognorm, double z,
-                                        float ulo, float cell, ExactU exact_u, const double *exp2_j)
+                                        Cell cell, ExactU exact_u, const double *exp2_j)
 {
     if constexpr (ARITH == ARITH_EXACT)
         return mc_step_exact<POT>(x, e, beta, sigma, lognorm, z, exact_u(), exp2_j) != 0;
     else
-        return mc_step_fast<POT>(x, e, beta, sigma, z, ulo, cell, exact_u, exp2_j);
+        return mc_step_fast<POT>(x, e, beta, sigma, z, cell, exact_u, exp2_j);
 }
 
 // Distributions.Categorical inverse-CDF scan [EXT] (metropolis.jl:206); weights in shared memory.
@@ -361,15 +376,15 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                     const U64Pair r = philox_block<kTagMetropolis>(sid, d.pr, 1);
                     return m64::u53_prefix_refine(d.f0, r.a_lo, r.a_hi);
                 };
-                const float ulo = m64::ulo_from_prefix11(d.f0);
+                const CellP11 ulo{d.f0};
                 if constexpr (MULTI) {
                     const int k = categorical(nm, s_weight, u53(d.b2.a_lo, d.b2.a_hi));
-                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z0, ulo, 0x1p-11f,
+                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z0, ulo,
                                                        exact_u, s_T.exp2_j);
                     if (a) s_acc[k * kBlock + threadIdx.x] += 1;
                     s_tot[k * kBlock + threadIdx.x] += 1;
                 } else {
-                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, ulo, 0x1p-11f, exact_u, s_T.exp2_j))
+                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, ulo, exact_u, s_T.exp2_j))
                         ++acc;
                 }
             }
@@ -378,15 +393,15 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                     const U64Pair r = philox_block<kTagMetropolis>(sid, d.pr, 1);
                     return m64::u53_prefix_refine(d.f1, r.b_lo, r.b_hi);
                 };
-                const float ulo = m64::ulo_from_prefix11(d.f1);
+                const CellP11 ulo{d.f1};
                 if constexpr (MULTI) {
                     const int k = categorical(nm, s_weight, u53(d.b2.b_lo, d.b2.b_hi));
-                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z1, ulo, 0x1p-11f,
+                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z1, ulo,
                                                        exact_u, s_T.exp2_j);
                     if (a) s_acc[k * kBlock + threadIdx.x] += 1;
                     s_tot[k * kBlock + threadIdx.x] += 1;
                 } else {
-                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, ulo, 0x1p-11f, exact_u, s_T.exp2_j))
+                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, ulo, exact_u, s_T.exp2_j))
                         ++acc;
                 }
             }
@@ -707,16 +722,16 @@ __global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroPara
             const uint64_t uaw = g.next();  // rand(rng) = (next >> 11)·2^-53 [EXT]
             const uint32_t ua_lo = (uint32_t)uaw, ua_hi = (uint32_t)(uaw >> 32);
             auto exact_u = [&]() { return u53(ua_lo, ua_hi); };
-            const float ulo = m64::ulo_from_word23(ua_hi);
+            const CellF ulo{m64::ulo_from_word23(ua_hi), 0x1p-23f};
             if constexpr (MULTI) {
                 const int k = categorical(nm, s_weight, uc);
-                const bool d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], zz, ulo, 0x1p-23f, exact_u,
+                const bool d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], zz, ulo, exact_u,
                                                    s_exp2);
                 if (d) s_acc[k * kBlock + threadIdx.x] += 1;
                 s_tot[k * kBlock + threadIdx.x] += 1;
             } else {
                 (void)uc;
-                if (mc_step<POT, ARITH>(x, e, beta, s_sigma[0], s_lognorm[0], zz, ulo, 0x1p-23f, exact_u, s_exp2))
+                if (mc_step<POT, ARITH>(x, e, beta, s_sigma[0], s_lognorm[0], zz, ulo, exact_u, s_exp2))
                     ++acc;
             }
         }
@@ -961,7 +976,7 @@ __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const doub
             const uint32_t f = (uint32_t)b[i] & 0x7ffu;
             const uint64_t r = cc[i];
             auto exact_u = [&]() { return m64::u53_prefix_refine(f, (uint32_t)r, (uint32_t)(r >> 32)); };
-            out[2 * i] = m64::exp_accept(a[i], m64::ulo_from_prefix11(f), m64::ulo_from_prefix11(f) + 0x1p-11f, exact_u, s_T.exp2_j) ? 1.0 : 0.0;
+            out[2 * i] = m64::exp_accept_prefix11(a[i], f, exact_u, s_T.exp2_j) ? 1.0 : 0.0;
             out[2 * i + 1] = m64::exp_accept_ref(a[i], exact_u(), s_T.exp2_j) ? 1.0 : 0.0;
         }
     }

@@ -276,6 +276,43 @@ AM_FN bool exp_accept(double x, float ulo, float uhi, ExactU exact_u, const doub
     return acc;
 }
 
+// The same decision for the native stream, where u is known through its 11-bit PREFIX f (u ∈ [f, f+1)·2^-11): the
+// comparison is done in the integer domain, so no float cell has to be assembled from f (5 ALU instructions per step)
+// and the error bound is a constant (no per-step FFMA):
+//   Es ≈ 2^11·exp(x) from MUFU.EX2(a·log2e + 11);  floor(Es(1−ε)) ≥ f+1 accepts,  floor(Es(1+ε)) < f rejects,
+//   ε = 2^-13.  Valid for −127 ≤ a < 0: |Es/(2^11 e^x) − 1| ≤ 2^-24|a| (a = RN32(x)) + 2^-25|a| (log2e) + 2^-17·ln2
+//   (rounding of the fma at |y'| < 256) + 2^-22 (EX2) + 2^-24 (the ε multiply) < 2^-15.6, a 6x margin.  a < −127:
+//   Es = 0 (the EX2 argument is below −172, flushed), which rejects every f ≥ 1 — correct because
+//   exp(x) < 2^-183 < 2^-11 ≤ u — and sends f = 0 to the exact path.  a ≥ 0 (incl. −0, +inf) accepts: α = 1 > u.
+//   NaN: every float comparison is false and the float->int conversion gives 0: f ≥ 1 rejects here, f = 0 rejects in
+//   the exact path -- min(1, NaN) > u is false in the reference too.
+// The two F2I run on the XU pipe, which idles beside the issue-bound sweep (17 % busy).
+AM_FN int float2int_floor(float v)
+{
+#if AM_DEV
+    return __float2int_rd(v);
+#else
+    return (v != v) ? 0 : (int)floorf(v);
+#endif
+}
+template <class ExactU>
+AM_FN bool exp_accept_prefix11(double x, uint32_t f, ExactU exact_u, const double *exp2_j)
+{
+    const float a = (float)x;
+    const float Es = ex2_approx(fmaf(a, 1.44269504f, 11.0f));
+    const int ilo = float2int_floor(Es * 0.9998779296875f);    // 1 − 2^-13
+    const int ihi = float2int_floor(Es * 1.0001220703125f);    // 1 + 2^-13
+    bool acc = (a >= 0.0f) || (ilo > (int)f);
+    const bool rej = ihi < (int)f;
+    if (!(acc || rej)) {
+        const uint32_t t = double2hi(x) - 0x7ff00000u;
+        const bool core = (t - 0x00100000u) < (0x40962000u - 0x00100000u);  // x ∈ [−708, −0]
+        const bool tiny_pos = t >= 0x80100000u;                             // 0 ≤ x, finite
+        acc = tiny_pos || (core && (exp_core(x, exp2_j) > exact_u()));
+    }
+    return acc;
+}
+
 // Filter cell from the top 23 bits of a raw 64-bit word whose u is (w >> 11)·2^-53 (XOSHIRO mode).
 AM_FN float ulo_from_word23(uint32_t w_hi) { return uint_as_float(0x3f800000u | (w_hi >> 9)) - 1.0f; }
 // Filter cell from an 11-bit prefix f: u ∈ [f·2^-11, (f+1)·2^-11) (native Philox mode).

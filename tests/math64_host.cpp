@@ -32,7 +32,7 @@ void m64_accept(const double *x, const uint64_t *w, const uint64_t *r, int mode,
         } else {
             const uint32_t f = lo & 0x7ffu;
             const double u = u53_prefix_refine(f, (uint32_t)r[i], (uint32_t)(r[i] >> 32));
-            filt[i] = exp_accept(x[i], ulo_from_prefix11(f), ulo_from_prefix11(f) + 4.8828125e-04f, [&] { return u; }, T.exp2_j);
+            filt[i] = exp_accept_prefix11(x[i], f, [&] { return u; }, T.exp2_j);
             ref[i] = exp_accept_ref(x[i], u, T.exp2_j);
             u_out[i] = u;
         }
