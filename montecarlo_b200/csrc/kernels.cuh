@@ -187,6 +187,14 @@ __device__ __forceinline__ bool mc_step(double &x, double &e, double beta, doubl
         return mc_step_fast<POT>(x, e, beta, sigma, z, cell, exact_u, exp2_j);
 }
 
+// acc += flag as ONE predicated add (@p VIADD).  Written as `if (flag) ++acc` the compiler emits an add, a predicated
+// move and a copy (three issue slots in an issue-bound loop); ptxas folds the setp below into the predicate that
+// produced `flag`.
+__device__ __forceinline__ void count_if(uint32_t &acc, uint32_t flag)
+{
+    asm("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0;\n @p add.u32 %0, %0, 1;\n}" : "+r"(acc) : "r"(flag));
+}
+
 // Distributions.Categorical inverse-CDF scan [EXT] (metropolis.jl:206); weights in shared memory.
 __device__ __forceinline__ int categorical(int n, const double *w, double u)
 {
@@ -384,8 +392,8 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                     if (a) s_acc[k * kBlock + threadIdx.x] += 1;
                     s_tot[k * kBlock + threadIdx.x] += 1;
                 } else {
-                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, ulo, exact_u, s_T.exp2_j))
-                        ++acc;
+                    const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, ulo, exact_u, s_T.exp2_j);
+                    count_if(acc, a);
                 }
             }
             if constexpr (decltype(do1)::value) {
@@ -401,8 +409,8 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                     if (a) s_acc[k * kBlock + threadIdx.x] += 1;
                     s_tot[k * kBlock + threadIdx.x] += 1;
                 } else {
-                    if (mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, ulo, exact_u, s_T.exp2_j))
-                        ++acc;
+                    const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, ulo, exact_u, s_T.exp2_j);
+                    count_if(acc, a);
                 }
             }
         };
