@@ -504,6 +504,7 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
     const bool exact = h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
 
     if (h->cfg.rng_mode == ARIANNA_RNG_PHILOX) {
+
         SweepParams sp{};
         sp.x = h->d_x; sp.acc = h->d_acc; sp.tot = h->d_tot; sp.betas = h->d_betas; sp.beta = h->cfg.beta;
         sp.M = h->M; sp.K = K; sp.t0 = h->steps_done;
@@ -512,19 +513,26 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
         sp.partials = h->d_partials; sp.ticket = h->d_ticket; sp.sums = h->d_sums;
         sp.tables = h->d_tables;
         sp.pool = h->pool;
-        dispatch_pot(h->cfg.potential, [&](auto pot) {
+        // the Philox sweep keeps its math tables in dynamic shared memory too (one pinned base register, kernels.cuh)
+        const size_t psmem = smem + sizeof(m64::MathTables);
+        auto launch = [&](auto kernel) -> int32_t {
+            if (psmem > 48 * 1024)
+                CU_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            kernel<<<wave_grid(h, kernel, psmem, h->M), kBlock, psmem, h->stream>>>(sp);
+            return ARIANNA_OK;
+        };
+        const int32_t rc = dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
             constexpr int POT = decltype(pot)::value;
             if (exact) {
-                if (multi) sweep_philox_kernel<POT, ARITH_EXACT, true><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_EXACT, true>, smem, h->M), kBlock, smem, h->stream>>>(sp);
-                else if (h->d_betas) sweep_philox_kernel<POT, ARITH_EXACT, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_EXACT, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
-                else sweep_philox_kernel<POT, ARITH_EXACT, false, false, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_EXACT, false, false, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
-            } else {
-                if (multi) sweep_philox_kernel<POT, ARITH_FAST, true><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_FAST, true>, smem, h->M), kBlock, smem, h->stream>>>(sp);
-                else if (h->d_betas) sweep_philox_kernel<POT, ARITH_FAST, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_FAST, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
-                else sweep_philox_kernel<POT, ARITH_FAST, false, false, false><<<wave_grid(h, sweep_philox_kernel<POT, ARITH_FAST, false, false, false>, 0, h->M), kBlock, 0, h->stream>>>(sp);
+                if (multi) return launch(sweep_philox_kernel<POT, ARITH_EXACT, true>);
+                if (h->d_betas) return launch(sweep_philox_kernel<POT, ARITH_EXACT, false>);
+                return launch(sweep_philox_kernel<POT, ARITH_EXACT, false, false, false>);
             }
-            return 0;
+            if (multi) return launch(sweep_philox_kernel<POT, ARITH_FAST, true>);
+            if (h->d_betas) return launch(sweep_philox_kernel<POT, ARITH_FAST, false>);
+            return launch(sweep_philox_kernel<POT, ARITH_FAST, false, false, false>);
         });
+        if (rc) return rc;
     } else {
         XoshiroParams xp{};
         xp.x = h->d_x; xp.acc = h->d_acc; xp.tot = h->d_tot; xp.betas = h->d_betas; xp.beta = h->cfg.beta;
@@ -555,7 +563,7 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
 }
 
 // Store intervals fused per series launch.  Each interval costs kSeriesBytesPerStore (3 KB) of shared memory per CTA
-// on top of the kernel's static tables (~19 KB, mostly the sin/cos directions): as many intervals as keep the
+// on top of the kernel's math tables (~19 KB, mostly the sin/cos directions): as many intervals as keep the
 // sweep's 4 resident CTAs per SM (11 on B200's 228 KB); an ensemble that fits one CTA per SM anyway (M <= 256 x SM
 // count: the reference's own small-M configurations) fuses up to ARIANNA_MAX_SERIES per launch.
 static int series_per_launch(const arianna_handle *h)
@@ -565,12 +573,13 @@ static int series_per_launch(const arianna_handle *h)
     if (env > 0) return env < kMaxSeries ? env : kMaxSeries;
     if (h->M <= (int64_t)kBlock * h->sm_count) return kMaxSeries;
     cudaFuncAttributes fa{};
-    size_t stat = 20 * 1024;
+    size_t stat = 1024;
     if (cudaFuncGetAttributes(&fa, sweep_philox_kernel<POT_HARMONIC, ARITH_FAST, false, true, false>) == cudaSuccess)
         stat = fa.sharedSizeBytes;
     else
         cudaGetLastError();
-    const long per_cta = (long)(h->smem_per_sm / ARIANNA_MINB) - 1024 - (long)stat - (long)(sizeof(unsigned long long) * kBlock);
+    const long per_cta = (long)(h->smem_per_sm / ARIANNA_MINB) - 1024 - (long)stat - (long)sizeof(m64::MathTables) -
+                         (long)(sizeof(unsigned long long) * kBlock);
     long n = per_cta / kSeriesBytesPerStore;
     if (n < 1) n = 1;
     if (n > 16) n = 16;
@@ -637,7 +646,7 @@ int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t 
         sp.series_K[ns] = 0;
         sp.series_even = even ? 1 : 0;
         sp.K = k_launch;
-        const size_t smem = (size_t)ns * kSeriesBytesPerStore + sizeof(unsigned long long) * kBlock;
+        const size_t smem = sizeof(m64::MathTables) + (size_t)ns * kSeriesBytesPerStore + sizeof(unsigned long long) * kBlock;
         int grid = 0;
         int32_t rc = dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
             constexpr int POT = decltype(pot)::value;

@@ -85,6 +85,22 @@ __device__ __forceinline__ void load_tables(m64::MathTables *dst, const m64::Mat
     for (int i = threadIdx.x; i < (int)(sizeof(m64::MathTables) / sizeof(double)); i += blockDim.x) d[i] = s[i];
 }
 
+// Handle of a MathTables copy in shared memory (m64::Tab).  pin = true makes the window address opaque to the
+// optimiser so that it stays in ONE register across the sweep's loops instead of being re-derived next to every use.
+__device__ __forceinline__ m64::Tab shared_tab(const void *smem_ptr, bool pin)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+    if (pin) asm volatile("" : "+r"(a));
+    return m64::Tab{a};
+}
+// explicit shared-memory accesses relative to such an address (series accumulators of the sweep)
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+
 // ---------------------------------------------------------------------------------------------------------
 // potential(x)
 // ---------------------------------------------------------------------------------------------------------
@@ -121,7 +137,7 @@ __device__ __forceinline__ double potential(double x)
 // ---------------------------------------------------------------------------------------------------------
 template <int POT>
 __device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, double sigma, double lognorm,
-                                             double z, double u_acc, const double *exp2_j)
+                                             double z, double u_acc, m64::Tab tb)
 {
     double delta = __dadd_rn(0.0, __dmul_rn(sigma, z));                       // particle_1d.jl:57
     double s2 = __dmul_rn(sigma, sigma);
@@ -138,7 +154,7 @@ __device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, 
     // evaluation of exp (≤1 ulp, like Julia's / glibc's) would, through the FP32 filter of m64::exp_accept
     float ulo, uhi;
     m64::ucell_from_double(u_acc, ulo, uhi);
-    if (m64::exp_accept(arg, ulo, uhi, [&]() { return u_acc; }, exp2_j)) return 1;
+    if (m64::exp_accept(arg, ulo, uhi, [&]() { return u_acc; }, tb)) return 1;
     x = __dadd_rn(x, delta);                                                  // :187 re-applied negated move:
     e = potential<POT, ARITH_EXACT>(x);                                       //      x = fl(fl(x+δ)-δ), not a restore
     return 0;
@@ -152,26 +168,26 @@ struct CellP11 { uint32_t f; };
 struct CellF { float ulo, cell; };
 
 template <class ExactU>
-__device__ __forceinline__ bool accept_in_cell(double arg, CellP11 c, ExactU exact_u, const double *exp2_j)
+__device__ __forceinline__ bool accept_in_cell(double arg, CellP11 c, ExactU exact_u, m64::Tab tb)
 {
-    return m64::exp_accept_prefix11(arg, c.f, exact_u, exp2_j);
+    return m64::exp_accept_prefix11(arg, c.f, exact_u, tb);
 }
 template <class ExactU>
-__device__ __forceinline__ bool accept_in_cell(double arg, CellF c, ExactU exact_u, const double *exp2_j)
+__device__ __forceinline__ bool accept_in_cell(double arg, CellF c, ExactU exact_u, m64::Tab tb)
 {
-    return m64::exp_accept(arg, c.ulo, c.ulo + c.cell, exact_u, exp2_j);   // ulo + cell is exact
+    return m64::exp_accept(arg, c.ulo, c.ulo + c.cell, exact_u, tb);   // ulo + cell is exact
 }
 
 template <int POT, class Cell, class ExactU>
 __device__ __forceinline__ bool mc_step_fast(double &x, double &e, double beta, double sigma, double z, Cell cell,
-                                             ExactU exact_u, const double *exp2_j)
+                                             ExactU exact_u, m64::Tab tb)
 {
     // e is re-derived from x (one DMUL on the idle FP64 pipe) instead of being carried through two more selects on
     // the ALU pipe, which is the busiest pipe of the sweep
     const double e0 = potential<POT, ARITH_FAST>(x);
     const double xn = fma(sigma, z, x);
     const double en = potential<POT, ARITH_FAST>(xn);
-    const bool a = accept_in_cell(beta * (e0 - en), cell, exact_u, exp2_j);
+    const bool a = accept_in_cell(beta * (e0 - en), cell, exact_u, tb);
     x = a ? xn : x;
     (void)e;  // FAST never carries e: callers that need it (the fused reduction) evaluate potential(x)
     return a;
@@ -179,12 +195,12 @@ __device__ __forceinline__ bool mc_step_fast(double &x, double &e, double beta, 
 
 template <int POT, int ARITH, class Cell, class ExactU>
 __device__ __forceinline__ bool mc_step(double &x, double &e, double beta, double sigma, double lognorm, double z,
-                                        Cell cell, ExactU exact_u, const double *exp2_j)
+                                        Cell cell, ExactU exact_u, m64::Tab tb)
 {
     if constexpr (ARITH == ARITH_EXACT)
-        return mc_step_exact<POT>(x, e, beta, sigma, lognorm, z, exact_u(), exp2_j) != 0;
+        return mc_step_exact<POT>(x, e, beta, sigma, lognorm, z, exact_u(), tb) != 0;
     else
-        return mc_step_fast<POT>(x, e, beta, sigma, z, cell, exact_u, exp2_j);
+        return mc_step_fast<POT>(x, e, beta, sigma, z, cell, exact_u, tb);
 }
 
 // acc += flag as ONE predicated add (@p VIADD).  Written as `if (flag) ++acc` the compiler emits an add, a predicated
@@ -284,30 +300,33 @@ template <int POT, int ARITH, bool MULTI, bool SERIES = false, bool BETAS = true
 __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(const SweepParams p)
 {
     static_assert(!(MULTI && SERIES), "series mode is implemented for single-move pools");
+    // dynamic shared memory: [MathTables][kernel-specific arrays] -- ONE symbol, so one pinned base register serves
+    // the math tables and the series accumulators alike
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // MULTI: [n_moves][kBlock] acc, [n_moves][kBlock] tot (u32), then sigma/weight/lognorm tables
-    uint32_t *s_acc = reinterpret_cast<uint32_t *>(smem_raw);
+    constexpr uint32_t kTabBytes = (uint32_t)sizeof(m64::MathTables);
+    // MULTI: [n_moves][kBlock] acc, [n_moves][kBlock] tot (u32)
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(smem_raw + kTabBytes);
     uint32_t *s_tot = s_acc + (MULTI ? p.pool.n_moves * kBlock : 0);
-    // SERIES: [n_series][kBlock] f64 Σe, [n_series][kBlock] u32 ΣΔacc, [kBlock] u64 Σacc at entry
-    double *s_se = reinterpret_cast<double *>(smem_raw);
-    uint32_t *s_da = reinterpret_cast<uint32_t *>(s_se + (SERIES ? p.n_series * kBlock : 0));
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_da + (SERIES ? p.n_series * kBlock : 0));
-    if constexpr (SERIES) {
-        for (int s = 0; s < p.n_series; ++s) {
-            s_se[s * kBlock + threadIdx.x] = 0.0;
-            s_da[s * kBlock + threadIdx.x] = 0u;
-        }
-        s_base[threadIdx.x] = 0ull;
-    }
     __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves];
-    __shared__ m64::MathTables s_T;
     if (threadIdx.x < kMaxMoves) {
         s_sigma[threadIdx.x] = p.pool.sigma[threadIdx.x];
         s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
         s_lognorm[threadIdx.x] = p.pool.lognorm[threadIdx.x];
     }
-    load_tables(&s_T, p.tables);
+    load_tables(reinterpret_cast<m64::MathTables *>(smem_raw), p.tables);
     __syncthreads();
+    const m64::Tab tb = shared_tab(smem_raw, true);
+    // SERIES: [n_series][kBlock] f64 Σe, [n_series][kBlock] u32 ΣΔacc, [kBlock] u64 Σacc at entry, as byte addresses
+    const uint32_t a_se = tb.s + kTabBytes + 8u * threadIdx.x;
+    const uint32_t a_da = tb.s + kTabBytes + (SERIES ? 8u * kBlock * (uint32_t)p.n_series : 0u) + 4u * threadIdx.x;
+    const uint32_t a_base = tb.s + kTabBytes + (SERIES ? 12u * kBlock * (uint32_t)p.n_series : 0u) + 8u * threadIdx.x;
+    if constexpr (SERIES) {
+        for (int s = 0; s < p.n_series; ++s) {
+            sts_f64(a_se + 8u * kBlock * s, 0.0);
+            sts_u32(a_da + 4u * kBlock * s, 0u);
+        }
+        sts_u64(a_base, 0ull);
+    }
 
     const int nm = p.pool.n_moves;
     const int64_t tend = p.t0 + p.K;
@@ -369,7 +388,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         auto gen_pair = [&](uint64_t pr) {
             PairDraws d;
             const U64Pair b0 = ph.block((uint32_t)pr);
-            m64::box_muller_u64(u64_of(b0.a_lo, b0.a_hi), u64_of(b0.b_lo, b0.b_hi), &s_T, d.z0, d.z1);
+            m64::box_muller_u64(u64_of(b0.a_lo, b0.a_hi), u64_of(b0.b_lo, b0.b_hi), tb, d.z0, d.z1);
             d.f0 = b0.a_lo & 0x7ffu;
             d.f1 = b0.b_lo & 0x7ffu;
             d.pr = pr;
@@ -388,11 +407,11 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                 if constexpr (MULTI) {
                     const int k = categorical(nm, s_weight, u53(d.b2.a_lo, d.b2.a_hi));
                     const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z0, ulo,
-                                                       exact_u, s_T.exp2_j);
+                                                       exact_u, tb);
                     if (a) s_acc[k * kBlock + threadIdx.x] += 1;
                     s_tot[k * kBlock + threadIdx.x] += 1;
                 } else {
-                    const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, ulo, exact_u, s_T.exp2_j);
+                    const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, ulo, exact_u, tb);
                     count_if(acc, a);
                 }
             }
@@ -405,11 +424,11 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                 if constexpr (MULTI) {
                     const int k = categorical(nm, s_weight, u53(d.b2.b_lo, d.b2.b_hi));
                     const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z1, ulo,
-                                                       exact_u, s_T.exp2_j);
+                                                       exact_u, tb);
                     if (a) s_acc[k * kBlock + threadIdx.x] += 1;
                     s_tot[k * kBlock + threadIdx.x] += 1;
                 } else {
-                    const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, ulo, exact_u, s_T.exp2_j);
+                    const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, ulo, exact_u, tb);
                     count_if(acc, a);
                 }
             }
@@ -444,7 +463,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         if (trail) do_steps(gen_pair(pr), T_{}, F_{});
         };
         if constexpr (SERIES) {
-            s_base[threadIdx.x] += acc;
+            sts_u64(a_base, lds_u64(a_base) + acc);
             uint32_t acc_prev = acc, ta = (uint32_t)p.t0;
             if (p.series_even) {
                 // whole pairs only: ONE flat loop over the pairs of all intervals; a countdown marks the store points
@@ -457,8 +476,8 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                 for (uint32_t pr = ta >> 1; pr < pr1; ++pr) {
                     do_steps(gen_pair((uint64_t)pr), T_{}, T_{});
                     if (--left == 0) {
-                        s_se[s * kBlock + threadIdx.x] += potential<POT, ARITH>(x);
-                        s_da[s * kBlock + threadIdx.x] += acc - acc_prev;
+                        sts_f64(a_se + 8u * kBlock * s, lds_f64(a_se + 8u * kBlock * s) + potential<POT, ARITH>(x));
+                        sts_u32(a_da + 4u * kBlock * s, lds_u32(a_da + 4u * kBlock * s) + (acc - acc_prev));
                         acc_prev = acc;
                         left = p.series_K[++s] >> 1;
                     }
@@ -468,8 +487,8 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
             for (int s = 0; s < p.n_series; ++s) {
                 const uint32_t tb = ta + (uint32_t)p.series_K[s];
                 run_steps(ta, tb);
-                s_se[s * kBlock + threadIdx.x] += potential<POT, ARITH>(x);   // callback_energy: e == potential(x)
-                s_da[s * kBlock + threadIdx.x] += acc - acc_prev;             // accepted within this interval
+                sts_f64(a_se + 8u * kBlock * s, lds_f64(a_se + 8u * kBlock * s) + potential<POT, ARITH>(x));  // Σ e
+                sts_u32(a_da + 4u * kBlock * s, lds_u32(a_da + 4u * kBlock * s) + (acc - acc_prev));          // accepted here
                 acc_prev = acc;
                 ta = tb;
             }
@@ -501,10 +520,10 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         for (int s = 0; s <= p.n_series; ++s) {
             double v0, v1;
             if (s < p.n_series) {
-                v0 = s_se[s * kBlock + threadIdx.x];
-                v1 = (double)s_da[s * kBlock + threadIdx.x];
+                v0 = lds_f64(a_se + 8u * kBlock * s);
+                v1 = (double)lds_u32(a_da + 4u * kBlock * s);
             } else {
-                v0 = (double)s_base[threadIdx.x];
+                v0 = (double)lds_u64(a_base);
                 v1 = 0.0;
             }
             v0 = warp_sum(v0);
@@ -601,9 +620,10 @@ __global__ void __launch_bounds__(kBlock) sweep_replay_kernel(const ReplayParams
         s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
         s_lognorm[threadIdx.x] = p.pool.lognorm[threadIdx.x];
     }
-    __shared__ double s_exp2[m64::kExpTab];
-    if (threadIdx.x < m64::kExpTab) s_exp2[threadIdx.x] = p.tables->exp2_j[threadIdx.x];
+    __shared__ m64::MathTables s_T;
+    load_tables(&s_T, p.tables);
     __syncthreads();
+    const m64::Tab tb = shared_tab(&s_T, false);
     const int nm = p.pool.n_moves;
     constexpr int PF = 4;
 
@@ -640,11 +660,11 @@ __global__ void __launch_bounds__(kBlock) sweep_replay_kernel(const ReplayParams
                     int d;
                     if constexpr (MULTI) {
                         const int k = categorical(nm, s_weight, uc[i]);
-                        d = mc_step_exact<POT>(x, e, beta, s_sigma[k], s_lognorm[k], zz[i], ua[i], s_exp2);
+                        d = mc_step_exact<POT>(x, e, beta, s_sigma[k], s_lognorm[k], zz[i], ua[i], tb);
                         s_acc[k * kBlock + threadIdx.x] += d;
                         s_tot[k * kBlock + threadIdx.x] += 1;
                     } else {
-                        d = mc_step_exact<POT>(x, e, beta, s_sigma[0], s_lognorm[0], zz[i], ua[i], s_exp2);
+                        d = mc_step_exact<POT>(x, e, beta, s_sigma[0], s_lognorm[0], zz[i], ua[i], tb);
                         acc += d;
                     }
                     if (p.decisions) __stcs(p.decisions + (size_t)(s0 + i) * p.M + c, (uint8_t)d);
@@ -692,8 +712,8 @@ __global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroPara
     __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves];
     __shared__ uint64_t s_ki[256];
     __shared__ double s_wi[256], s_fi[256];
-    __shared__ double s_exp2[m64::kExpTab];
-    if (threadIdx.x < m64::kExpTab) s_exp2[threadIdx.x] = p.tables->exp2_j[threadIdx.x];
+    __shared__ m64::MathTables s_T;
+    load_tables(&s_T, p.tables);
     if (threadIdx.x < kMaxMoves) {
         s_sigma[threadIdx.x] = p.pool.sigma[threadIdx.x];
         s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
@@ -705,6 +725,7 @@ __global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroPara
         s_fi[i] = p.fi[i];
     }
     __syncthreads();
+    const m64::Tab tb = shared_tab(&s_T, false);
     const ZigTables T{s_ki, s_wi, s_fi};
     const int nm = p.pool.n_moves;
 
@@ -734,12 +755,12 @@ __global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroPara
             if constexpr (MULTI) {
                 const int k = categorical(nm, s_weight, uc);
                 const bool d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], zz, ulo, exact_u,
-                                                   s_exp2);
+                                                   tb);
                 if (d) s_acc[k * kBlock + threadIdx.x] += 1;
                 s_tot[k * kBlock + threadIdx.x] += 1;
             } else {
                 (void)uc;
-                if (mc_step<POT, ARITH>(x, e, beta, s_sigma[0], s_lognorm[0], zz, ulo, exact_u, s_exp2))
+                if (mc_step<POT, ARITH>(x, e, beta, s_sigma[0], s_lognorm[0], zz, ulo, exact_u, tb))
                     ++acc;
             }
         }
@@ -853,7 +874,7 @@ struct PgmcParams {
 template <int POT, int ARITH>
 __device__ __forceinline__ void pgmc_sample(double &x, double &e, double beta, double sigma, double lognorm,
                                             double z, double &sj, double &sdj, double &sgf, double &sg,
-                                            const double *exp2_j)
+                                            m64::Tab tb)
 {
     if constexpr (ARITH == ARITH_EXACT) {
         double delta = __dadd_rn(0.0, __dmul_rn(sigma, z));                                    // gradients.jl:119
@@ -883,7 +904,7 @@ __device__ __forceinline__ void pgmc_sample(double &x, double &e, double beta, d
         const double w = fma(z, z, -1.0);
         const double xn = fma(sigma, z, x);
         const double en = potential<POT, ARITH_FAST>(xn);
-        const double alpha = m64::exp_nonpos(beta * (e - en), exp2_j);   // = min(1, exp(·))
+        const double alpha = m64::exp_nonpos(beta * (e - en), tb);   // = min(1, exp(·))
         const double ja = z2 * alpha;
         sj += ja; sdj = fma(ja, w, sdj); sgf += w; sg = fma(w, w, sg);
     }
@@ -895,6 +916,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) pgmc_kernel(const PgmcPa
     __shared__ m64::MathTables s_T;
     load_tables(&s_T, p.tables);
     __syncthreads();
+    const m64::Tab tb = shared_tab(&s_T, true);
     double sj = 0.0, sdj = 0.0, sgf = 0.0, sg = 0.0, sn = 0.0;
     const int64_t qend = p.q0 + p.q_batch;
     for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
@@ -904,7 +926,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) pgmc_kernel(const PgmcPa
         if constexpr (REPLAY) {
             for (int b = 0; b < p.q_batch; ++b)
                 pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, __ldcs(p.z + (size_t)b * p.M + c), sj, sdj,
-                                        sgf, sg, s_T.exp2_j);
+                                        sgf, sg, tb);
         } else {
             const uint64_t sid = p.sid0 + (uint64_t)c;
             const PhiloxChain<kTagEstimator, 0> ph(sid);
@@ -913,9 +935,9 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) pgmc_kernel(const PgmcPa
             auto pair = [&](uint32_t pr, bool do0, bool do1) {
                 const U64Pair blk = ph.block(pr);
                 double z0, z1;
-                m64::box_muller_u64(u64_of(blk.a_lo, blk.a_hi), u64_of(blk.b_lo, blk.b_hi), &s_T, z0, z1);
-                if (do0) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z0, sj, sdj, sgf, sg, s_T.exp2_j);
-                if (do1) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z1, sj, sdj, sgf, sg, s_T.exp2_j);
+                m64::box_muller_u64(u64_of(blk.a_lo, blk.a_hi), u64_of(blk.b_lo, blk.b_hi), tb, z0, z1);
+                if (do0) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z0, sj, sdj, sgf, sg, tb);
+                if (do1) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z1, sj, sdj, sgf, sg, tb);
             };
             const bool lead = (p.q0 & 1) != 0, trail = (qend & 1) != 0;
             uint32_t pr = (uint32_t)(p.q0 >> 1);
@@ -967,12 +989,13 @@ __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const doub
     __shared__ m64::MathTables s_T;
     load_tables(&s_T, tables);
     __syncthreads();
+    const m64::Tab tb = shared_tab(&s_T, false);
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
-        if (kind == 0) out[i] = m64::exp_nonpos(a[i], s_T.exp2_j);
-        else if (kind == 1) out[i] = m64::neg2log_u53(b[i], s_T.log_rc, s_T.log_m2lc, s_T.e_m2ln2);
+        if (kind == 0) out[i] = m64::exp_nonpos(a[i], tb);
+        else if (kind == 1) out[i] = m64::neg2log_u53(b[i], tb);
         else if (kind == 2) out[i] = m64::sqrt_pos(a[i]);
-        else if (kind == 3) m64::sincos_turn53_tab((uint32_t)(b[i] >> 32), (uint32_t)b[i], s_T.sincos, out[2 * i], out[2 * i + 1]);
-        else if (kind == 4) m64::box_muller_u64(b[i], cc[i], &s_T, out[2 * i], out[2 * i + 1]);
+        else if (kind == 3) m64::sincos_turn53_tab((uint32_t)(b[i] >> 32), (uint32_t)b[i], tb, out[2 * i], out[2 * i + 1]);
+        else if (kind == 4) m64::box_muller_u64(b[i], cc[i], tb, out[2 * i], out[2 * i + 1]);
         else if (kind == 6 || kind == 7) {
             // Philox4x32-10 block (sid = b, p = c): 6 = per-chain hoisted form (sub 0), 7 = general form, sub = a
             U64Pair r;
@@ -984,8 +1007,8 @@ __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const doub
             const uint32_t f = (uint32_t)b[i] & 0x7ffu;
             const uint64_t r = cc[i];
             auto exact_u = [&]() { return m64::u53_prefix_refine(f, (uint32_t)r, (uint32_t)(r >> 32)); };
-            out[2 * i] = m64::exp_accept_prefix11(a[i], f, exact_u, s_T.exp2_j) ? 1.0 : 0.0;
-            out[2 * i + 1] = m64::exp_accept_ref(a[i], exact_u(), s_T.exp2_j) ? 1.0 : 0.0;
+            out[2 * i] = m64::exp_accept_prefix11(a[i], f, exact_u, tb) ? 1.0 : 0.0;
+            out[2 * i + 1] = m64::exp_accept_ref(a[i], exact_u(), tb) ? 1.0 : 0.0;
         }
     }
 }

@@ -13,6 +13,7 @@
 // the device through arianna_debug_math, tests/test_gpu_math.py).  Every function is also compilable for the host
 // (ARIANNA_MATH_HOST) so the accuracy tests run without a GPU.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 #if defined(__CUDA_ARCH__) || (defined(__CUDACC__) && !defined(ARIANNA_MATH_HOST))
@@ -172,11 +173,48 @@ static inline void build_math_tables(MathTables &T)
     for (int j = 0; j < kExpTab; ++j) T.exp2_j[j] = (double)__builtin_exp2l((long double)j / 32.0L);
 }
 
+// ---- table handle ------------------------------------------------------------------------------------------
+// On the device a MathTables copy lives in shared memory and is addressed through its 32-bit shared-window address
+// with explicit ld.shared: passing C++ pointers makes ptxas re-derive the window base (S2UR SR_CgaCtaId + UMOV + ULEA)
+// next to the uses, i.e. inside the issue-bound loops; one pinned register holds it instead (kernels.cuh:shared_tab).
+// On the host (accuracy tests) the handle is a plain pointer.
+#if AM_DEV
+struct Tab { uint32_t s; };
+AM_FN double tab_ld(Tab t, uint32_t byte_off)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(t.s + byte_off));
+    return v;
+}
+AM_FN void tab_ld2(Tab t, uint32_t byte_off, double &a, double &b)
+{
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(t.s + byte_off));
+}
+#else
+struct Tab { const MathTables *p; };
+AM_FN double tab_ld(Tab t, uint32_t byte_off)
+{
+    double v;
+    std::memcpy(&v, reinterpret_cast<const char *>(t.p) + byte_off, 8);
+    return v;
+}
+AM_FN void tab_ld2(Tab t, uint32_t byte_off, double &a, double &b)
+{
+    a = tab_ld(t, byte_off);
+    b = tab_ld(t, byte_off + 8);
+}
+#endif
+constexpr uint32_t kOffSinCos = (uint32_t)offsetof(MathTables, sincos);
+constexpr uint32_t kOffLogRc = (uint32_t)offsetof(MathTables, log_rc);
+constexpr uint32_t kOffLogM2lc = (uint32_t)offsetof(MathTables, log_m2lc);
+constexpr uint32_t kOffEM2ln2 = (uint32_t)offsetof(MathTables, e_m2ln2);
+constexpr uint32_t kOffExp2 = (uint32_t)offsetof(MathTables, exp2_j);
+
 // ---- exp ------------------------------------------------------------------------------------------------
 // exp(x) for x ∈ [−708, 0] (also correct for small positive x): n = round(x·32/ln2) = 32m + j,
 // r = x − n·ln2/32 (|r| ≤ ln2/64), exp(x) = 2^m · 2^(j/32) · (1 + expm1(r)).  11 FP64 instructions, no range checks:
 // outside the interval the result is garbage and the CALLER must not use it (see exp_class / exp_nonpos).
-AM_FN double exp_core(double x, const double *exp2_j)
+AM_FN double exp_core(double x, Tab tb)
 {
     const double nf = fma64(x, kExpK[0], kExpK[7]);
     const int32_t n = (int32_t)double2lo(nf);
@@ -189,7 +227,7 @@ AM_FN double exp_core(double x, const double *exp2_j)
     q = fma64(q, r, kExpK[6]);
     q = fma64(q, r, 0.5);
     const double p = r * fma64(q, r, 1.0);                  // expm1(r) = r·(1 + r·q)
-    const double t = exp2_j[n & 31];
+    const double t = tab_ld(tb, kOffExp2 + 8u * (uint32_t)(n & 31));
     const double res = fma64(t, p, t);
     return hilo2double(double2hi(res) + ((uint32_t)(n >> 5) << 20), double2lo(res));
 }
@@ -207,10 +245,10 @@ AM_FN int exp_class(double x)
 }
 
 // min(1, exp(x)) as a value (PGMC's α).
-AM_FN double exp_nonpos(double x, const double *exp2_j)
+AM_FN double exp_nonpos(double x, Tab tb)
 {
     const int c = exp_class(x);
-    const double v = exp_core(x, exp2_j);
+    const double v = exp_core(x, tb);
     return c == kExpCore ? v : (c == kExpOne ? 1.0 : 0.0);
 }
 
@@ -255,7 +293,7 @@ AM_FN float uint_as_float(uint32_t b)
 // Error budget: a = RN32(x) (2^-24), y = a·log2e (2·2^-24), EX2 (2^-22) -> |Ê/E − 1| ≤ 2^-22 + 3·2^-24·|x|;
 // ε = 2^-21·(1 + |a|) over-covers it by > 2.5x.
 template <class ExactU>
-AM_FN bool exp_accept(double x, float ulo, float uhi, ExactU exact_u, const double *exp2_j)
+AM_FN bool exp_accept(double x, float ulo, float uhi, ExactU exact_u, Tab tb)
 {
     const float a = (float)x;
     const float E = ex2_approx(a * 1.44269504f);
@@ -271,7 +309,7 @@ AM_FN bool exp_accept(double x, float ulo, float uhi, ExactU exact_u, const doub
         const uint32_t t = double2hi(x) - 0x7ff00000u;
         const bool core = (t - 0x00100000u) < (0x40962000u - 0x00100000u);  // x ∈ [−708, −0]
         const bool tiny_pos = t >= 0x80100000u;                             // 0 ≤ x, finite (float(x) rounded to −0… never)
-        acc = tiny_pos || (core && (exp_core(x, exp2_j) > exact_u()));
+        acc = tiny_pos || (core && (exp_core(x, tb) > exact_u()));
     }
     return acc;
 }
@@ -296,7 +334,7 @@ AM_FN int float2int_floor(float v)
 #endif
 }
 template <class ExactU>
-AM_FN bool exp_accept_prefix11(double x, uint32_t f, ExactU exact_u, const double *exp2_j)
+AM_FN bool exp_accept_prefix11(double x, uint32_t f, ExactU exact_u, Tab tb)
 {
     const float a = (float)x;
     const float Es = ex2_approx(fmaf(a, 1.44269504f, 11.0f));
@@ -308,7 +346,7 @@ AM_FN bool exp_accept_prefix11(double x, uint32_t f, ExactU exact_u, const doubl
         const uint32_t t = double2hi(x) - 0x7ff00000u;
         const bool core = (t - 0x00100000u) < (0x40962000u - 0x00100000u);  // x ∈ [−708, −0]
         const bool tiny_pos = t >= 0x80100000u;                             // 0 ≤ x, finite
-        acc = tiny_pos || (core && (exp_core(x, exp2_j) > exact_u()));
+        acc = tiny_pos || (core && (exp_core(x, tb) > exact_u()));
     }
     return acc;
 }
@@ -343,20 +381,19 @@ AM_FN void ucell_from_double(double u, float &ulo, float &uhi)
 }
 
 // Reference decision (no filter) -- used by the accuracy tests to prove the filter never changes a decision.
-AM_FN bool exp_accept_ref(double x, double u, const double *exp2_j)
+AM_FN bool exp_accept_ref(double x, double u, Tab tb)
 {
     const int c = exp_class(x);
-    return c == kExpOne || (c == kExpCore && exp_core(x, exp2_j) > u);
+    return c == kExpOne || (c == kExpCore && exp_core(x, tb) > u);
 }
 
 // ---- −2·ln(n·2^-53) --------------------------------------------------------------------------------------
 // Core: u = m·2^E with m ∈ [√½, √2) given by its words (hx, lx) after fdlibm's fold; i = mantissa interval.
-AM_FN double neg2log_core(uint32_t hx_folded, uint32_t lx, int negE, const double *log_rc, const double *log_m2lc,
-                          const double *e_m2ln2)
+AM_FN double neg2log_core(uint32_t hx_folded, uint32_t lx, int negE, Tab tb)
 {
     const double m = hilo2double(hx_folded, lx);
-    const int i = (int)((hx_folded - kHxBase) >> 13);
-    const double rc = log_rc[i];
+    const uint32_t i8 = ((hx_folded - kHxBase) >> 13) * 8u;   // byte offset of mantissa interval i
+    const double rc = tab_ld(tb, kOffLogRc + i8);
     const double r = fma64(m, rc, -1.0);    // |r| ≤ 2^-8
     // −2·log1p(r) = r·(−2 + r·(1 − (2/3)r + (1/2)r² − (2/5)r³ + (1/3)r⁴ − (2/7)r⁵))
     double q = kLogK[0];
@@ -366,11 +403,11 @@ AM_FN double neg2log_core(uint32_t hx_folded, uint32_t lx, int negE, const doubl
     q = fma64(q, r, kLogK[3]);
     q = fma64(q, r, 1.0);
     const double t = r * fma64(q, r, -2.0);
-    return (e_m2ln2[negE] + log_m2lc[i]) + t;
+    return (tab_ld(tb, kOffEM2ln2 + 8u * (uint32_t)negE) + tab_ld(tb, kOffLogM2lc + i8)) + t;
 }
 
 // From the integer n ∈ [1, 2^53) (clz normalisation; reference formulation used by the accuracy tests).
-AM_FN double neg2log_u53(uint64_t n, const double *log_rc, const double *log_m2lc, const double *e_m2ln2)
+AM_FN double neg2log_u53(uint64_t n, Tab tb)
 {
     const int lz = clz64(n);                // lz ∈ [11, 63]
     const uint64_t nm = n << lz;            // bit 63 set; at most 53 significant bits
@@ -380,21 +417,20 @@ AM_FN double neg2log_u53(uint64_t n, const double *log_rc, const double *log_m2l
     hx += 0x3ff00000u - kHxBase;            // fdlibm: fold the mantissa's top bit into the exponent
     E += (int)(hx >> 20) - 0x3ff;
     hx = (hx & 0x000fffffu) + kHxBase;
-    return neg2log_core(hx, lx, -E, log_rc, log_m2lc, e_m2ln2);
+    return neg2log_core(hx, lx, -E, tb);
 }
 
 // Same value, from the two 32-bit halves of k = n (k_hi: top 21 bits, k_lo: low 32 bits): u = k·2^-53 is first
 // assembled EXACTLY with two DADDs (no clz / 64-bit normalising shifts: the FP64 adder does the normalisation and
 // 12 ALU-pipe instructions disappear from the hot loop), then split into exponent and mantissa words.
-AM_FN double neg2log_words(uint32_t k_hi, uint32_t k_lo, const double *log_rc, const double *log_m2lc,
-                           const double *e_m2ln2)
+AM_FN double neg2log_words(uint32_t k_hi, uint32_t k_lo, Tab tb)
 {
     const double dh = hilo2double(0x41E00000u, k_hi);   // 2^31 + k_hi·2^-21
     const double dl = hilo2double(0x3FE00000u, k_lo);   // 2^-1 + k_lo·2^-53
     const double u = (dh - 2147483648.5) + dl;          // exact
     const uint32_t hx = double2hi(u) + (0x3ff00000u - kHxBase);
     const int negE = 0x3ff - (int)(hx >> 20);           // −E ∈ [0, 53]
-    return neg2log_core((hx & 0x000fffffu) + kHxBase, double2lo(u), negE, log_rc, log_m2lc, e_m2ln2);
+    return neg2log_core((hx & 0x000fffffu) + kHxBase, double2lo(u), negE, tb);
 }
 
 // ---- √w, w > 0 normal ---------------------------------------------------------------------------------------
@@ -453,7 +489,7 @@ AM_FN void sincos_turn53(uint64_t k, double &sn, double &cs)
 // 12 FP64 instructions + one 16-byte shared load instead of 18 FP64 + ~20 integer/select instructions of the
 // quadrant-reduced polynomial form above (no quadrant swap, no sign fix-up, four polynomial constants instead of
 // twelve).  Error ≤ 0.5 ulp (table) + 0.5 ulp (inner fma) + 0.5 ulp (outer fma); exact on the axes (S or C = 0, ±1).
-AM_FN void sincos_turn53_tab(uint32_t k_hi, uint32_t k_lo, const double (*tab)[2], double &sn, double &cs)
+AM_FN void sincos_turn53_tab(uint32_t k_hi, uint32_t k_lo, Tab tb, double &sn, double &cs)
 {
     const uint32_t kk = k_hi + (1u << 10);                 // k + 2^42: round to the nearest direction
     const uint32_t i = (kk >> 11) & (uint32_t)(kTrigTab - 1);
@@ -464,12 +500,8 @@ AM_FN void sincos_turn53_tab(uint32_t k_hi, uint32_t k_lo, const double (*tab)[2
     const double ps = fma64(z, kTrigK[0], kTrigK[1]);      // 1/120, −1/6
     const double sphi = fma64(z * phi, ps, phi);
     const double cm1 = fma64(z, kTrigK[2], -0.5) * z;      // 1/24
-#if AM_DEV
-    const double2 t = *reinterpret_cast<const double2 *>(tab[i]);
-    const double S = t.x, C = t.y;
-#else
-    const double S = tab[i][0], C = tab[i][1];
-#endif
+    double S, C;
+    tab_ld2(tb, kOffSinCos + 16u * i, S, C);
     sn = fma64(C, sphi, fma64(S, cm1, S));
     cs = fma64(-S, sphi, fma64(C, cm1, C));
 }
@@ -477,14 +509,14 @@ AM_FN void sincos_turn53_tab(uint32_t k_hi, uint32_t k_lo, const double (*tab)[2
 // Box-Muller from two raw 64-bit Philox words (B0 -> radius, B1 -> angle); same definition as the oracle:
 //   u1 = ((B0 >> 11) | 1)·2^-53 ∈ (0,1) (odd lattice: never 0 or 1, so −2 ln u1 > 0 without a special case),
 //   u2 = (B1 >> 11)·2^-53, z0 = √(−2 ln u1)·cos(2π u2), z1 = …·sin(2π u2).
-AM_FN void box_muller_u64(uint64_t B0, uint64_t B1, const MathTables *T, double &z0, double &z1)
+AM_FN void box_muller_u64(uint64_t B0, uint64_t B1, Tab tb, double &z0, double &z1)
 {
     const uint32_t a_lo = (uint32_t)B0, a_hi = (uint32_t)(B0 >> 32);
-    const double w = neg2log_words(a_hi >> 11, ((a_hi << 21) | (a_lo >> 11)) | 1u, T->log_rc, T->log_m2lc, T->e_m2ln2);
+    const double w = neg2log_words(a_hi >> 11, ((a_hi << 21) | (a_lo >> 11)) | 1u, tb);
     const double r = sqrt_pos(w);
     double s, c;
     const uint32_t b_lo = (uint32_t)B1, b_hi = (uint32_t)(B1 >> 32);
-    sincos_turn53_tab(b_hi >> 11, (b_hi << 21) | (b_lo >> 11), T->sincos, s, c);
+    sincos_turn53_tab(b_hi >> 11, (b_hi << 21) | (b_lo >> 11), tb, s, c);
     z0 = r * c;
     z1 = r * s;
 }
