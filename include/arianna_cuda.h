@@ -151,6 +151,18 @@ ARIANNA_API int32_t arianna_series_global(arianna_handle *h, int32_t n_stores, d
  * callers that can choose the length of a stretch should use a multiple of it. */
 ARIANNA_API int32_t arianna_series_per_launch(arianna_handle *h, int32_t *n);
 
+/* The same stretch as a complete job with HOST buffers: chains in (x_in, [n_chains], NULL = keep the resident state),
+ * n_stores store intervals, records out ([n_stores][3] local-shard sums, may be NULL), chains out (x_out, may be
+ * NULL) -- i.e. `chains = [...]; run!(Simulation(chains, (Metropolis, StoreCallbacks, StoreLastFrames), steps))`
+ * (src/simulation.jl:175-204) in one call.  The ensemble is cut into n_slices slices of chains that go through ALL the
+ * store intervals one slice after the other, so that the upload of the next slice and the download of the previous
+ * one overlap the sweep of the current one (pass page-locked buffers for the copies to be asynchronous).  Chains are
+ * independent: the final chains and counters are bit-identical to arianna_set_state + arianna_sweep_series +
+ * arianna_get_state, the records equal up to the order of the slice sums.  Synchronous: host buffers are complete /
+ * reusable on return.  Multi-GPU hosts all-reduce the device records afterwards (arianna_series_global). */
+ARIANNA_API int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_stores, const int64_t *K,
+                                         double *records, double *x_out, int32_t n_slices);
+
 /* Replay mode: the same K steps consuming caller-supplied draws instead of the native RNG, always in EXACT
  * arithmetic.  u_cat / z / u_acc are step-major [K][n_chains] (u_cat may be NULL when n_moves == 1);
  * `on_device` != 0 means the three pointers (and decisions_out) are device pointers.  decisions_out

@@ -71,6 +71,8 @@ SYMBOLS = {
     "arianna_series_device": (C.c_int32, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "arianna_series_global": (C.c_int32, [_H, C.c_int32, C.c_void_p]),
     "arianna_series_per_launch": (C.c_int32, [_H, C.POINTER(C.c_int32)]),
+    "arianna_run_host_job": (C.c_int32, [_H, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p,
+                                         C.c_int32]),
     "arianna_sweep_replay": (C.c_int32, [_H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "arianna_set_rng_state": (C.c_int32, [_H, C.c_void_p]),
     "arianna_get_rng_state": (C.c_int32, [_H, C.c_void_p]),

@@ -146,9 +146,18 @@ double host_lognorm(double sigma)
 
 int grid_for(const arianna_handle *h, int64_t M, int ctas_per_sm)
 {
-    int64_t need = (M + kBlock - 1) / kBlock;
-    int64_t cap = (int64_t)h->sm_count * ctas_per_sm;
-    return (int)(need < cap ? need : cap);
+    // at most `cap` CTAs, and every thread gets the same number of chains (to within one): with only a few chains
+    // per thread a grid of exactly `cap` CTAs leaves a ragged last round (3.46 chains per thread = 13 % imbalance)
+    const int64_t need = (M + kBlock - 1) / kBlock;
+    const int64_t cap = (int64_t)h->sm_count * ctas_per_sm;
+    if (need <= cap) return (int)need;
+    const int64_t per_thread = (need + cap - 1) / cap;
+    int64_t grid = (need + per_thread - 1) / per_thread;
+    // ... rounded up to whole resident waves (one wave = ctas_per_sm / waves CTAs per SM; callers pass a multiple of
+    // the SM count): a partial last wave costs more than a 2 % spread in chains per thread
+    const int64_t wave = (int64_t)h->sm_count * 4;
+    grid = (grid + wave - 1) / wave * wave;
+    return (int)(grid < cap ? grid : cap);
 }
 
 size_t ensure_scratch(arianna_handle *h, size_t bytes)
@@ -595,49 +604,27 @@ int32_t arianna_series_per_launch(arianna_handle *h, int32_t *n)
     return ARIANNA_OK;
 }
 
-int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t *K, double *records)
+// n_stores store intervals over the chains [off, off + m) of this handle, starting at MC step t0; records are written
+// to (accumulate = 0) or added into (1) d_series[0 .. n_stores).  Asynchronous on h->stream.
+static int32_t series_range(arianna_handle *h, int64_t off, int64_t m, int64_t t0, int32_t n_stores, const int64_t *K,
+                            int accumulate)
 {
-    if (!h) return ARIANNA_ERR_INVALID;
-    REQUIRE(h, n_stores >= 0 && (n_stores == 0 || K != nullptr), "arianna_sweep_series: bad arguments");
-    if (h->pool.n_moves != 1 || h->cfg.rng_mode != ARIANNA_RNG_PHILOX)
-        return fail(h, ARIANNA_ERR_UNSUPPORTED,
-                    "arianna_sweep_series: single-move pools with the native Philox stream only (use arianna_sweep)");
-    int64_t total = 0;
-    for (int32_t i = 0; i < n_stores; ++i) {
-        REQUIRE(h, K[i] >= 0 && K[i] < (int64_t(1) << 31), "arianna_sweep_series: K[i] must be in [0, 2^31)");
-        total += K[i];
-    }
-    REQUIRE(h, h->steps_done + total <= 0xFFFFFFFFll, "arianna_sweep_series: per-chain counters are 32-bit (2^32-1 steps max)");
-    h->series_n = 0;
-    if (n_stores == 0) return ARIANNA_OK;
-    DeviceGuard guard(h->device);
-    if (h->series_cap < n_stores) {
-        CU_TRY(h, cudaStreamSynchronize(h->stream));
-        cudaFree(h->d_series);
-        h->d_series = nullptr;
-        h->series_cap = 0;
-        const int64_t cap = n_stores < 1024 ? 1024 : n_stores;
-        CU_TRY(h, cudaMalloc(&h->d_series, sizeof(double) * 3 * cap));
-        h->series_cap = cap;
-    }
-    if (!h->d_series_partials)
-        CU_TRY(h, cudaMalloc(&h->d_series_partials,
-                             sizeof(double) * 2 * (kMaxSeries + 1) * (size_t)h->sm_count * 8 * kMaxGridWaves));
     const bool exact = h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
     const int per_launch = series_per_launch(h);
     for (int32_t s0 = 0; s0 < n_stores; s0 += per_launch) {
         const int ns = n_stores - s0 < per_launch ? n_stores - s0 : per_launch;
         SweepParams sp{};
-        sp.x = h->d_x; sp.acc = h->d_acc; sp.tot = nullptr; sp.betas = h->d_betas; sp.beta = h->cfg.beta;
-        sp.M = h->M; sp.t0 = h->steps_done;
-        sp.sid0 = (uint64_t)(h->cfg.seed + h->cfg.chain_offset);
+        sp.x = h->d_x + off; sp.acc = h->d_acc + off; sp.tot = nullptr;
+        sp.betas = h->d_betas ? h->d_betas + off : nullptr; sp.beta = h->cfg.beta;
+        sp.M = m; sp.t0 = t0;
+        sp.sid0 = (uint64_t)(h->cfg.seed + h->cfg.chain_offset + off);
         sp.tables = h->d_tables;
         sp.pool = h->pool;
         sp.n_series = ns;
         sp.series_partials = h->d_series_partials;
         SeriesK sk{};
         int64_t k_launch = 0;
-        bool even = (h->steps_done & 1) == 0;
+        bool even = (t0 & 1) == 0;
         for (int i = 0; i < ns; ++i) {
             sp.series_K[i] = sk.k[i] = (int)K[s0 + i];
             k_launch += K[s0 + i];
@@ -652,7 +639,7 @@ int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t 
             constexpr int POT = decltype(pot)::value;
             auto go = [&](auto kernel) -> int32_t {
                 CU_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                grid = wave_grid(h, kernel, smem, h->M);
+                grid = wave_grid(h, kernel, smem, m);
                 kernel<<<grid, kBlock, smem, h->stream>>>(sp);
                 return ARIANNA_OK;
             };
@@ -664,18 +651,134 @@ int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t 
         });
         if (rc) return rc;
         CU_TRY(h, cudaGetLastError());
-        series_fold_kernel<<<ns, kBlock, 0, h->stream>>>(h->d_series_partials, grid, ns, h->steps_done, sk, h->M,
-                                                       h->d_series + 3 * (size_t)s0, h->d_sums);
+        series_fold_kernel<<<ns, kBlock, 0, h->stream>>>(h->d_series_partials, grid, ns, t0, sk, m,
+                                                       h->d_series + 3 * (size_t)s0, h->d_sums, accumulate);
         CU_TRY(h, cudaGetLastError());
         h->launches += 2;
-        h->steps_done += k_launch;
+        t0 += k_launch;
     }
+    return ARIANNA_OK;
+}
+
+static int32_t series_prepare(arianna_handle *h, const char *who, int32_t n_stores, const int64_t *K, int64_t *total_out)
+{
+    REQUIRE(h, n_stores >= 0 && (n_stores == 0 || K != nullptr), std::string(who) + ": bad arguments");
+    if (h->pool.n_moves != 1 || h->cfg.rng_mode != ARIANNA_RNG_PHILOX)
+        return fail(h, ARIANNA_ERR_UNSUPPORTED,
+                    std::string(who) + ": single-move pools with the native Philox stream only (use arianna_sweep)");
+    int64_t total = 0;
+    for (int32_t i = 0; i < n_stores; ++i) {
+        REQUIRE(h, K[i] >= 0 && K[i] < (int64_t(1) << 31), std::string(who) + ": K[i] must be in [0, 2^31)");
+        total += K[i];
+    }
+    REQUIRE(h, h->steps_done + total <= 0xFFFFFFFFll, std::string(who) + ": per-chain counters are 32-bit (2^32-1 steps max)");
+    *total_out = total;
+    h->series_n = 0;
+    if (n_stores == 0) return ARIANNA_OK;
+    if (h->series_cap < n_stores) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_series);
+        h->d_series = nullptr;
+        h->series_cap = 0;
+        const int64_t cap = n_stores < 1024 ? 1024 : n_stores;
+        CU_TRY(h, cudaMalloc(&h->d_series, sizeof(double) * 3 * cap));
+        h->series_cap = cap;
+    }
+    if (!h->d_series_partials)
+        CU_TRY(h, cudaMalloc(&h->d_series_partials,
+                             sizeof(double) * 2 * (kMaxSeries + 1) * (size_t)h->sm_count * 8 * kMaxGridWaves));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t *K, double *records)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    int64_t total = 0;
+    int32_t rc = series_prepare(h, "arianna_sweep_series", n_stores, K, &total);
+    if (rc || n_stores == 0) return rc;
+    rc = series_range(h, 0, h->M, h->steps_done, n_stores, K, 0);
+    if (rc) return rc;
+    h->steps_done += total;
     h->series_n = n_stores;
     h->sums_valid = true;   // the last record doubles as the callback sums of the current state
     if (records) {
         CU_TRY(h, cudaMemcpyAsync(records, h->d_series, sizeof(double) * 3 * n_stores, cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
     }
+    return ARIANNA_OK;
+}
+
+// A whole callbacks-only job with HOST buffers, pipelined over slices of the chains: the upload of slice i+1 and the
+// download of slice i-1 run on the copy stream while slice i sweeps through ALL the store intervals on the compute
+// stream (chains are independent, so slice-major order gives the same chains and the same records as time-major).
+int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_stores, const int64_t *K, double *records,
+                             double *x_out, int32_t n_slices)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, n_slices >= 1 && n_slices <= 1024, "arianna_run_host_job: n_slices must be in 1..1024");
+    DeviceGuard guard(h->device);
+    int64_t total = 0;
+    int32_t rc = series_prepare(h, "arianna_run_host_job", n_stores, K, &total);
+    if (rc) return rc;
+    if (!h->copy_stream) {
+        CU_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+        CU_TRY(h, cudaEventRecord(h->ev_copy, h->copy_stream));
+    }
+    // slices: whole CTAs' worth of chains each
+    int64_t per = (h->M + n_slices - 1) / n_slices;
+    per = (per + kBlock - 1) / kBlock * kBlock;
+    const int ns = (int)((h->M + per - 1) / per);
+    std::vector<cudaEvent_t> up(ns, nullptr), done(ns, nullptr);
+    auto cleanup = [&]() {
+        for (auto e : up) if (e) cudaEventDestroy(e);
+        for (auto e : done) if (e) cudaEventDestroy(e);
+    };
+#define JOB_TRY(expr)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess) {                                                                              \
+            cleanup();                                                                                        \
+            return fail(h, ARIANNA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+        }                                                                                                     \
+    } while (0)
+    // everything already queued on the compute stream must be done with x before the uploads overwrite it
+    JOB_TRY(cudaEventRecord(h->ev_snap, h->stream));
+    JOB_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
+    for (int i = 0; i < ns; ++i) {
+        JOB_TRY(cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming));
+        JOB_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        const int64_t off = (int64_t)i * per, m = (h->M - off < per) ? h->M - off : per;
+        if (x_in) {
+            JOB_TRY(cudaMemcpyAsync(h->d_x + off, x_in + off, sizeof(double) * m, cudaMemcpyHostToDevice, h->copy_stream));
+            JOB_TRY(cudaEventRecord(up[i], h->copy_stream));
+        }
+    }
+    for (int i = 0; i < ns; ++i) {
+        const int64_t off = (int64_t)i * per, m = (h->M - off < per) ? h->M - off : per;
+        if (x_in) JOB_TRY(cudaStreamWaitEvent(h->stream, up[i], 0));
+        if (n_stores > 0) {
+            rc = series_range(h, off, m, h->steps_done, n_stores, K, i > 0);
+            if (rc) { cleanup(); return rc; }
+        }
+        if (x_out) {
+            JOB_TRY(cudaEventRecord(done[i], h->stream));
+            JOB_TRY(cudaStreamWaitEvent(h->copy_stream, done[i], 0));
+            JOB_TRY(cudaMemcpyAsync(x_out + off, h->d_x + off, sizeof(double) * m, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+    }
+    h->steps_done += total;
+    h->series_n = n_stores;
+    h->sums_valid = n_stores > 0;
+    if (records && n_stores > 0)
+        JOB_TRY(cudaMemcpyAsync(records, h->d_series, sizeof(double) * 3 * n_stores, cudaMemcpyDeviceToHost, h->stream));
+    JOB_TRY(cudaEventRecord(h->ev_copy, h->copy_stream));
+    JOB_TRY(cudaStreamSynchronize(h->stream));
+    JOB_TRY(cudaStreamSynchronize(h->copy_stream));
+#undef JOB_TRY
+    cleanup();
     return ARIANNA_OK;
 }
 

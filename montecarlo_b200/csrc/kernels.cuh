@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
 struct SeriesK { int k[kMaxSeries]; };
 __global__ void __launch_bounds__(kBlock) series_fold_kernel(const double *partials, int n_ctas, int n_series,
                                                              int64_t t0, const SeriesK series_K, int64_t M,
-                                                             double *out, double *sums)
+                                                             double *out, double *sums, int accumulate)
 {
     __shared__ double s_w[kWarpsPerBlock][2];
     __shared__ int64_t s_t;
@@ -582,9 +582,12 @@ __global__ void __launch_bounds__(kBlock) series_fold_kernel(const double *parti
         double te = 0.0, ta = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; ++w) { te += s_w[w][0]; ta += s_w[w][1]; }
-        const double r1 = ta / (double)s_t;
-        out[3 * s] = te; out[3 * s + 1] = r1; out[3 * s + 2] = (double)M;
-        if (s == n_series - 1 && sums) { sums[0] = te; sums[1] = r1; sums[2] = (double)M; }
+        // accumulate: this launch covered one SLICE of the chains (arianna_run_host_job); slices are folded one after
+        // the other on one stream, so the sum order is fixed
+        double r0 = te, r1 = ta / (double)s_t, r2 = (double)M;
+        if (accumulate) { r0 += out[3 * s]; r1 += out[3 * s + 1]; r2 += out[3 * s + 2]; }
+        out[3 * s] = r0; out[3 * s + 1] = r1; out[3 * s + 2] = r2;
+        if (s == n_series - 1 && sums) { sums[0] = r0; sums[1] = r1; sums[2] = r2; }
     }
 }
 

@@ -158,6 +158,24 @@ class CudaEnsemble:
                                                 _ptr(rec)))
         return rec
 
+    def run_host_job(self, Ks: Sequence[int], x_in=None, x_out=None, n_slices: int = 8, read: bool = True):
+        """A complete callbacks-only job with host buffers, pipelined over slices of the chains
+        (arianna_run_host_job): chains in, len(Ks) store intervals, records out, chains out.  x_in / x_out: numpy
+        arrays or raw pointers of page-locked host memory ([n_chains] f64), or None."""
+        ks = np.ascontiguousarray(Ks, dtype=np.int64)
+        rec = np.empty((ks.size, 3), dtype=np.float64) if read else None
+
+        def ptr(a):
+            if a is None:
+                return None
+            if isinstance(a, np.ndarray):
+                assert a.dtype == np.float64 and a.size == self.n_chains and a.flags.c_contiguous
+                return a.ctypes.data_as(C.c_void_p)
+            return C.c_void_p(int(a))
+        self._ck(self._lib.arianna_run_host_job(self._h, ptr(x_in), int(ks.size), ks.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                _ptr(rec), ptr(x_out), int(n_slices)))
+        return rec
+
     @property
     def series_per_launch(self) -> int:
         """Store intervals one sweep_series launch fuses for this ensemble (arianna_series_per_launch)."""

@@ -279,6 +279,36 @@ def test_series_equals_per_store_sweeps(arith, per_launch, even, monkeypatch):
         np.testing.assert_allclose(a.series_global(2), np.stack([s1, s2]), rtol=1e-13)
 
 
+@pytest.mark.parametrize("n_slices", [1, 3, 8])
+def test_host_job_pipelined_over_slices(n_slices):
+    """arianna_run_host_job == set_state + sweep_series + get_state: chains and counters bit-identical (chains are
+    independent, slice-major order changes nothing), records equal up to the order of the slice sums."""
+    import torch
+    M, seed = 100003, 5                                             # not a multiple of the slice / CTA size
+    Ks = [10] * 14 + [3, 7]
+    x0 = O.init_synthetic(seed, 0, M)
+    xin = torch.from_numpy(x0.copy()).pin_memory()
+    xout = torch.empty(M, dtype=torch.float64).pin_memory()
+    with mb.CudaEnsemble(M, 2.0, [0.1], seed=seed) as a, mb.CudaEnsemble(M, 2.0, [0.1], seed=seed) as b:
+        b.set_state(x0)
+        rec_b = b.sweep_series(Ks)
+        rec_a = a.run_host_job(Ks, x_in=xin.data_ptr(), x_out=xout.data_ptr(), n_slices=n_slices)
+        assert np.array_equal(xout.numpy(), b.get_state()) and np.array_equal(a.get_state(), b.get_state())
+        assert np.array_equal(a.chain_counters()[0], b.chain_counters()[0])
+        np.testing.assert_allclose(rec_a, rec_b, rtol=1e-13)
+        assert np.array_equal(rec_a[:, 2], np.full(len(Ks), float(M))) and a.steps_done == b.steps_done == sum(Ks)
+        np.testing.assert_array_equal(a.callback_sums(), rec_a[-1])
+        # a second job continues from the resident state (x_in = None) and may skip the download
+        rec_a2 = a.run_host_job([4, 4], n_slices=n_slices)
+        rec_b2 = b.sweep_series([4, 4])
+        np.testing.assert_allclose(rec_a2, rec_b2, rtol=1e-13)
+        assert np.array_equal(a.get_state(), b.get_state())
+    ref = O.Ensemble(x0, 2.0, [0.1])
+    _, z, ua = O.draws_philox(seed, 0, M, 0, sum(Ks) + 8, with_cat=False)
+    ref.sweep_replay(None, z, ua)
+    assert abs(rec_a2[-1, 0] / M / ref.callback_energy() - 1) < 1e-12
+
+
 def test_series_small_ensemble_and_errors():
     """M = 10 (BASELINE config 1's width): up to ARIANNA_MAX_SERIES stores per launch; multi-move pools refuse."""
     M, seed = 10, 42
