@@ -17,7 +17,7 @@ using ComponentArrays
 using Libdl
 using Random
 
-export CudaEnsemble, callback_acceptance_cuda, flush!, device_positions, nccl_unique_id, comm_init!, plan!
+export CudaEnsemble, callback_acceptance_cuda, flush!, device_positions, nccl_unique_id, comm_init!, plan!, run_host_job!
 
 const MAX_MOVES = 16
 const libarianna = Ref{String}(get(ENV, "ARIANNA_CUDA_LIB", "libarianna_cuda.so"))
@@ -159,6 +159,28 @@ function plan!(simulation::Simulation)
         return out
     end
     return nothing
+end
+
+"""
+    run_host_job!(ens, x_in, Ks; x_out=nothing, n_slices=8) -> records::Matrix{Float64} (3 × length(Ks))
+
+A whole callbacks-only job with host buffers in one call (arianna_run_host_job): chains in, `length(Ks)` store
+intervals of `Ks[i]` Metropolis steps, `(Σe, Σacc/tot, count)` per store out, final chains out; the library pipelines
+slices of chains so that the PCIe copies overlap the sweeps.  With a communicator the records are all-reduced.
+"""
+function run_host_job!(ens::CudaEnsemble, x_in::Union{Nothing,Vector{Float64}}, Ks::Vector{Int64};
+                       x_out::Union{Nothing,Vector{Float64}}=nothing, n_slices::Int=8)
+    flush!(ens)
+    n = length(Ks)
+    rec = Matrix{Float64}(undef, 3, n)
+    check(ens.handle, ccall((:arianna_run_host_job, libarianna[]), Int32,
+                            (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Int32), ens.handle,
+                            x_in === nothing ? C_NULL : pointer(x_in), n, Ks, C_NULL,
+                            x_out === nothing ? C_NULL : pointer(x_out), n_slices))
+    check(ens.handle, ccall((:arianna_series_global, libarianna[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}),
+                            ens.handle, n, rec))
+    ens.cache_t = -1
+    return rec
 end
 
 "One arianna_sweep_series call for [pending, K_1, K_2, ...]; every record lands in ens.series."
