@@ -120,6 +120,14 @@ AM_CONST double kExpK[8] = {
     1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,  // [3..6] expm1 Taylor, |r| ≤ ln2/64
     6755399441055744.0};    // [7] 1.5·2^52
 AM_CONST double kLogK[4] = {-2.0 / 7.0, 1.0 / 3.0, -0.4, -2.0 / 3.0};  // −2·log1p(r) = r(−2 + r(1 + k3 r + ½r² + k2 r³ + k1 r⁴ + k0 r⁵))
+// High-order coefficients whose terms are below 5·10^-11 of the result only need 20 mantissa bits: as doubles with a
+// zero low word they are encoded as 32-bit IMMEDIATES of DFMA/DMUL (no constant load, no register pair).  Truncation
+// errors: k2 r⁴·3.6e-7 < 2·10^-17, 1/120·φ⁴·6e-8 < 10^-19, 1/24·φ⁴·2.4e-7 < 10^-18 (|r| ≤ 2^-8, |φ| ≤ π/1024).
+constexpr double kLogK0t = -0x1.24924p-2;   // −2/7
+constexpr double kLogK1t = 0x1.55555p-2;    // 1/3
+constexpr double kLogK2t = -0x1.99999p-2;   // −2/5
+constexpr double kTrig120t = 0x1.11111p-7;  // 1/120
+constexpr double kTrig24t = 0x1.55555p-5;   // 1/24
 AM_CONST double kSinK[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
                             -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};
 AM_CONST double kCosK[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
@@ -396,9 +404,8 @@ AM_FN double neg2log_core(uint32_t hx_folded, uint32_t lx, int negE, Tab tb)
     const double rc = tab_ld(tb, kOffLogRc + i8);
     const double r = fma64(m, rc, -1.0);    // |r| ≤ 2^-8
     // −2·log1p(r) = r·(−2 + r·(1 − (2/3)r + (1/2)r² − (2/5)r³ + (1/3)r⁴ − (2/7)r⁵))
-    double q = kLogK[0];
-    q = fma64(q, r, kLogK[1]);
-    q = fma64(q, r, kLogK[2]);
+    double q = fma64(r, kLogK0t, kLogK1t);
+    q = fma64(q, r, kLogK2t);
     q = fma64(q, r, 0.5);
     q = fma64(q, r, kLogK[3]);
     q = fma64(q, r, 1.0);
@@ -494,12 +501,12 @@ AM_FN void sincos_turn53_tab(uint32_t k_hi, uint32_t k_lo, Tab tb, double &sn, d
     const uint32_t kk = k_hi + (1u << 10);                 // k + 2^42: round to the nearest direction
     const uint32_t i = (kk >> 11) & (uint32_t)(kTrigTab - 1);
     // rem = ((kk & 0x7ff) − 0x400)·2^32 + k_lo, converted exactly: bits(1.5·2^52) + rem, minus 1.5·2^52
-    const double d = hilo2double(0x43380000u - 0x400u + (kk & 0x7ffu), k_lo) - kTurnK[1];
+    const double d = hilo2double(0x43380000u - 0x400u + (kk & 0x7ffu), k_lo) - 6755399441055744.0;   // 1.5·2^52
     const double phi = d * kTurnK[0];
     const double z = phi * phi;
-    const double ps = fma64(z, kTrigK[0], kTrigK[1]);      // 1/120, −1/6
+    const double ps = fma64(z, kTrig120t, kTrigK[1]);      // 1/120, −1/6
     const double sphi = fma64(z * phi, ps, phi);
-    const double cm1 = fma64(z, kTrigK[2], -0.5) * z;      // 1/24
+    const double cm1 = fma64(z, kTrig24t, -0.5) * z;       // 1/24
     double S, C;
     tab_ld2(tb, kOffSinCos + 16u * i, S, C);
     sn = fma64(C, sphi, fma64(S, cm1, S));
