@@ -232,7 +232,8 @@ ARIANNA_API int32_t arianna_pgmc_read_global(arianna_handle *h, arianna_gradient
 /* Diagnostic: evaluates the device FP64 math layer (csrc/math64.cuh) on host arrays so that tests can compare
  * the device code paths with extended-precision references.  kind: 0 min(1,exp(a)) | 1 -2 ln(b 2^-53) | 2 sqrt(a) |
  * 3 sin/cos(2 pi b 2^-53) -> out[2i], out[2i+1] | 4 Box-Muller(b, c) -> out[2i], out[2i+1] | 5 accept test of
- * x = a with prefix word b and refinement word c -> out[2i] = FP32-filtered, out[2i+1] = plain FP64 decision |
+ * x = a with the 11-bit prefix word b and refinement word c -> out[2i] = FP32-filtered, out[2i+1] = plain FP64
+ * decision (8: the same with a 12-bit prefix) | 9 -2 ln(b 2^-52), b < 2^52 (the Box-Muller radius form) |
  * 6 / 7 Philox4x32-10 block of the Metropolis stream for (sid = b, p = c[, sub = a]) through the per-chain hoisted
  * form (sub 0) / the general form -> out[4i .. 4i+3] = the four 32-bit output words. */
 ARIANNA_API int32_t arianna_debug_math(arianna_handle *h, int32_t kind, const double *a, const uint64_t *b,

@@ -1204,10 +1204,10 @@ int32_t arianna_debug_math(arianna_handle *h, int32_t kind, const double *a, con
                            double *out, int64_t n)
 {
     if (!h) return ARIANNA_ERR_INVALID;
-    REQUIRE(h, kind >= 0 && kind <= 7 && out != nullptr && n >= 0, "arianna_debug_math: bad arguments");
+    REQUIRE(h, kind >= 0 && kind <= 9 && out != nullptr && n >= 0, "arianna_debug_math: bad arguments");
     if (n == 0) return ARIANNA_OK;
     DeviceGuard guard(h->device);
-    const int64_t nout = (kind >= 6) ? 4 * n : (kind >= 3) ? 2 * n : n;
+    const int64_t nout = (kind == 6 || kind == 7) ? 4 * n : (kind == 9 || kind < 3) ? n : 2 * n;
     const size_t bytes = sizeof(double) * (size_t)(nout + 3 * n);
     if (!ensure_scratch(h, bytes)) return fail(h, ARIANNA_ERR_NOMEM, "arianna_debug_math: scratch allocation failed");
     double *d_out = h->d_scratch;

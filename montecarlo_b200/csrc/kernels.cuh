@@ -163,14 +163,14 @@ __device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, 
 // FAST: symmetric proposal => log q terms cancel; α > u  <=>  exp(β(e - e')) > u  because u < 1; reject restores x.
 // The accept uniform arrives as (ulo, cell, exact_u): a float cell [ulo, ulo + cell) that contains u and a callable
 // producing the exact 53-bit u on demand (see m64::exp_accept).
-// A cell with cell < 0 carries the 11-bit prefix of the native stream in `ulo`'s bits (integer-domain filter).
-struct CellP11 { uint32_t f; };
+template <int PBITS>
+struct CellP { uint32_t f; };     // PBITS-bit prefix of the accept uniform: u ∈ [f, f+1)·2^-PBITS
 struct CellF { float ulo, cell; };
 
-template <class ExactU>
-__device__ __forceinline__ bool accept_in_cell(double arg, CellP11 c, ExactU exact_u, m64::Tab tb)
+template <int PBITS, class ExactU>
+__device__ __forceinline__ bool accept_in_cell(double arg, CellP<PBITS> c, ExactU exact_u, m64::Tab tb)
 {
-    return m64::exp_accept_prefix11(arg, c.f, exact_u, tb);
+    return m64::exp_accept_prefix<PBITS>(arg, c.f, exact_u, tb);
 }
 template <class ExactU>
 __device__ __forceinline__ bool accept_in_cell(double arg, CellF c, ExactU exact_u, m64::Tab tb)
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         // uniform come from sub-block 1 of the pair and are only generated when the FP32 filter cannot decide (lazy refinement).
         struct PairDraws {
             double z0, z1;
-            uint32_t f0, f1;   // 11-bit prefixes of u_acc(2p), u_acc(2p+1)
+            uint32_t f0, f1;   // 12-bit / 11-bit prefixes of u_acc(2p), u_acc(2p+1)
             uint64_t pr;
             U64Pair b2;        // categorical uniforms (multi-move pools)
         };
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
             PairDraws d;
             const U64Pair b0 = ph.block((uint32_t)pr);
             m64::box_muller_u64(u64_of(b0.a_lo, b0.a_hi), u64_of(b0.b_lo, b0.b_hi), tb, d.z0, d.z1);
-            d.f0 = b0.a_lo & 0x7ffu;
+            d.f0 = b0.a_lo & 0xfffu;   // 12 bits: the radius uniform takes A >> 12
             d.f1 = b0.b_lo & 0x7ffu;
             d.pr = pr;
             d.b2 = U64Pair{};
@@ -401,9 +401,9 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
             if constexpr (decltype(do0)::value) {
                 auto exact_u = [&]() {
                     const U64Pair r = philox_block<kTagMetropolis>(sid, d.pr, 1);
-                    return m64::u53_prefix_refine(d.f0, r.a_lo, r.a_hi);
+                    return m64::u53_prefix_refine<12>(d.f0, r.a_lo, r.a_hi);
                 };
-                const CellP11 ulo{d.f0};
+                const CellP<12> ulo{d.f0};
                 if constexpr (MULTI) {
                     const int k = categorical(nm, s_weight, u53(d.b2.a_lo, d.b2.a_hi));
                     const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z0, ulo,
@@ -418,9 +418,9 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
             if constexpr (decltype(do1)::value) {
                 auto exact_u = [&]() {
                     const U64Pair r = philox_block<kTagMetropolis>(sid, d.pr, 1);
-                    return m64::u53_prefix_refine(d.f1, r.b_lo, r.b_hi);
+                    return m64::u53_prefix_refine<11>(d.f1, r.b_lo, r.b_hi);
                 };
-                const CellP11 ulo{d.f1};
+                const CellP<11> ulo{d.f1};
                 if constexpr (MULTI) {
                     const int k = categorical(nm, s_weight, u53(d.b2.b_lo, d.b2.b_hi));
                     const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z1, ulo,
@@ -999,6 +999,7 @@ __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const doub
         else if (kind == 2) out[i] = m64::sqrt_pos(a[i]);
         else if (kind == 3) m64::sincos_turn53_tab((uint32_t)(b[i] >> 32), (uint32_t)b[i], tb, out[2 * i], out[2 * i + 1]);
         else if (kind == 4) m64::box_muller_u64(b[i], cc[i], tb, out[2 * i], out[2 * i + 1]);
+        else if (kind == 9) out[i] = m64::neg2log_k52((uint32_t)(b[i] >> 32), (uint32_t)b[i], tb);
         else if (kind == 6 || kind == 7) {
             // Philox4x32-10 block (sid = b, p = c): 6 = per-chain hoisted form (sub 0), 7 = general form, sub = a
             U64Pair r;
@@ -1007,11 +1008,18 @@ __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const doub
             out[4 * i] = (double)r.a_lo; out[4 * i + 1] = (double)r.a_hi;
             out[4 * i + 2] = (double)r.b_lo; out[4 * i + 3] = (double)r.b_hi;
         } else {
-            const uint32_t f = (uint32_t)b[i] & 0x7ffu;
             const uint64_t r = cc[i];
-            auto exact_u = [&]() { return m64::u53_prefix_refine(f, (uint32_t)r, (uint32_t)(r >> 32)); };
-            out[2 * i] = m64::exp_accept_prefix11(a[i], f, exact_u, tb) ? 1.0 : 0.0;
-            out[2 * i + 1] = m64::exp_accept_ref(a[i], exact_u(), tb) ? 1.0 : 0.0;
+            if (kind == 5) {
+                const uint32_t f = (uint32_t)b[i] & 0x7ffu;
+                auto exact_u = [&]() { return m64::u53_prefix_refine<11>(f, (uint32_t)r, (uint32_t)(r >> 32)); };
+                out[2 * i] = m64::exp_accept_prefix<11>(a[i], f, exact_u, tb) ? 1.0 : 0.0;
+                out[2 * i + 1] = m64::exp_accept_ref(a[i], exact_u(), tb) ? 1.0 : 0.0;
+            } else {
+                const uint32_t f = (uint32_t)b[i] & 0xfffu;
+                auto exact_u = [&]() { return m64::u53_prefix_refine<12>(f, (uint32_t)r, (uint32_t)(r >> 32)); };
+                out[2 * i] = m64::exp_accept_prefix<12>(a[i], f, exact_u, tb) ? 1.0 : 0.0;
+                out[2 * i + 1] = m64::exp_accept_ref(a[i], exact_u(), tb) ? 1.0 : 0.0;
+            }
         }
     }
 }

@@ -341,11 +341,13 @@ AM_FN int float2int_floor(float v)
     return (v != v) ? 0 : (int)floorf(v);
 #endif
 }
-template <class ExactU>
-AM_FN bool exp_accept_prefix11(double x, uint32_t f, ExactU exact_u, Tab tb)
+// PBITS = length of the prefix (11 for the odd step of a pair, 12 for the even one: DESIGN.md "RNG stream layout");
+// the bound above is for 11 + log2e·127 < 256, unchanged for 12.
+template <int PBITS, class ExactU>
+AM_FN bool exp_accept_prefix(double x, uint32_t f, ExactU exact_u, Tab tb)
 {
     const float a = (float)x;
-    const float Es = ex2_approx(fmaf(a, 1.44269504f, 11.0f));
+    const float Es = ex2_approx(fmaf(a, 1.44269504f, (float)PBITS));
     const int ilo = float2int_floor(Es * 0.9998779296875f);    // 1 − 2^-13
     const int ihi = float2int_floor(Es * 1.0001220703125f);    // 1 + 2^-13
     bool acc = (a >= 0.0f) || (ilo > (int)f);
@@ -363,12 +365,14 @@ AM_FN bool exp_accept_prefix11(double x, uint32_t f, ExactU exact_u, Tab tb)
 AM_FN float ulo_from_word23(uint32_t w_hi) { return uint_as_float(0x3f800000u | (w_hi >> 9)) - 1.0f; }
 // Filter cell from an 11-bit prefix f: u ∈ [f·2^-11, (f+1)·2^-11) (native Philox mode).
 AM_FN float ulo_from_prefix11(uint32_t f) { return uint_as_float(0x3f800000u | (f << 12)) - 1.0f; }
-// Exact native-mode uniform: u = ((f << 42) | r)·2^-53 with r = (word >> 22) the 42 refinement bits.
+// Exact native-mode uniform: u = ((f << (53 − PBITS)) | r)·2^-53 with r = word >> (11 + PBITS), the 53 − PBITS
+// refinement bits (PBITS = 11: 42 bits, PBITS = 12: 41 bits).
+template <int PBITS>
 AM_FN double u53_prefix_refine(uint32_t f, uint32_t r_lo, uint32_t r_hi)
 {
-    // r = word >> 22: r_hi10 = r_hi >> 22 (10 bits), r_lo32 = (r_hi << 10) | (r_lo >> 22)
-    const uint32_t k_hi = (f << 10) | (r_hi >> 22);
-    const uint32_t k_lo = (r_hi << 10) | (r_lo >> 22);
+    // k = (f << (53 − PBITS)) | (word >> (11 + PBITS)): k_hi = top 21 bits, k_lo = low 32 bits
+    const uint32_t k_hi = (f << (21 - PBITS)) | (r_hi >> (11 + PBITS));
+    const uint32_t k_lo = (r_hi << (21 - PBITS)) | (r_lo >> (11 + PBITS));
     const double dh = hilo2double(0x41E00000u, k_hi);
     const double dl = hilo2double(0x3FE00000u, k_lo);
     return (dh - 2147483648.5) + dl;
@@ -438,6 +442,18 @@ AM_FN double neg2log_words(uint32_t k_hi, uint32_t k_lo, Tab tb)
     const uint32_t hx = double2hi(u) + (0x3ff00000u - kHxBase);
     const int negE = 0x3ff - (int)(hx >> 20);           // −E ∈ [0, 53]
     return neg2log_core((hx & 0x000fffffu) + kHxBase, double2lo(u), negE, tb);
+}
+
+// −2·ln(k·2^-52) for a 52-bit k given as (k_hi: top 20 bits, k_lo: low 32 bits), k ≥ 1: the Box-Muller radius of the
+// native stream.  k fits the mantissa field of one double: bits(0x433 | k) = 2^52 + k, so ONE exact DADD with an
+// immediate recovers k as a normalised double (the 53-bit form above needs two DADDs and three materialised
+// constants); the 2^-52 is folded into the exponent bookkeeping.
+AM_FN double neg2log_k52(uint32_t k_hi, uint32_t k_lo, Tab tb)
+{
+    const double kd = hilo2double(0x43300000u | k_hi, k_lo) - 4503599627370496.0;   // exact
+    const uint32_t hx = double2hi(kd) + (0x3ff00000u - kHxBase);
+    const int negE = (0x3ff + 52) - (int)(hx >> 20);    // −E ∈ [0, 52]
+    return neg2log_core((hx & 0x000fffffu) + kHxBase, double2lo(kd), negE, tb);
 }
 
 // ---- √w, w > 0 normal ---------------------------------------------------------------------------------------
@@ -514,12 +530,12 @@ AM_FN void sincos_turn53_tab(uint32_t k_hi, uint32_t k_lo, Tab tb, double &sn, d
 }
 
 // Box-Muller from two raw 64-bit Philox words (B0 -> radius, B1 -> angle); same definition as the oracle:
-//   u1 = ((B0 >> 11) | 1)·2^-53 ∈ (0,1) (odd lattice: never 0 or 1, so −2 ln u1 > 0 without a special case),
+//   u1 = ((B0 >> 12) | 1)·2^-52 ∈ (0,1) (odd lattice: never 0 or 1, so −2 ln u1 > 0 without a special case),
 //   u2 = (B1 >> 11)·2^-53, z0 = √(−2 ln u1)·cos(2π u2), z1 = …·sin(2π u2).
 AM_FN void box_muller_u64(uint64_t B0, uint64_t B1, Tab tb, double &z0, double &z1)
 {
     const uint32_t a_lo = (uint32_t)B0, a_hi = (uint32_t)(B0 >> 32);
-    const double w = neg2log_words(a_hi >> 11, ((a_hi << 21) | (a_lo >> 11)) | 1u, tb);
+    const double w = neg2log_k52(a_hi >> 12, ((a_hi << 20) | (a_lo >> 12)) | 1u, tb);
     const double r = sqrt_pos(w);
     double s, c;
     const uint32_t b_lo = (uint32_t)B1, b_hi = (uint32_t)(B1 >> 32);

@@ -359,7 +359,7 @@ class CudaEnsemble:
         arrs = [None if v is None else np.ascontiguousarray(v, dtype=t)
                 for v, t in ((a, np.float64), (b, np.uint64), (c, np.uint64))]
         n = next(v.size for v in arrs if v is not None)
-        out = np.empty(4 * n if kind >= 6 else 2 * n if kind >= 3 else n, dtype=np.float64)
+        out = np.empty(4 * n if kind in (6, 7) else n if (kind == 9 or kind < 3) else 2 * n, dtype=np.float64)
         self._ck(self._lib.arianna_debug_math(self._h, int(kind), _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
                                               _ptr(out), n))
         return out

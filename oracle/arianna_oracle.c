@@ -74,15 +74,16 @@ static inline void philox_block(uint64_t sid, uint64_t p, uint32_t sub, uint32_t
 }
 
 static inline double u53(uint64_t w) { return (double)(w >> 11) * 0x1.0p-53; }
-/* (0,1) variant for the Box-Muller radius: odd 53-bit lattice, so log() never sees 0 and never returns 0 */
-static inline double u53_open0(uint64_t w) { return (double)((w >> 11) | 1) * 0x1.0p-53; }
+/* (0,1) variant for the Box-Muller radius: odd 52-bit lattice (top 52 bits of the word), so log() never sees 0 and
+ * never returns 0; the low 12 bits of the word are left for the accept-uniform prefix of the pair's even step */
+static inline double u52_open0(uint64_t w) { return (double)((w >> 12) | 1) * 0x1.0p-52; }
 
 #define AO_TWO_PI 6.283185307179586 /* binary64 nearest of 2pi == Julia's 2π (particle_1d.jl:53) */
 
 /* Box-Muller pair from the two B words of blocks (b0, b1). */
 static inline void box_muller(uint64_t B0, uint64_t B1, double *z0, double *z1)
 {
-    double u1 = u53_open0(B0);
+    double u1 = u52_open0(B0);
     double u2 = u53(B1);
     double r = sqrt(-2.0 * log(u1));
     double a = AO_TWO_PI * u2;
@@ -104,10 +105,10 @@ AO_API void ao_init_synthetic(int64_t seed, int64_t chain_offset, int64_t M, dou
 
 /* Native-mode Metropolis draws for MC steps t0 .. t0+K-1 of chains [chain_offset, chain_offset+M), written
  * as step-major [K][M] arrays so that native mode == replay of these arrays.
- *   pair p = t >> 1:  sub-block 0: words (A, B): A>>11 -> Box-Muller u1 (|1), B>>11 -> Box-Muller u2;
- *                                 A & 0x7ff -> 11-bit PREFIX of u_acc(2p), B & 0x7ff -> prefix of u_acc(2p+1)
- *                     sub-block 1: A>>22 -> 42 refinement bits of u_acc(2p), B>>22 -> of u_acc(2p+1)
- *                                 u_acc = ((prefix << 42) | refinement) * 2^-53   (the engine only generates
+ *   pair p = t >> 1:  sub-block 0: words (A, B): A>>12 -> Box-Muller u1 (|1, 52 bits), B>>11 -> Box-Muller u2;
+ *                                 A & 0xfff -> 12-bit PREFIX of u_acc(2p), B & 0x7ff -> 11-bit prefix of u_acc(2p+1)
+ *                     sub-block 1: A>>23 -> 41 refinement bits of u_acc(2p), B>>22 -> 42 of u_acc(2p+1)
+ *                                 u_acc = ((prefix << (53 - bits)) | refinement) * 2^-53   (the engine only generates
  *                                 this block when its FP32 filter cannot decide from the prefix alone)
  *                     sub-block 2: A -> u_cat(2p), B -> u_cat(2p+1)      (only consumed when n_moves > 1)
  *   z(2p) = r cos(2π u2), z(2p+1) = r sin(2π u2).
@@ -128,9 +129,10 @@ AO_API void ao_draws_philox(int64_t seed, int64_t chain_offset, int64_t M, int64
             box_muller(A0, B0, &z0, &z1);
             int odd = (int)(t & 1);
             z[s * M + c] = odd ? z1 : z0;
-            uint64_t prefix = (odd ? B0 : A0) & 0x7ffu;
-            uint64_t refine = (odd ? B1 : A1) >> 22;
-            u_acc[s * M + c] = (double)((prefix << 42) | refine) * 0x1.0p-53;
+            /* even step: 12-bit prefix (A0's low 12 bits) + 41 refinement bits; odd step: 11 + 42 */
+            uint64_t prefix = odd ? (B0 & 0x7ffu) : (A0 & 0xfffu);
+            uint64_t refine = odd ? (B1 >> 22) : (A1 >> 23);
+            u_acc[s * M + c] = (double)((prefix << (odd ? 42 : 41)) | refine) * 0x1.0p-53;
             if (u_cat) {
                 uint64_t A2, B2;
                 philox_block(sid, p, 2, AO_TAG_METROPOLIS, &A2, &B2);

@@ -11,12 +11,13 @@ extern "C" {
 void m64_exp(const double *x, double *out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = exp_nonpos(x[i], Tab{&T}); }
 void m64_neg2log(const uint64_t *k, double *out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = neg2log_u53(k[i], Tab{&T}); }
 void m64_neg2log_words(const uint64_t *k, double *out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = neg2log_words((uint32_t)(k[i] >> 32), (uint32_t)k[i], Tab{&T}); }
+void m64_neg2log_k52(const uint64_t *k, double *out, long n) { init(); for (long i = 0; i < n; ++i) out[i] = neg2log_k52((uint32_t)(k[i] >> 32), (uint32_t)k[i], Tab{&T}); }
 void m64_sqrt(const double *x, double *out, long n) { for (long i = 0; i < n; ++i) out[i] = sqrt_pos(x[i]); }
 void m64_sincos(const uint64_t *k, double *s, double *c, long n) { init(); for (long i = 0; i < n; ++i) sincos_turn53_tab((uint32_t)(k[i] >> 32), (uint32_t)k[i], Tab{&T}, s[i], c[i]); }
 void m64_sincos_poly(const uint64_t *k, double *s, double *c, long n) { for (long i = 0; i < n; ++i) sincos_turn53(k[i], s[i], c[i]); }
 void m64_box_muller(const uint64_t *b0, const uint64_t *b1, double *z0, double *z1, long n) { init(); for (long i = 0; i < n; ++i) box_muller_u64(b0[i], b1[i], Tab{&T}, z0[i], z1[i]); }
-// mode 0: XOSHIRO-style word (23-bit cell, u = (w >> 11) 2^-53); mode 1: native (11-bit prefix f = w & 0x7ff,
-// refinement word r given separately)
+// mode 0: XOSHIRO-style word (23-bit cell, u = (w >> 11) 2^-53); mode 1 / 3: native (11- / 12-bit prefix = the low
+// bits of w, refinement word r given separately); mode 2: directed-rounding float cell of an arbitrary double
 void m64_accept(const double *x, const uint64_t *w, const uint64_t *r, int mode, unsigned char *filt,
                 unsigned char *ref, double *u_out, long n)
 {
@@ -29,10 +30,16 @@ void m64_accept(const double *x, const uint64_t *w, const uint64_t *r, int mode,
             else { float a, b; ucell_from_double(u, a, b); filt[i] = exp_accept(x[i], a, b, [&] { return u; }, Tab{&T}); }
             ref[i] = exp_accept_ref(x[i], u, Tab{&T});
             u_out[i] = u;
-        } else {
+        } else if (mode == 1) {
             const uint32_t f = lo & 0x7ffu;
-            const double u = u53_prefix_refine(f, (uint32_t)r[i], (uint32_t)(r[i] >> 32));
-            filt[i] = exp_accept_prefix11(x[i], f, [&] { return u; }, Tab{&T});
+            const double u = u53_prefix_refine<11>(f, (uint32_t)r[i], (uint32_t)(r[i] >> 32));
+            filt[i] = exp_accept_prefix<11>(x[i], f, [&] { return u; }, Tab{&T});
+            ref[i] = exp_accept_ref(x[i], u, Tab{&T});
+            u_out[i] = u;
+        } else {
+            const uint32_t f = lo & 0xfffu;
+            const double u = u53_prefix_refine<12>(f, (uint32_t)r[i], (uint32_t)(r[i] >> 32));
+            filt[i] = exp_accept_prefix<12>(x[i], f, [&] { return u; }, Tab{&T});
             ref[i] = exp_accept_ref(x[i], u, Tab{&T});
             u_out[i] = u;
         }

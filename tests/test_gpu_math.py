@@ -37,6 +37,11 @@ def test_device_neg2log_sqrt_sincos(eng):
                         rng.integers(1, 2 ** 20, size=100000, dtype=np.uint64) | np.uint64(1)])
     w = eng.debug_math(1, b=k)
     assert ulp_err(w, -2 * np.log(k.astype(LD) * LD(2) ** -53)).max() <= 2.5 and w.min() > 0
+    k52 = np.concatenate([rng.integers(1, 2 ** 52, size=500000, dtype=np.uint64) | np.uint64(1),
+                          np.array([1, 3, 2 ** 52 - 1, 2 ** 51 + 1, 2 ** 51 - 1], dtype=np.uint64),
+                          rng.integers(1, 2 ** 20, size=100000, dtype=np.uint64) | np.uint64(1)])
+    w52 = eng.debug_math(9, b=k52)                                   # the Box-Muller radius form (one DADD)
+    assert ulp_err(w52, -2 * np.log(k52.astype(LD) * LD(2) ** -52)).max() <= 2.5 and w52.min() > 0
     v = np.concatenate([rng.random(300000) * 75, 10.0 ** rng.uniform(-16, 2, size=300000)])
     assert ulp_err(eng.debug_math(2, a=v), np.sqrt(v.astype(LD))).max() <= 1.0     # Newton from the MUFU.RSQ64H seed
     kk = np.concatenate([rng.integers(0, 2 ** 53, size=500000, dtype=np.uint64),
@@ -52,7 +57,7 @@ def test_device_box_muller(eng):
     b0 = rng.integers(0, 2 ** 64, size=400000, dtype=np.uint64)
     b1 = rng.integers(0, 2 ** 64, size=400000, dtype=np.uint64)
     z = eng.debug_math(4, b=b0, c=b1).reshape(-1, 2)
-    u1 = ((b0 >> np.uint64(11)) | np.uint64(1)).astype(LD) * LD(2) ** -53
+    u1 = ((b0 >> np.uint64(12)) | np.uint64(1)).astype(LD) * LD(2) ** -52
     u2 = (b1 >> np.uint64(11)).astype(LD) * LD(2) ** -53
     r = np.sqrt(-2 * np.log(u1))
     twopi = LD(2) * np.arctan(LD(1)) * 4
@@ -82,8 +87,11 @@ def test_device_philox_kat(eng):
     assert np.array_equal(got.astype(np.uint64), want)
 
 
-def test_device_fp32_filter_never_changes_a_decision(eng):
-    rng = np.random.default_rng(7)
+@pytest.mark.parametrize("pbits,kind", [(11, 5), (12, 8)])
+def test_device_fp32_filter_never_changes_a_decision(eng, pbits, kind):
+    """Integer-domain prefix filter (11-bit prefix: odd step of a pair, 12-bit: even step) on the DEVICE (MUFU.EX2,
+    F2I) against the plain FP64 decision, half of the cases adversarial near-ties."""
+    rng = np.random.default_rng(7 + pbits)
     n = 4_000_000
     x = -rng.random(n) * rng.choice([0.01, 1.0, 3.0, 30.0, 300.0], size=n)
     w = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
@@ -91,9 +99,10 @@ def test_device_fp32_filter_never_changes_a_decision(eng):
     h = n // 2
     tie = np.exp(x[:h]) * (1 + rng.normal(size=h) * 2.0 ** -rng.integers(18, 40, size=h))
     k = np.clip(tie * 2.0 ** 53, 0, 2 ** 53 - 1).astype(np.uint64)
-    w[:h] = (w[:h] & ~np.uint64(0x7ff)) | (k >> np.uint64(42))
-    r[:h] = (k & np.uint64(2 ** 42 - 1)) << np.uint64(22)
-    d = eng.debug_math(5, a=x, b=w, c=r).reshape(-1, 2)
+    rb = 53 - pbits
+    w[:h] = (w[:h] & ~np.uint64(2 ** pbits - 1)) | (k >> np.uint64(rb))
+    r[:h] = (k & np.uint64(2 ** rb - 1)) << np.uint64(64 - rb)
+    d = eng.debug_math(kind, a=x, b=w, c=r).reshape(-1, 2)
     assert np.array_equal(d[:, 0], d[:, 1])
     u = np.concatenate([k.astype(np.float64) * 2.0 ** -53])
     with np.errstate(all="ignore"):

@@ -58,6 +58,14 @@ def test_neg2log_accuracy(lib):
     out2 = np.empty(k.size)
     lib.m64_neg2log_words(P(k), P(out2), C.c_long(k.size))
     assert np.array_equal(out, out2)             # the DADD-normalised variant is the same function, bit for bit
+    # the 52-bit form the Box-Muller radius uses: −2 ln(k 2^-52), one exact DADD
+    k52 = np.concatenate([rng.integers(1, 2 ** 52, size=400000, dtype=np.uint64) | np.uint64(1),
+                          np.array([1, 3, 2 ** 52 - 1, 2 ** 51 + 1, 2 ** 51 - 1], dtype=np.uint64),
+                          (np.uint64(2 ** 52) - rng.integers(1, 2 ** 20, size=100000, dtype=np.uint64)) | np.uint64(1),
+                          rng.integers(1, 2 ** 20, size=100000, dtype=np.uint64) | np.uint64(1)])
+    out3 = np.empty(k52.size)
+    lib.m64_neg2log_k52(P(k52), P(out3), C.c_long(k52.size))
+    assert ulp_err(out3, -2 * np.log(k52.astype(LD) * LD(2) ** -52)).max() <= 2.5 and out3.min() > 0
 
 
 def test_sqrt_is_correctly_rounded(lib):
@@ -98,7 +106,7 @@ def test_box_muller_matches_oracle_definition(lib):
     b1 = rng.integers(0, 2 ** 64, size=100000, dtype=np.uint64)
     z0, z1 = np.empty(b0.size), np.empty(b0.size)
     lib.m64_box_muller(P(b0), P(b1), P(z0), P(z1), C.c_long(b0.size))
-    u1 = ((b0 >> np.uint64(11)) | np.uint64(1)).astype(LD) * LD(2) ** -53
+    u1 = ((b0 >> np.uint64(12)) | np.uint64(1)).astype(LD) * LD(2) ** -52
     u2 = (b1 >> np.uint64(11)).astype(LD) * LD(2) ** -53
     r = np.sqrt(-2 * np.log(u1))
     twopi = LD(2) * np.arctan(LD(1)) * 4
@@ -108,10 +116,11 @@ def test_box_muller_matches_oracle_definition(lib):
     assert abs(zz.mean()) < 4 / np.sqrt(zz.size) and abs(zz.std() - 1) < 4 / np.sqrt(2 * zz.size)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_fp32_filter_never_changes_a_decision(lib, mode):
-    """mode 0: 23-bit cell of a 53-bit word (XOSHIRO path); mode 1: 11-bit prefix + lazy 42-bit refinement (native);
-    mode 2: directed-rounding float cell of an arbitrary double u (replay / EXACT paths)."""
+    """mode 0: 23-bit cell of a 53-bit word (XOSHIRO path); mode 1 / 3: 11- / 12-bit prefix + lazy 42- / 41-bit
+    refinement (native, odd / even step of a pair); mode 2: directed-rounding float cell of an arbitrary double u
+    (replay / EXACT paths)."""
     rng = np.random.default_rng(6 + mode)
     n = 2_000_000
     x = -rng.random(n) * rng.choice([0.01, 1.0, 3.0, 30.0, 300.0], size=n)
@@ -123,9 +132,12 @@ def test_fp32_filter_never_changes_a_decision(lib, mode):
     k = np.clip(tie * 2.0 ** 53, 0, 2 ** 53 - 1).astype(np.uint64)
     if mode in (0, 2):
         w[:h] = (k << np.uint64(11)) | (w[:h] & np.uint64(0x7ff))
-    else:
+    elif mode == 1:
         w[:h] = (w[:h] & ~np.uint64(0x7ff)) | (k >> np.uint64(42))
         r[:h] = (k & np.uint64(2 ** 42 - 1)) << np.uint64(22)
+    else:
+        w[:h] = (w[:h] & ~np.uint64(0xfff)) | (k >> np.uint64(41))
+        r[:h] = (k & np.uint64(2 ** 41 - 1)) << np.uint64(23)
     x = np.concatenate([x, [0.0, -0.0, 1e-300, 5.0, -708.0, -709.0, -1e10, -np.inf, np.nan, 1e308, -1e-320]])
     w = np.concatenate([w, rng.integers(0, 2 ** 64, size=11, dtype=np.uint64)])
     r = np.concatenate([r, rng.integers(0, 2 ** 64, size=11, dtype=np.uint64)])

@@ -67,7 +67,7 @@ def test_philox_draws_layout_and_moments():
     n = z.size
     assert abs(z.mean()) < 4 / math.sqrt(n) and abs(z.std() - 1) < 4 / math.sqrt(2 * n)
     # numpy restatement of the counter layout for chain 3, pair 0 (lazy-refinement layout):
-    # u_acc(step 0) = ((A0 & 0x7ff) << 42 | A1 >> 22) * 2^-53 with A0 from sub-block 0, A1 from sub-block 1
+    # even step: 12-bit prefix + 41 refinement bits, odd step: 11 + 42; the radius uniform takes the top 52 bits of A0
     sid = 42 + 5 + 3
     # layout v2: ctr = (sid_lo, p, sid_hi, sub), key = (tag, 'ARIA'); pair p = 0, sub-blocks 0 and 1
     o0 = N.philox4x32_10(sid & 0xffffffff, 0, sid >> 32, 0, 1, 0x41524941)
@@ -76,9 +76,9 @@ def test_philox_draws_layout_and_moments():
     B0 = int(o0[2]) | (int(o0[3]) << 32)
     A1 = int(o1[0]) | (int(o1[1]) << 32)
     B1 = int(o1[2]) | (int(o1[3]) << 32)
-    assert ua[0, 3] == (((A0 & 0x7ff) << 42) | (A1 >> 22)) * 2.0 ** -53
+    assert ua[0, 3] == (((A0 & 0xfff) << 41) | (A1 >> 23)) * 2.0 ** -53
     assert ua[1, 3] == (((B0 & 0x7ff) << 42) | (B1 >> 22)) * 2.0 ** -53
-    u1, u2 = ((A0 >> 11) | 1) * 2.0 ** -53, (B0 >> 11) * 2.0 ** -53
+    u1, u2 = ((A0 >> 12) | 1) * 2.0 ** -52, (B0 >> 11) * 2.0 ** -53
     r = math.sqrt(-2.0 * math.log(u1))
     assert abs(z[0, 3] - r * math.cos(2 * math.pi * u2)) < 1e-14 and abs(z[1, 3] - r * math.sin(2 * math.pi * u2)) < 1e-14
 
