@@ -403,3 +403,35 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     assert np.array_equal(sig[0], sig[1])                      # every rank applies the same update
     assert sig[0][0] == 0.3 and abs(sig[0][1] - ref.sigma[1]) < 1e-12 and sig[0][1] != 0.05
     assert os.path.exists(tmp_path / "trajectories" / "rank1.bin")
+
+
+# ---- bench.py: the reference arm runs on the CPU and prints the contract's JSON line -------------------------
+def test_bench_reference_arm_prints_the_contract_line():
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
+                          "--warmup", "1", "--ref-log2-chains", "12"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "metropolis_chain_steps_per_sec"
+    assert line["unit"] == "chain-steps/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "C3" in line["config"]["workload"]
+    # under torchrun only rank 0 works: the other ranks exit 0 without output
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=60, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_refuses_to_run_without_a_gpu():
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
