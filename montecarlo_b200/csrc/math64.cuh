@@ -1,11 +1,13 @@
 // math64.cuh -- FP64 transcendental kernels of the sweep, written for the B200 FP64 pipe (64 DFMA/clk/SM).
 //
-// The fused sweep is FP64-pipe / issue bound (DESIGN.md "Roofline"): CUDA's libm exp/log/sincospi/sqrt cost ≈150
+// The fused sweep is instruction-issue bound (DESIGN.md "Roofline"): CUDA's libm exp/log/sincospi/sqrt cost ≈150
 // FP64 instructions per chain-step.  These replacements are specialised to what the sweep actually needs and take
 // their arguments straight from the Philox INTEGER words (no int->fp64 conversion instructions):
 //
 //   exp_core / exp_accept / exp_nonpos   exp for the accept test / PGMC α      11 FP64, 1 table load, integer range checks
-//   neg2log_u53(n)       −2·ln(n·2^-53), n ∈ [1, 2^53)  (Box-Muller radius²)   10 FP64, 3 table loads
+//   exp_accept_prefix<P> the accept test against a P-bit prefix of u          FP32 + MUFU.EX2 + 2 F2I; FP64 only when ambiguous
+//   neg2log_k52(k)       −2·ln(k·2^-52), k ∈ [1, 2^52)  (Box-Muller radius²)   10 FP64 (incl. the exact int->fp64 DADD), 3 table loads
+//   neg2log_u53(n)       −2·ln(n·2^-53), n ∈ [1, 2^53)  (reference form, clz)   9 FP64, 3 table loads
 //   sqrt_pos(w)          √w, w > 0 normal                                       6 FP64 + 1 MUFU.RSQ64H
 //   sincos_turn53_tab    sin/cos(2π·k·2^-53), k ∈ [0, 2^53)                    12 FP64, one 16-byte table load (1024 directions)
 //
@@ -363,8 +365,6 @@ AM_FN bool exp_accept_prefix(double x, uint32_t f, ExactU exact_u, Tab tb)
 
 // Filter cell from the top 23 bits of a raw 64-bit word whose u is (w >> 11)·2^-53 (XOSHIRO mode).
 AM_FN float ulo_from_word23(uint32_t w_hi) { return uint_as_float(0x3f800000u | (w_hi >> 9)) - 1.0f; }
-// Filter cell from an 11-bit prefix f: u ∈ [f·2^-11, (f+1)·2^-11) (native Philox mode).
-AM_FN float ulo_from_prefix11(uint32_t f) { return uint_as_float(0x3f800000u | (f << 12)) - 1.0f; }
 // Exact native-mode uniform: u = ((f << (53 − PBITS)) | r)·2^-53 with r = word >> (11 + PBITS), the 53 − PBITS
 // refinement bits (PBITS = 11: 42 bits, PBITS = 12: 41 bits).
 template <int PBITS>
