@@ -569,6 +569,20 @@ def test_config3_full_size_properties():
         x2 = eng.get_state()
     assert np.array_equal(x1, x2)
     np.testing.assert_allclose(s1, s2, rtol=1e-13)
+    # the series path and the pipelined host job at full size: 100 store intervals of 10 steps == the above, and the
+    # records inside the stretch carry the analytic acceptance (2/π)·atan(2s/σ) = 0.9365 of the stationary chain
+    import torch
+    xout = torch.empty(M, dtype=torch.float64).pin_memory()
+    with mb.CudaEnsemble(M, 2.0, [0.1], seed=seed, arith="fast") as eng:
+        eng.init_synthetic()
+        rec = eng.run_host_job([10] * 100, x_out=xout.data_ptr(), n_slices=8)
+        np.testing.assert_allclose(rec[-1], s1, rtol=1e-12)
+        assert np.array_equal(xout.numpy(), x1)
+        rec2 = eng.sweep_series([10] * 22)                         # 2 full launches of 11 stores, t = 1010 .. 1220
+        assert np.all(rec2[:, 2] == M)
+        assert np.all(np.abs(rec2[:, 0] / M - 0.25) < 3 * math.sqrt(1 / 8 / M) + 1e-4)
+        acc_inc = (rec2[-1, 1] * 1220 - rec2[0, 1] * 1010) / M / 210   # mean acceptance over steps 1010 .. 1220
+        assert abs(acc_inc - 2 / math.pi * math.atan(2 * 0.5 / 0.1)) < 1e-4
 
 
 # ---------------------------------------------------------------------------------------------------------
