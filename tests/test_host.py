@@ -435,3 +435,57 @@ def test_bench_refuses_to_run_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True,
                          text=True, timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+_WORKER_SERIES = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch.distributed as dist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+import montecarlo_b200 as mb
+from montecarlo_b200 import arianna as A
+from fake_engine import OracleEngine
+from oracle import oracle as O
+A.CudaEnsemble = OracleEngine
+M, steps = 77, 300
+chains = mb.ParticleEnsemble(O.init_synthetic(9, 0, M), 2.0)
+pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.1), 1.0),)
+sim = mb.Simulation(chains, (dict(algorithm=mb.Metropolis, pool=pool, seed=9),
+                             dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance),
+                                  scheduler=mb.build_schedule(steps, 100, 10)),
+                             dict(algorithm=mb.StoreTrajectories, scheduler=[150, steps], store_first=False)),
+                    steps, path={path!r})
+mb.run(sim)
+np.save(os.path.join({path!r}, f"x_rank{{chains.rank}}.npy"), chains.x)
+np.save(os.path.join({path!r}, f"calls_rank{{chains.rank}}.npy"), np.array([chains.engine.series_calls, chains.engine.launch_count]))
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_series_lookahead(tmp_path):
+    """The look-ahead / series path with the chains sharded over 2 ranks: ONE all-reduce per fused stretch, records
+    equal to the single-process oracle's callbacks at every store, trajectory frames (barriers) at their own times."""
+    port = 31500 + os.getpid() % 2000
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER_SERIES.format(root=ROOT, port=port, path=str(tmp_path)))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    M, steps = 77, 300
+    ref = O.Ensemble(O.init_synthetic(9, 0, M), 2.0, [0.1])
+    sched = A.build_schedule(steps, 100, 10)
+    rows_e = open(tmp_path / "energy.dat").read().split("\n")[:-1]
+    rows_a = open(tmp_path / "acceptance.dat").read().split("\n")[:-1]
+    done = 0
+    for i, t in enumerate(sched):
+        _, z, ua = O.draws_philox(9, 0, M, done, t - done, with_cat=False)
+        ref.sweep_replay(None, z, ua)
+        done = t
+        assert int(rows_e[1 + i].split()[0]) == t and abs(float(rows_e[1 + i].split()[1]) / ref.callback_energy() - 1) < 1e-12
+        assert abs(float(rows_a[1 + i].split("[")[1][:-1]) / ref.callback_acceptance()[0] - 1) < 1e-12
+    x = np.concatenate([np.load(tmp_path / f"x_rank{r}.npy") for r in range(2)])
+    assert np.array_equal(x, ref.x)
+    for r in range(2):       # stretches: t=100..150 (barrier at 150), 160..300 (barrier at 300) -> 2 series calls
+        calls = np.load(tmp_path / f"calls_rank{r}.npy")
+        assert calls[0] == 2 and calls[1] == 2
