@@ -424,18 +424,25 @@ int32_t arianna_get_state(arianna_handle *h, double *x, double *e)
     return ARIANNA_OK;
 }
 
+// The copy stream and its two events (trajectory frames, pipelined host jobs), created on first use.
+static int32_t ensure_copy_stream(arianna_handle *h)
+{
+    if (h->copy_stream) return ARIANNA_OK;
+    CU_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU_TRY(h, cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+    CU_TRY(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    CU_TRY(h, cudaEventRecord(h->ev_copy, h->copy_stream));
+    return ARIANNA_OK;
+}
+
 int32_t arianna_get_state_async(arianna_handle *h, double *x_pinned)
 {
     if (!h) return ARIANNA_ERR_INVALID;
     REQUIRE(h, x_pinned != nullptr, "arianna_get_state_async: destination is NULL");
     DeviceGuard guard(h->device);
-    if (!h->copy_stream) {
-        CU_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
-        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
-        CU_TRY(h, cudaMalloc(&h->d_snap, sizeof(double) * h->M));
-        CU_TRY(h, cudaEventRecord(h->ev_copy, h->copy_stream));
-    }
+    int32_t rc = ensure_copy_stream(h);
+    if (rc) return rc;
+    if (!h->d_snap) CU_TRY(h, cudaMalloc(&h->d_snap, sizeof(double) * h->M));
     // snapshot x on the compute stream (D2D, ~0.1 ms/GiB-scale) so the next sweep can start at once, then drain the
     // snapshot over PCIe on the copy stream; the previous frame must have left the snapshot first
     CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
@@ -721,12 +728,8 @@ int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_st
     int64_t total = 0;
     int32_t rc = series_prepare(h, "arianna_run_host_job", n_stores, K, &total);
     if (rc) return rc;
-    if (!h->copy_stream) {
-        CU_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
-        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
-        CU_TRY(h, cudaEventRecord(h->ev_copy, h->copy_stream));
-    }
+    rc = ensure_copy_stream(h);
+    if (rc) return rc;
     // slices: whole CTAs' worth of chains each
     int64_t per = (h->M + n_slices - 1) / n_slices;
     per = (per + kBlock - 1) / kBlock * kBlock;

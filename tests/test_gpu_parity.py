@@ -303,6 +303,10 @@ def test_host_job_pipelined_over_slices(n_slices):
         rec_b2 = b.sweep_series([4, 4])
         np.testing.assert_allclose(rec_a2, rec_b2, rtol=1e-13)
         assert np.array_equal(a.get_state(), b.get_state())
+        # the overlapped trajectory write-back shares the copy stream with the host job
+        a.get_state_async(xout.data_ptr())
+        a.synchronize()
+        assert np.array_equal(xout.numpy(), b.get_state())
     ref = O.Ensemble(x0, 2.0, [0.1])
     _, z, ua = O.draws_philox(seed, 0, M, 0, sum(Ks) + 8, with_cat=False)
     ref.sweep_replay(None, z, ua)
