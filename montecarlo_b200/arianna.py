@@ -679,7 +679,11 @@ def _make_lookahead(sim: "Simulation"):
         return None                      # callbacks listed before Metropolis see the state BEFORE the step at t
     m = met[0]
     passive = (Metropolis, PrintTimeSteps)
-    barriers = sorted({t for k, a in enumerate(algs) if k not in cbs and not isinstance(a, passive)
+
+    def is_passive(a):     # never looks at the chains during the t-loop (e.g. StoreLastFrames only acts in finalise)
+        return isinstance(a, passive) or type(a).make_step is AriannaAlgorithm.make_step
+
+    barriers = sorted({t for k, a in enumerate(algs) if k not in cbs and not is_passive(a)
                        for t in sim.schedulers[k]})
     stores = sorted({t for k in cbs for t in sim.schedulers[k]})
     msched = sorted(sim.schedulers[m])

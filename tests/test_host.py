@@ -489,3 +489,16 @@ def test_two_rank_gloo_series_lookahead(tmp_path):
     for r in range(2):       # stretches: t=100..150 (barrier at 150), 160..300 (barrier at 300) -> 2 series calls
         calls = np.load(tmp_path / f"calls_rank{r}.npy")
         assert calls[0] == 2 and calls[1] == 2
+
+
+def test_lookahead_ignores_algorithms_that_only_act_in_finalise(tmp_path, fake_engine):
+    """StoreLastFrames with the DEFAULT scheduler (every step) has a no-op make_step: it must not act as a barrier."""
+    chains = mb.ParticleEnsemble(O.init_synthetic(1, 0, 20), 2.0)
+    pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.1), 1.0),)
+    sim = mb.Simulation(chains, (dict(algorithm=mb.Metropolis, pool=pool, seed=1),
+                                 dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy,),
+                                      scheduler=mb.build_schedule(100, 20, 10)),
+                                 dict(algorithm=mb.StoreLastFrames)), 100, path=str(tmp_path))
+    mb.run(sim)
+    assert chains.engine.series_calls == 1 and chains.engine.steps_done == 100
+    assert os.path.exists(tmp_path / "trajectories" / "1" / "lastframe.dat")
