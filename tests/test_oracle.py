@@ -83,6 +83,35 @@ def test_philox_draws_layout_and_moments():
     assert abs(z[0, 3] - r * math.cos(2 * math.pi * u2)) < 1e-14 and abs(z[1, 3] - r * math.sin(2 * math.pi * u2)) < 1e-14
 
 
+def test_philox_stream_statistics():
+    """Distributional checks of the native stream (layout v3: 52-bit radius uniform, 12/11-bit prefix + lazy
+    refinement): normal draws, accept and categorical uniforms are correctly distributed, mutually uncorrelated,
+    and uncorrelated along the step axis and across neighbouring chains (stream ids differ by one)."""
+    from scipy import stats
+    M, K = 512, 2000
+    uc, z, ua = O.draws_philox(1234, 77, M, 0, K)
+    n = z.size
+    assert stats.kstest(z.ravel(), "norm").pvalue > 1e-3
+    assert stats.kstest(ua.ravel(), "uniform").pvalue > 1e-3
+    assert stats.kstest(uc.ravel(), "uniform").pvalue > 1e-3
+    # even and odd steps use different bit fields of the block (cos/sin half, 12/11-bit prefix): check both
+    for par in (0, 1):
+        assert stats.kstest(z[par::2].ravel(), "norm").pvalue > 1e-3
+        assert stats.kstest(ua[par::2].ravel(), "uniform").pvalue > 1e-3
+    lim = 4.5 / math.sqrt(n)
+
+    def corr(a, b):
+        a, b = a.ravel() - a.mean(), b.ravel() - b.mean()
+        return float((a * b).mean() / (a.std() * b.std()))
+    assert abs(corr(z, ua)) < lim and abs(corr(z, uc)) < lim and abs(corr(ua, uc)) < lim
+    assert abs(corr(z[:-1], z[1:])) < lim and abs(corr(z[::2], z[1::2])) < 1.5 * lim      # lag 1, and within a pair
+    assert abs(corr(z[:-1] ** 2, z[1:] ** 2)) < lim                                        # shared radius must not show
+    assert abs(corr(ua[:-1], ua[1:])) < lim and abs(corr(z[:, :-1], z[:, 1:])) < lim      # neighbouring chains
+    # tails: P(|z| > 4) = 6.33e-5
+    tail = (np.abs(z) > 4).sum()
+    assert abs(tail - 6.334e-5 * n) < 5 * math.sqrt(6.334e-5 * n)
+
+
 # ---- the sweep: C restatement == numpy restatement, bit for bit ---------------------------------------------
 @pytest.mark.parametrize("sigma,weight", [([0.1], [1.0]), ([0.2] * 7, [0.4] + [0.1] * 6), ([1.5, 0.01], [0.3, 0.7])])
 def test_c_matches_numpy_replay(sigma, weight):
