@@ -209,6 +209,12 @@ ARIANNA_API int32_t arianna_pgmc_sums_device(arianna_handle *h, double **dptr, i
 /* Plumbing. */
 ARIANNA_API int32_t arianna_get_stream(arianna_handle *h, void **stream);
 ARIANNA_API int32_t arianna_synchronize(arianna_handle *h);
+/* Device time (CUDA events on the engine's stream, milliseconds) of the LAST arianna_sweep / arianna_sweep_series /
+ * arianna_run_host_job call (sweep_ms: kernels + fused reductions + record folds; for a host job also the waits on the
+ * slice uploads) and of the last estimator pass (pgmc_ms).  NaN when there was none; either pointer may be NULL.
+ * Synchronises with the end of that work.  The reference only has a wall-clock `@elapsed` around its t-loop
+ * (src/simulation.jl:184). */
+ARIANNA_API int32_t arianna_timing(arianna_handle *h, double *sweep_ms, double *pgmc_ms);
 ARIANNA_API int32_t arianna_launch_count(arianna_handle *h, int64_t *n_launches);
 ARIANNA_API int32_t arianna_steps_done(arianna_handle *h, int64_t *steps);
 ARIANNA_API int32_t arianna_device_info(arianna_handle *h, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor,

@@ -89,6 +89,7 @@ SYMBOLS = {
     "arianna_pgmc_sums_device": (C.c_int32, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "arianna_get_stream": (C.c_int32, [_H, C.POINTER(C.c_void_p)]),
     "arianna_synchronize": (C.c_int32, [_H]),
+    "arianna_timing": (C.c_int32, [_H, _D, _D]),
     "arianna_launch_count": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
     "arianna_steps_done": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
     "arianna_device_info": (C.c_int32, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),

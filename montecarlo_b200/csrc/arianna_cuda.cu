@@ -70,6 +70,8 @@ struct arianna_handle {
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;   // D2H of trajectory frames overlaps the next sweep
     cudaEvent_t ev_snap = nullptr, ev_copy = nullptr;
+    cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};   // device-time brackets: [0,1] last sweep/series/job, [2,3] last estimator pass
+    bool timed[2] = {false, false};
     double *d_snap = nullptr;             // device snapshot of x the copy stream reads from
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t hbm_bytes = 0;
@@ -376,6 +378,7 @@ int32_t arianna_destroy(arianna_handle *h)
     if (h->comm) { nccl::g_api.CommDestroy(h->comm); h->comm = nullptr; }
     cudaFree(h->d_coll);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (auto &e : h->ev_t) if (e) cudaEventDestroy(e);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     cudaFree(h->d_snap);
@@ -422,6 +425,15 @@ int32_t arianna_get_state(arianna_handle *h, double *x, double *e)
     }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return ARIANNA_OK;
+}
+
+// Device-time bracket `which` (0 sweeps, 1 estimator) on the compute stream; read by arianna_timing.
+static void time_mark(arianna_handle *h, int which, bool begin)
+{
+    cudaEvent_t &e = h->ev_t[2 * which + (begin ? 0 : 1)];
+    if (!e && cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); e = nullptr; return; }
+    if (cudaEventRecord(e, h->stream) != cudaSuccess) { cudaGetLastError(); return; }
+    if (!begin) h->timed[which] = true;
 }
 
 // The copy stream and its two events (trajectory frames, pipelined host jobs), created on first use.
@@ -518,6 +530,7 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
     if (K == 0) return want_reduce ? launch_callback_reduce(h) : ARIANNA_OK;
     const size_t smem = multi ? sizeof(uint32_t) * 2 * h->pool.n_moves * kBlock : 0;
     const bool exact = h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
+    time_mark(h, 0, true);
 
     if (h->cfg.rng_mode == ARIANNA_RNG_PHILOX) {
 
@@ -571,11 +584,13 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
     ++h->launches;
     h->steps_done += K;
     h->sums_valid = false;
+    int32_t rc_red = ARIANNA_OK;
     if (want_reduce) {
         if (!multi && h->cfg.rng_mode == ARIANNA_RNG_PHILOX) h->sums_valid = true;  // fused at the sweep's tail
-        else return launch_callback_reduce(h);
+        else rc_red = launch_callback_reduce(h);
     }
-    return ARIANNA_OK;
+    time_mark(h, 0, false);
+    return rc_red;
 }
 
 // Store intervals fused per series launch.  Each interval costs kSeriesBytesPerStore (3 KB) of shared memory per CTA
@@ -704,8 +719,10 @@ int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t 
     int64_t total = 0;
     int32_t rc = series_prepare(h, "arianna_sweep_series", n_stores, K, &total);
     if (rc || n_stores == 0) return rc;
+    time_mark(h, 0, true);
     rc = series_range(h, 0, h->M, h->steps_done, n_stores, K, 0);
     if (rc) return rc;
+    time_mark(h, 0, false);
     h->steps_done += total;
     h->series_n = n_stores;
     h->sums_valid = true;   // the last record doubles as the callback sums of the current state
@@ -759,6 +776,7 @@ int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_st
             JOB_TRY(cudaEventRecord(up[i], h->copy_stream));
         }
     }
+    time_mark(h, 0, true);
     for (int i = 0; i < ns; ++i) {
         const int64_t off = (int64_t)i * per, m = (h->M - off < per) ? h->M - off : per;
         if (x_in) JOB_TRY(cudaStreamWaitEvent(h->stream, up[i], 0));
@@ -772,6 +790,7 @@ int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_st
             JOB_TRY(cudaMemcpyAsync(x_out + off, h->d_x + off, sizeof(double) * m, cudaMemcpyDeviceToHost, h->copy_stream));
         }
     }
+    time_mark(h, 0, false);
     h->steps_done += total;
     h->series_n = n_stores;
     h->sums_valid = n_stores > 0;
@@ -1087,6 +1106,7 @@ static int32_t pgmc_impl(arianna_handle *h, int32_t q_batch, const int32_t *lear
         CU_TRY(h, cudaMemcpyAsync(h->d_scratch, z, bytes, cudaMemcpyHostToDevice, h->stream));
         dz = h->d_scratch;
     }
+    time_mark(h, 1, true);
     for (int l = 0; l < n_learn; ++l) {
         const int k = learn_ids[l];
         PgmcParams pp{};
@@ -1110,6 +1130,7 @@ static int32_t pgmc_impl(arianna_handle *h, int32_t q_batch, const int32_t *lear
         CU_TRY(h, cudaGetLastError());
         ++h->launches;
     }
+    time_mark(h, 1, false);
     if (!replay) h->pgmc_samples += (int64_t)n_learn * q_batch;
     if (replay && !on_device) CU_TRY(h, cudaStreamSynchronize(h->stream));
     if (exact) h->sums_valid = false;  // chain state drifted by the perform/undo rounding
@@ -1173,6 +1194,23 @@ int32_t arianna_synchronize(arianna_handle *h)
     DeviceGuard guard(h->device);
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     if (h->copy_stream) CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_timing(arianna_handle *h, double *sweep_ms, double *pgmc_ms)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    double *out[2] = {sweep_ms, pgmc_ms};
+    for (int w = 0; w < 2; ++w) {
+        if (!out[w]) continue;
+        *out[w] = std::nan("");
+        if (!h->timed[w]) continue;
+        CU_TRY(h, cudaEventSynchronize(h->ev_t[2 * w + 1]));
+        float ms = 0.f;
+        CU_TRY(h, cudaEventElapsedTime(&ms, h->ev_t[2 * w], h->ev_t[2 * w + 1]));
+        *out[w] = ms;
+    }
     return ARIANNA_OK;
 }
 

@@ -337,6 +337,13 @@ class CudaEnsemble:
     def synchronize(self):
         self._ck(self._lib.arianna_synchronize(self._h))
 
+    def timing(self):
+        """(sweep_ms, pgmc_ms): device time of the last sweep / series / host job and of the last estimator pass
+        (arianna_timing; NaN when there was none)."""
+        a, b = C.c_double(), C.c_double()
+        self._ck(self._lib.arianna_timing(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     @property
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -313,6 +313,30 @@ def test_host_job_pipelined_over_slices(n_slices):
     assert abs(rec_a2[-1, 0] / M / ref.callback_energy() - 1) < 1e-12
 
 
+def test_device_timers():
+    """arianna_timing: CUDA-event brackets of the last sweep and estimator pass (SURVEY.md §8b's arianna_timing)."""
+    import time
+    with mb.CudaEnsemble(1 << 22, 2.0, [0.1], seed=1) as eng:
+        eng.init_synthetic()
+        s, p = eng.timing()
+        assert math.isnan(s) and math.isnan(p)
+        eng.sweep(100, reduce=True)
+        t0 = time.perf_counter()
+        s100, _ = eng.timing()                                      # synchronises with the sweep
+        wall = (time.perf_counter() - t0) * 1e3
+        assert 0.05 < s100 < 50.0
+        eng.sweep(1000)
+        s1000, p = eng.timing()
+        assert 5 * s100 < s1000 < 15 * s100 and math.isnan(p)       # device time scales with the fused steps
+        eng.sweep_series([10] * 30)
+        s300, _ = eng.timing()
+        assert 1.5 * s100 < s300 < 6 * s100
+        eng.pgmc_estimate(10, [0])
+        _, p = eng.timing()
+        assert 0.01 < p < 50.0
+        del wall
+
+
 def test_series_small_ensemble_and_errors():
     """M = 10 (BASELINE config 1's width): up to ARIANNA_MAX_SERIES stores per launch; multi-move pools refuse."""
     M, seed = 10, 42
