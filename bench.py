@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-log2-chains", type=int, default=20, help="bounded sample of the workload for the CPU arm")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="time budget of the cpu_baseline leg")
     return ap.parse_args()
 
 
@@ -365,7 +366,7 @@ def run_ours(args):
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
-            rate, done, dt, cores = cpu_reference_rate(args.ref_log2_chains, S, 10 ** 9, 2, 15.0)
+            rate, done, dt, cores = cpu_reference_rate(args.ref_log2_chains, S, 10 ** 9, 2, args.cpu_seconds)
             line["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"2^{args.ref_log2_chains} chains x {done} store intervals of {S} MC steps in {dt:.1f} s "

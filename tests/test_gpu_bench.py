@@ -1,0 +1,39 @@
+"""bench.py's JSON contract on a real GPU, at a reduced size (the driver runs the default size)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*extra):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--log2-chains", "22", "--steps", "25",
+                          "--warmup", "3", "--ref-log2-chains", "12", "--cpu-seconds", "1", *extra], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("series", ["0", "1"])
+def test_bench_line_contract(series):
+    d = _run("--series", series)
+    assert d["metric"] == "metropolis_chain_steps_per_sec" and d["unit"] == "chain-steps/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 25 and d["warmup"] == 3 and d["higher_is_better"] is True
+    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert "C3" in d["config"]["workload"] and d["config"]["chains_per_gpu"] == 1 << 22
+    assert d["value"] > 1e10 and abs(d["value"] - (1 << 22) * 10 * 25 / (d["ms_per_step"] * 25e-3)) < 1e-6 * d["value"]
+    assert d["gpu_launches"] >= 25 // max(1, d["config"]["stores_per_launch"])
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    r = d["roofline"]
+    assert r["bound"] in ("fp64", "hbm", "tensor") and r["unit"] == "TFLOP/s" and "traffic" in r
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.2 < r["frac"] < 2.0
+    assert abs(r["hbm"]["frac"] - r["hbm"]["achieved"] / r["hbm"]["peak"]) < 1e-9
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and 0 < e["value"] <= 1.05 * d["value"]
+    assert e["h2d_bytes_per_step"] >= 8 * (1 << 22) // 25 and e["d2h_bytes_per_step"] >= 8 * (1 << 22) // 25
+    assert abs(d["mean_energy"] - e["energy"]) < 0.02          # both runs sample the same ensemble a little later
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == d["unit"] and c["sample"]
