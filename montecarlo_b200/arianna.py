@@ -37,7 +37,7 @@ __all__ = [
     "AriannaSystem", "Particle", "System", "ParticleEnsemble", "Action", "Policy", "Displacement",
     "StandardGaussian", "ComponentArray", "Move", "Metropolis", "Simulation", "run", "build_schedule",
     "StoreCallbacks", "StoreTrajectories", "StoreLastFrames", "StoreParameters", "PrintTimeSteps",
-    "callback_energy", "callback_acceptance", "mc_sweep", "DAT", "TXT",
+    "callback_energy", "callback_acceptance", "mc_sweep", "DAT", "TXT", "shard_bounds",
 ]
 
 

@@ -695,6 +695,70 @@ def test_two_gpu_nccl_simulation_matches_one_gpu(tmp_path):
     assert outs[1][1][0] == 0.3 and outs[1][1][1] != 0.05
 
 
+_NCCL_SERIES_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+import montecarlo_b200 as mb
+M, steps = 100003, 400
+chains = mb.ParticleEnsemble(n_chains=M, beta=2.0)
+pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.1), 1.0),)
+sim = mb.Simulation(chains, (dict(algorithm=mb.Metropolis, pool=pool, seed=7),
+                             dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance),
+                                  scheduler=mb.build_schedule(steps, 100, 10)),
+                             dict(algorithm=mb.StoreLastFrames, scheduler=[steps])), steps, path={path!r})
+mb.run(sim)                                           # look-ahead: ONE series call + ONE NCCL all-reduce per stretch
+np.save(os.path.join({path!r}, f"x_rank{{rank}}.npy"), chains.x)
+np.save(os.path.join({path!r}, f"launches_rank{{rank}}.npy"), np.array([chains.engine.launch_count]))
+# the library-side path a Julia host uses: arianna_comm_init + arianna_series_global
+ids = [mb.CudaEnsemble.nccl_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+off, n = mb.shard_bounds(M, rank, world)
+with mb.CudaEnsemble(n, 2.0, [0.1], seed=7, chain_offset=off, n_chains_total=M) as eng:
+    eng.comm_init(ids[0], rank, world)
+    eng.init_synthetic()
+    eng.sweep_series([100] + [10] * 30, read=False)
+    np.save(os.path.join({path!r}, f"lib_rank{{rank}}.npy"), eng.series_global(31))
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_two_gpu_series_allreduce(tmp_path):
+    """The series path sharded over 2 GPUs: torch.distributed all-reduce of the whole stretch in the host mirror,
+    arianna_series_global inside the library; both equal the single-GPU records."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for n in (1, 2):
+        d = tmp_path / f"n{n}"
+        d.mkdir()
+        script = d / "worker.py"
+        script.write_text(_NCCL_SERIES_WORKER.format(root=root, path=str(d)))
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                            "--master-addr", "127.0.0.1", "--master-port", str(29700 + n), str(script)],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[n] = (np.concatenate([np.load(d / f"x_rank{k}.npy") for k in range(n)]), np.loadtxt(d / "energy.dat"),
+                   [np.load(d / f"lib_rank{k}.npy") for k in range(n)], np.load(d / "launches_rank0.npy")[0])
+    assert np.array_equal(outs[2][0], outs[1][0])                               # chains independent of the sharding
+    np.testing.assert_allclose(outs[2][1], outs[1][1], rtol=1e-12)              # energy.dat
+    assert np.array_equal(outs[2][2][0], outs[2][2][1])                         # every rank holds the global records
+    np.testing.assert_allclose(outs[2][2][0], outs[1][2][0], rtol=1e-12)
+    assert outs[2][2][0][0, 2] == 100003 and outs[1][3] <= 2 + 2 * 3 + 2        # init + t=0 record + 3 series launches
+    M = 100003
+    ref = O.Ensemble(O.init_synthetic(7, 0, M), 2.0, [0.1])
+    _, z, ua = O.draws_philox(7, 0, M, 0, 400, with_cat=False)
+    ref.sweep_replay(None, z, ua)
+    assert np.max(np.abs(outs[2][0] - ref.x)) < 1e-12
+    assert abs(outs[2][1][-1, 1] / ref.callback_energy() - 1) < 1e-12
+
+
 def test_config1_verbatim(tmp_path):
     """BASELINE config 1 = example/particle_1d/harmonic_oscillator/MC_harmonic_oscillator.jl verbatim: β = 2, M = 10,
     10^5 steps, burn 1000, σ = 0.1, Metropolis + StoreCallbacks energy/acceptance + StoreTrajectories + StoreLastFrames
