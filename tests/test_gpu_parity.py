@@ -337,6 +337,32 @@ def test_device_timers():
         del wall
 
 
+def test_c_host_example(tmp_path):
+    """examples/harmonic_oscillator.c: the reference's example script written against the C ABI alone (gcc, no
+    Python in the process) -- the records it prints are the oracle's callbacks."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe, libdir = str(tmp_path / "harmonic_oscillator"), os.path.dirname(mb.LIB_PATH)
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", "harmonic_oscillator.c"), "-L", libdir, "-larianna_cuda",
+                           f"-Wl,-rpath,{libdir}", "-o", exe])
+    M, steps = 20000, 1030
+    out = subprocess.run([exe, str(M), str(steps)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    rows = [ln for ln in out.stdout.splitlines() if ln and ln[0].isdigit()]
+    assert [int(r.split()[0]) for r in rows] == [1000, 1010, 1020, 1030]
+    ref = O.Ensemble(O.init_synthetic(42, 0, M), 2.0, [0.1])
+    done = 0
+    for r in rows:
+        t = int(r.split()[0])
+        _, z, ua = O.draws_philox(42, 0, M, done, t - done, with_cat=False)
+        ref.sweep_replay(None, z, ua)
+        done = t
+        assert abs(float(r.split()[1]) / ref.callback_energy() - 1) < 1e-12
+        assert abs(float(r.split("[")[1].rstrip("]")) / ref.callback_acceptance()[0] - 1) < 1e-12
+    assert "chain-steps/s" in out.stdout
+
+
 def test_series_small_ensemble_and_errors():
     """M = 10 (BASELINE config 1's width): up to ARIANNA_MAX_SERIES stores per launch; multi-move pools refuse."""
     M, seed = 10, 42

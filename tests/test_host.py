@@ -502,3 +502,22 @@ def test_lookahead_ignores_algorithms_that_only_act_in_finalise(tmp_path, fake_e
     mb.run(sim)
     assert chains.engine.series_calls == 1 and chains.engine.steps_done == 100
     assert os.path.exists(tmp_path / "trajectories" / "1" / "lastframe.dat")
+
+
+# ---- a host written against the C ABI alone (examples/harmonic_oscillator.c) --------------------------------
+def _build_c_example(tmp_path):
+    exe = str(tmp_path / "harmonic_oscillator")
+    libdir = os.path.dirname(mb.LIB_PATH)
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "harmonic_oscillator.c"), "-L", libdir, "-larianna_cuda",
+                           f"-Wl,-rpath,{libdir}", "-o", exe])
+    return exe
+
+
+def test_c_host_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    import torch
+    exe = _build_c_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: see tests/test_gpu_parity.py::test_c_host_example")
+    out = subprocess.run([exe, "1000", "1200"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 2 and "no CPU fallback" in out.stderr
