@@ -384,6 +384,9 @@ def test_series_small_ensemble_and_errors():
         assert eng.sweep_series([]).shape == (0, 3)
         with pytest.raises(mb.AriannaError):
             eng.sweep_series([-1])
+        with pytest.raises(mb.AriannaError):
+            eng.run_host_job([10], n_slices=0)
+        assert eng.run_host_job([], n_slices=2).shape == (0, 3)      # nothing to do is not an error
     with mb.CudaEnsemble(M, 2.0, [0.1, 0.2], seed=seed) as eng:
         with pytest.raises(mb.AriannaError) as ei:
             eng.sweep_series([10])
