@@ -350,6 +350,10 @@ def run_ours(args):
             "achieved": ach_tf, "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": ach_tf / (fp64_peak / 1e12),
             "peak_source": "DFMA microbenchmark in this run (arianna_measure_fp64_peak; MEASURED_PEAKS.json has no "
                            "FP64 entry); nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2",
+            "note": "issue-bound FP64/integer kernel, no tensor-core work: neither 'hbm' nor 'tensor' applies. achieved = "
+                    "110 conventional FP64 flop per chain-step (SURVEY.md 8d, fixed before the build) x steps/s; the "
+                    "kernel executes far fewer (tables, FP32 filter), so frac may exceed 1 -- see 'issue' for the "
+                    "hardware-side fraction and 'hbm' for the memory view",
             "flops_per_chain_step": FLOPS_PER_CHAIN_STEP, "kernel_ms": kern_ms, "mc_steps_per_launch": steps_per_launch,
             "traffic": ncu_traffic(m_local, S, G),
             "issue": ncu_issue(m_local, S, G, m_local * steps_per_launch / (kern_ms * 1e-3)),
