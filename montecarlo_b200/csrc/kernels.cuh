@@ -85,12 +85,15 @@ __device__ __forceinline__ void load_tables(m64::MathTables *dst, const m64::Mat
     for (int i = threadIdx.x; i < (int)(sizeof(m64::MathTables) / sizeof(double)); i += blockDim.x) d[i] = s[i];
 }
 
-// Handle of a MathTables copy in shared memory (m64::Tab).  pin = true makes the window address opaque to the
-// optimiser so that it stays in ONE register across the sweep's loops instead of being re-derived next to every use.
-__device__ __forceinline__ m64::Tab shared_tab(const void *smem_ptr, bool pin)
+// Handle of a MathTables copy in shared memory (m64::Tab).  Call it AFTER the __syncthreads() that follows
+// load_tables: the empty volatile asm makes the window address opaque to the optimiser, which (1) keeps it in ONE
+// register across the sweep's loops instead of being re-derived next to every use and (2) orders every table load
+// (plain, non-volatile ld.shared asm that the compiler may otherwise treat as a pure function of its address) after
+// the barrier through a data dependency.
+__device__ __forceinline__ m64::Tab shared_tab(const void *smem_ptr)
 {
     uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr);
-    if (pin) asm volatile("" : "+r"(a));
+    asm volatile("" : "+r"(a));
     return m64::Tab{a};
 }
 // explicit shared-memory accesses relative to such an address (series accumulators of the sweep)
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
     }
     load_tables(reinterpret_cast<m64::MathTables *>(smem_raw), p.tables);
     __syncthreads();
-    const m64::Tab tb = shared_tab(smem_raw, true);
+    const m64::Tab tb = shared_tab(smem_raw);
     // SERIES: [n_series][kBlock] f64 Σe, [n_series][kBlock] u32 ΣΔacc, [kBlock] u64 Σacc at entry, as byte addresses
     const uint32_t a_se = tb.s + kTabBytes + 8u * threadIdx.x;
     const uint32_t a_da = tb.s + kTabBytes + (SERIES ? 8u * kBlock * (uint32_t)p.n_series : 0u) + 4u * threadIdx.x;
@@ -626,7 +629,7 @@ __global__ void __launch_bounds__(kBlock) sweep_replay_kernel(const ReplayParams
     __shared__ m64::MathTables s_T;
     load_tables(&s_T, p.tables);
     __syncthreads();
-    const m64::Tab tb = shared_tab(&s_T, false);
+    const m64::Tab tb = shared_tab(&s_T);
     const int nm = p.pool.n_moves;
     constexpr int PF = 4;
 
@@ -728,7 +731,7 @@ __global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroPara
         s_fi[i] = p.fi[i];
     }
     __syncthreads();
-    const m64::Tab tb = shared_tab(&s_T, false);
+    const m64::Tab tb = shared_tab(&s_T);
     const ZigTables T{s_ki, s_wi, s_fi};
     const int nm = p.pool.n_moves;
 
@@ -919,7 +922,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) pgmc_kernel(const PgmcPa
     __shared__ m64::MathTables s_T;
     load_tables(&s_T, p.tables);
     __syncthreads();
-    const m64::Tab tb = shared_tab(&s_T, true);
+    const m64::Tab tb = shared_tab(&s_T);
     double sj = 0.0, sdj = 0.0, sgf = 0.0, sg = 0.0, sn = 0.0;
     const int64_t qend = p.q0 + p.q_batch;
     for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
@@ -992,7 +995,7 @@ __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const doub
     __shared__ m64::MathTables s_T;
     load_tables(&s_T, tables);
     __syncthreads();
-    const m64::Tab tb = shared_tab(&s_T, false);
+    const m64::Tab tb = shared_tab(&s_T);
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
         if (kind == 0) out[i] = m64::exp_nonpos(a[i], tb);
         else if (kind == 1) out[i] = m64::neg2log_u53(b[i], tb);
