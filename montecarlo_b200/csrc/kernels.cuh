@@ -26,12 +26,16 @@ namespace arianna {
 // Tuning knobs of the fused sweep (overridable for A/B builds, see scripts/ab_variants.sh):
 //   ARIANNA_MINB  resident CTAs per SM requested through __launch_bounds__ (register cap = 65536 / (256·MINB))
 //   ARIANNA_BLOCK threads per CTA (multiple of 32)
+//   ARIANNA_PGMC_MINB the same for the PGMC estimator kernel
 //   ARIANNA_PIPE  1 = software-pipeline the Box-Muller/Philox work of pair p+1 over the two steps of pair p
 #ifndef ARIANNA_MINB
 #define ARIANNA_MINB 4
 #endif
 #ifndef ARIANNA_PIPE
 #define ARIANNA_PIPE 0
+#endif
+#ifndef ARIANNA_PGMC_MINB
+#define ARIANNA_PGMC_MINB 3   // the estimator (a full FP64 exp per sample) prefers 80 registers x 3 CTAs: 4.20 vs 4.39 ms (C4)
 #endif
 
 #ifndef ARIANNA_BLOCK
@@ -917,7 +921,7 @@ __device__ __forceinline__ void pgmc_sample(double &x, double &e, double beta, d
 }
 
 template <int POT, int ARITH, bool REPLAY>
-__global__ void __launch_bounds__(kBlock, ARIANNA_MINB) pgmc_kernel(const PgmcParams p)
+__global__ void __launch_bounds__(kBlock, ARIANNA_PGMC_MINB) pgmc_kernel(const PgmcParams p)
 {
     __shared__ m64::MathTables s_T;
     load_tables(&s_T, p.tables);
