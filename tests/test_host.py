@@ -521,3 +521,61 @@ def test_c_host_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
         pytest.skip("a GPU is present: see tests/test_gpu_parity.py::test_c_host_example")
     out = subprocess.run([exe, "1000", "1200"], capture_output=True, text=True, timeout=60)
     assert out.returncode == 2 and "no CPU fallback" in out.stderr
+
+
+# ---- property tests (hypothesis) of the host-side planning helpers ---------------------------------------------
+def test_properties_of_schedules_and_shards():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 5000), st.integers(0, 200), st.integers(1, 300))
+    def linear(steps, burn, dt):
+        if burn > steps:
+            return
+        s = mb.build_schedule(steps, burn, dt)
+        assert s == N.build_schedule(steps, burn, dt)                       # the oracle's restatement (simulation.jl:95-97)
+        assert s[0] == burn and s[-1] == steps and all(a < b for a, b in zip(s, s[1:]))
+        assert all((t - burn) % dt == 0 for t in s[:-1])
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 10 ** 9), st.integers(1, 64))
+    def shards(n, world):
+        parts = [mb.shard_bounds(n, r, world) for r in range(world)]
+        assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+        assert all(parts[r][0] + parts[r][1] == parts[r + 1][0] for r in range(world - 1))      # contiguous
+        assert max(c for _, c in parts) - min(c for _, c in parts) <= 1                         # balanced
+
+    linear()
+    shards()
+
+
+def test_lookahead_plan_properties(tmp_path, fake_engine):
+    """For random schedules of a trajectory barrier the look-ahead never crosses a barrier, never skips a store and
+    the files equal the one-launch-per-store run."""
+    from hypothesis import given, settings, strategies as st
+    count = [0]
+
+    @settings(max_examples=12, deadline=None)
+    @given(st.integers(1, 40), st.integers(0, 30), st.lists(st.integers(1, 120), min_size=0, max_size=4, unique=True))
+    def prop(dt, burn, frames):
+        count[0] += 1
+        steps = 120
+        outs = []
+        for look in (True, False):
+            d = tmp_path / f"p{count[0]}_{int(look)}"
+            chains = mb.ParticleEnsemble(O.init_synthetic(3, 0, 16), 2.0)
+            pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.1), 1.0),)
+            algs = [dict(algorithm=mb.Metropolis, pool=pool, seed=3),
+                    dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance),
+                         scheduler=mb.build_schedule(steps, burn, dt))]
+            if frames:
+                algs.append(dict(algorithm=mb.StoreTrajectories, scheduler=sorted(frames), store_first=False))
+            sim = mb.Simulation(chains, tuple(algs), steps, path=str(d))
+            sim.lookahead = look
+            mb.run(sim)
+            outs.append((open(d / "energy.dat").read(), open(d / "acceptance.dat").read(), chains.engine.get_state(),
+                         open(d / "trajectories" / "rank0.bin", "rb").read() if frames else b""))
+        assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and outs[0][3] == outs[1][3]
+        assert np.array_equal(outs[0][2], outs[1][2])
+
+    prop()
