@@ -140,19 +140,30 @@ function plan!(simulation::Simulation)
     algs = simulation.algorithms
     met = findall(a -> a isa Metropolis, algs)
     cbs = findall(a -> a isa StoreCallbacks && all(cb -> nameof(cb) in (:callback_energy, :callback_acceptance_cuda), a.callbacks), algs)
-    (length(met) == 1 && !isempty(cbs) && minimum(cbs) > met[1] && length(ens.pool) == 1) || return nothing
-    passive(a) = a isa Metropolis || a isa Arianna.PrintTimeSteps
-    barriers = sort(unique(vcat([simulation.schedulers[k] for k in eachindex(algs) if !(k in cbs) && !passive(algs[k])]..., Int[])))
+    (length(met) == 1 && !isempty(cbs) && minimum(cbs) > met[1]) || return nothing
+    m = met[1]
+    # never looks at the chains during the t-loop: Metropolis itself, the progress printer, and every algorithm whose
+    # make_step! is the no-op default of algorithms.jl:25 (e.g. StoreLastFrames only acts in finalise)
+    default_step = which(Arianna.make_step!, Tuple{Simulation,Arianna.AriannaAlgorithm})
+    passive(a) = a isa Metropolis || a isa Arianna.PrintTimeSteps ||
+                 which(Arianna.make_step!, Tuple{typeof(simulation),typeof(a)}) === default_step
+    times(pred) = sort(unique(vcat([simulation.schedulers[k] for k in eachindex(algs)
+                                    if !(k in cbs) && !passive(algs[k]) && pred(k)]..., Int[])))
+    # a barrier listed AFTER Metropolis sees the state after the Metropolis step of its time (the stretch may include a
+    # store AT that time); one listed BEFORE Metropolis sees the state before it: the stretch must stop short of it
+    barriers_post, barriers_pre = times(k -> k > m), times(k -> k < m)
     stores = sort(unique(vcat([simulation.schedulers[k] for k in cbs]...)))
-    msched = sort(simulation.schedulers[met[1]])
-    step = algs[met[1]].sweepstep
+    msched = sort(simulation.schedulers[m])
+    step = algs[m].sweepstep
     ens.lookahead = function ()
         t = simulation.t
-        ib = searchsortedfirst(barriers, t)
-        tb = ib <= length(barriers) ? barriers[ib] : simulation.steps + 1
+        ib = searchsortedfirst(barriers_post, t)
+        tb = ib <= length(barriers_post) ? barriers_post[ib] : simulation.steps + 1
+        ip = searchsortedlast(barriers_pre, t) + 1
+        tp = ip <= length(barriers_pre) ? barriers_pre[ip] : simulation.steps + 2
         out, prev = Int64[], t
         for ts in stores[searchsortedlast(stores, t)+1:end]
-            (ts > tb || length(out) >= 4096) && break
+            (ts > tb || ts >= tp || length(out) >= 4096) && break
             push!(out, step * (searchsortedlast(msched, ts) - searchsortedlast(msched, prev)))
             prev = ts
         end

@@ -434,8 +434,16 @@ def _jl(v) -> str:
             return "NaN"
         if math.isinf(v):
             return "Inf" if v > 0 else "-Inf"
-        r = repr(float(v))
-        if "e" in r:
+        v = float(v)
+        r = repr(v)
+        if "e" not in r and v != 0.0 and abs(v) >= 1e6:
+            # Python keeps fixed notation up to 1e16, Julia (Ryu shortest, Base.show) switches at 1e6: "1.0e6"
+            digits = r.replace("-", "").replace(".", "").lstrip("0")
+            digits = digits.rstrip("0") or "0"
+            ex = len(r.replace("-", "").split(".")[0]) - 1
+            m = digits[0] + "." + (digits[1:] or "0")
+            return ("-" if v < 0 else "") + f"{m}e{ex}"
+        if "e" in r:                                   # Python "1e-05" / "1.5e+16" -> Julia "1.0e-5" / "1.5e16"
             m, ex = r.split("e")
             if "." not in m:
                 m += ".0"
@@ -683,8 +691,14 @@ def _make_lookahead(sim: "Simulation"):
     def is_passive(a):     # never looks at the chains during the t-loop (e.g. StoreLastFrames only acts in finalise)
         return isinstance(a, passive) or type(a).make_step is AriannaAlgorithm.make_step
 
-    barriers = sorted({t for k, a in enumerate(algs) if k not in cbs and not is_passive(a)
+    # Barriers = times at which some other algorithm looks at (or changes) the chains.  One listed AFTER Metropolis sees
+    # the state after the Metropolis step of its time tb (the stretch may include a store AT tb); one listed BEFORE
+    # Metropolis sees the state before that step (simulation.jl:184-191 runs the list in order), so the stretch must
+    # stop short of tb.
+    def times(pred):
+        return sorted({t for k, a in enumerate(algs) if k not in cbs and not is_passive(a) and pred(k)
                        for t in sim.schedulers[k]})
+    barriers_post, barriers_pre = times(lambda k: k > m), times(lambda k: k < m)
     stores = sorted({t for k in cbs for t in sim.schedulers[k]})
     msched = sorted(sim.schedulers[m])
     step = algs[m].sweepstep
@@ -692,12 +706,14 @@ def _make_lookahead(sim: "Simulation"):
 
     def lookahead():
         t = sim.t
-        ib = bisect.bisect_left(barriers, t)
-        tb = barriers[ib] if ib < len(barriers) else sim.steps + 1     # first barrier at or after now
+        ib = bisect.bisect_left(barriers_post, t)
+        tb = barriers_post[ib] if ib < len(barriers_post) else sim.steps + 1    # first one at or after now
+        ip = bisect.bisect_right(barriers_pre, t)                                # (those at t have already fired)
+        tp = barriers_pre[ip] if ip < len(barriers_pre) else sim.steps + 2      # first one after now
         i0 = bisect.bisect_right(stores, t)
         out, prev = [], t
         for ts in stores[i0:i0 + chains.max_lookahead]:
-            if ts > tb:
+            if ts > tb or ts >= tp:
                 break
             out.append(step * (bisect.bisect_right(msched, ts) - bisect.bisect_right(msched, prev)))
             prev = ts
@@ -735,4 +751,18 @@ def run(simulation: Simulation):
     finally:
         for a in sim.algorithms:
             a.finalise(sim)
+        _finalise_summary(sim)
     return None
+
+
+def _finalise_summary(sim: "Simulation"):
+    """finalise_summary (simulation.jl:153-165): size of everything under `path` and the completion stamp."""
+    if sim.chains.rank != 0 or not os.path.exists(os.path.join(sim.path, "summary.log")):
+        return
+    total = 0
+    for root, _, files in os.walk(sim.path):
+        for name in files:
+            total += os.path.getsize(os.path.join(root, name))
+    with open(os.path.join(sim.path, "summary.log"), "a") as f:
+        f.write(f"\tSimulation size: {_jl(total / 1024 ** 2)} MB\n")
+        f.write(f"\tStatus: Completed on {time.strftime('%Y-%m-%dT%H:%M:%S')}\n")

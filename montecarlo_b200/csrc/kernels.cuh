@@ -443,6 +443,8 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         using T_ = std::true_type;
         using F_ = std::false_type;
         auto run_steps = [&](uint32_t ta, uint32_t tb) {     // MC steps [ta, tb) of this chain; t < 2^32 (host check)
+        if (tb <= ta) return;    // empty interval (two stores with no Metropolis step between them): with an odd ta
+                                 // the lead step below would run and tb - tfull would wrap around
         const bool lead = (ta & 1u) != 0;
         const uint32_t tfull = ta + (lead ? 1u : 0u);
         const int npairs = (int)((tb - tfull) >> 1);

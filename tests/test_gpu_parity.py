@@ -239,7 +239,9 @@ def test_series_equals_per_store_sweeps(arith, per_launch, even, monkeypatch):
     if per_launch:
         monkeypatch.setenv("ARIANNA_SERIES_PER_LAUNCH", str(per_launch))
     M, seed = 70001, 11
-    Ks = [10, 1, 7, 10, 10, 3, 0, 12, 5, 10, 10, 10, 9, 10, 11, 10, 10, 2, 10, 10]      # 20 stores > 16 per launch
+    # 22 stores > 16 per launch; empty intervals (two stores with no Metropolis step between them: Metropolis every
+    # 2 steps, StoreCallbacks every step) at an even (44) AND at odd (57, 141) cumulative steps
+    Ks = [10, 1, 7, 10, 10, 3, 0, 12, 1, 0, 4, 10, 10, 10, 9, 10, 11, 10, 10, 0, 2, 10]
     pre = 3                                                         # the series starts on an odd step
     if even:                                                        # whole-pair intervals: the flat-loop fast path
         Ks, pre = [10, 2, 8, 10, 10, 4, 6, 12, 4, 10, 10, 10, 8, 10, 12, 10, 10, 2, 10, 10], 4

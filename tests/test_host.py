@@ -121,6 +121,10 @@ def test_shard_bounds_partition():
 def test_julia_number_rendering():
     assert A._jl(0.25) == "0.25" and A._jl(1e-5) == "1.0e-5" and A._jl(float("nan")) == "NaN"
     assert A._jl([0.5, float("nan")]) == "[0.5, NaN]" and A._jl(3) == "3"
+    # Julia switches to exponent form at 1e6 (Python only at 1e16) and writes "1.0e6", not "1e+06"
+    assert A._jl(999999.0) == "999999.0" and A._jl(1e6) == "1.0e6" and A._jl(-2.5e7) == "-2.5e7"
+    assert A._jl(123456789.125) == "1.23456789125e8" and A._jl(1e16) == "1.0e16" and A._jl(1.5e300) == "1.5e300"
+    assert A._jl(0.0001) == "0.0001" and A._jl(-0.0) == "-0.0" and A._jl(float("-inf")) == "-Inf"
 
 
 # ---- learner rules -------------------------------------------------------------------------------------------
@@ -198,7 +202,11 @@ def test_run_matches_stepwise_oracle_and_fuses_steps(tmp_path, fake_engine):
     assert list(t) == [0] + sampletimes and np.array_equal(x[-1], ref.x)
     last = open(tmp_path / "trajectories" / str(M) / "lastframe.dat").read()
     assert last == f"{steps} {A._jl(float(ref.x[-1]))}\n"
-    assert "Metropolis" in open(tmp_path / "summary.log").read()
+    summary = open(tmp_path / "summary.log").read()
+    assert "Metropolis" in summary
+    # update_summary / finalise_summary (simulation.jl:146-165)
+    assert "Report:\n\tSimulation time: " in summary and "\tSimulation size: " in summary and " MB\n" in summary
+    assert summary.rstrip().split("\n")[-1].startswith("\tStatus: Completed on ")
 
 
 def _callbacks_only_setup(path, M=48, steps=400, burn=100, traj_every=None):
@@ -279,6 +287,53 @@ def test_lookahead_refuses_unplanned_observation(tmp_path, fake_engine):
     assert chains3._ahead > 0
     with pytest.raises(RuntimeError):
         chains3.x
+
+
+def test_lookahead_barrier_listed_before_metropolis(tmp_path, fake_engine):
+    """An algorithm listed BEFORE Metropolis sees the chains before the Metropolis step of its time
+    (simulation.jl:184-191 runs the list in order): a look-ahead stretch must stop short of such a barrier even when a
+    callback store falls on the same time.  Also: Metropolis every 2nd step + callbacks every step gives empty store
+    intervals (K = 0) inside the stretch."""
+    seen = {}
+
+    class Peek(A.AriannaAlgorithm):
+        def __init__(self, chains, **extras):
+            pass
+
+        def make_step(self, simulation):
+            seen[simulation.t] = simulation.chains.x.copy()
+
+    def build(path, lookahead):
+        chains = mb.ParticleEnsemble(O.init_synthetic(42, 0, 48), 2.0)
+        pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.1), 1.0),)
+        sim = mb.Simulation(chains, (
+            dict(algorithm=Peek, scheduler=[120, 200, 333]),              # 120 and 200 coincide with stores
+            dict(algorithm=mb.Metropolis, pool=pool, seed=42, scheduler=list(range(1, 401, 2)) + [400]),
+            dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance),
+                 scheduler=list(range(100, 401))),
+        ), 400, path=str(path))
+        sim.lookahead = lookahead
+        return chains, sim
+
+    ca, sa = build(tmp_path / "look", True)
+    mb.run(sa)
+    seen_a = dict(seen)
+    seen.clear()
+    cb, sb = build(tmp_path / "plain", False)
+    mb.run(sb)
+    assert sorted(seen_a) == sorted(seen) == [120, 200, 333]
+    for t in seen:
+        assert np.array_equal(seen_a[t], seen[t]), t
+    for name in ("energy.dat", "acceptance.dat"):
+        assert open(tmp_path / "look" / name).read() == open(tmp_path / "plain" / name).read()
+    assert np.array_equal(ca.engine.get_state(), cb.engine.get_state())
+    assert ca.engine.steps_done == cb.engine.steps_done == 201
+    assert ca.engine.series_calls >= 3 and ca.engine.launch_count < cb.engine.launch_count / 10
+    # the barrier at t = 120 saw the state after the Metropolis steps scheduled at times < 120: 60 of them
+    ref = O.Ensemble(O.init_synthetic(42, 0, 48), 2.0, [0.1])
+    _, z, ua = O.draws_philox(42, 0, 48, 0, 60, with_cat=False)
+    ref.sweep_replay(None, z, ua)
+    assert np.array_equal(seen_a[120], ref.x)
 
 
 def test_simulation_constructor_contract(tmp_path, fake_engine):
@@ -525,6 +580,7 @@ def test_c_host_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
 
 # ---- property tests (hypothesis) of the host-side planning helpers ---------------------------------------------
 def test_properties_of_schedules_and_shards():
+    pytest.importorskip("hypothesis")
     from hypothesis import given, settings, strategies as st
 
     @settings(max_examples=200, deadline=None)
@@ -552,6 +608,7 @@ def test_properties_of_schedules_and_shards():
 def test_lookahead_plan_properties(tmp_path, fake_engine):
     """For random schedules of a trajectory barrier the look-ahead never crosses a barrier, never skips a store and
     the files equal the one-launch-per-store run."""
+    pytest.importorskip("hypothesis")
     from hypothesis import given, settings, strategies as st
     count = [0]
 
