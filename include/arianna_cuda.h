@@ -162,6 +162,10 @@ ARIANNA_API int32_t arianna_series_per_launch(arianna_handle *h, int32_t *n);
  * reusable on return.  Multi-GPU hosts all-reduce the device records afterwards (arianna_series_global). */
 ARIANNA_API int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_stores, const int64_t *K,
                                          double *records, double *x_out, int32_t n_slices);
+/* PCIe view of the LAST arianna_run_host_job call: device time (ms, first copy start -> last copy end on the upload /
+ * download stream, so it includes the waits on the sweeps in between) and the achieved GB/s of each direction; NaN for
+ * a direction the job did not use.  Any pointer may be NULL. */
+ARIANNA_API int32_t arianna_job_timing(arianna_handle *h, double *h2d_ms, double *h2d_gbs, double *d2h_ms, double *d2h_gbs);
 
 /* Replay mode: the same K steps consuming caller-supplied draws instead of the native RNG, always in EXACT
  * arithmetic.  u_cat / z / u_acc are step-major [K][n_chains] (u_cat may be NULL when n_moves == 1);
@@ -233,6 +237,12 @@ ARIANNA_API int32_t arianna_measure_fp64_peak(arianna_handle *h, double *flops_p
 ARIANNA_API int32_t arianna_nccl_unique_id(void *id128);
 ARIANNA_API int32_t arianna_comm_init(arianna_handle *h, const void *id128, int32_t rank, int32_t n_ranks);
 ARIANNA_API int32_t arianna_callbacks_global(arianna_handle *h, double *mean_energy, double *acc_per_move);
+/* arianna_series_global without stalling the compute stream: the records of the last series call are snapshotted and
+ * the all-reduce + the copy into `records_pinned` (page-locked host memory, [n_stores][3]) run on a side stream while
+ * the NEXT sweep already executes -- the next launch does not depend on the callback means of this one.
+ * arianna_series_global_wait (or arianna_synchronize) completes it; one operation in flight per handle. */
+ARIANNA_API int32_t arianna_series_global_begin(arianna_handle *h, int32_t n_stores, double *records_pinned);
+ARIANNA_API int32_t arianna_series_global_wait(arianna_handle *h);
 ARIANNA_API int32_t arianna_pgmc_read_global(arianna_handle *h, arianna_gradient_data *out, int32_t n_learn);
 
 /* Diagnostic: evaluates the device FP64 math layer (csrc/math64.cuh) on host arrays so that tests can compare

@@ -73,6 +73,7 @@ SYMBOLS = {
     "arianna_series_per_launch": (C.c_int32, [_H, C.POINTER(C.c_int32)]),
     "arianna_run_host_job": (C.c_int32, [_H, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p,
                                          C.c_int32]),
+    "arianna_job_timing": (C.c_int32, [_H, _D, _D, _D, _D]),
     "arianna_sweep_replay": (C.c_int32, [_H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "arianna_set_rng_state": (C.c_int32, [_H, C.c_void_p]),
     "arianna_get_rng_state": (C.c_int32, [_H, C.c_void_p]),
@@ -98,6 +99,8 @@ SYMBOLS = {
     "arianna_nccl_unique_id": (C.c_int32, [C.c_void_p]),
     "arianna_comm_init": (C.c_int32, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "arianna_callbacks_global": (C.c_int32, [_H, _D, _D]),
+    "arianna_series_global_begin": (C.c_int32, [_H, C.c_int32, C.c_void_p]),
+    "arianna_series_global_wait": (C.c_int32, [_H]),
     "arianna_pgmc_read_global": (C.c_int32, [_H, C.POINTER(GradientData), C.c_int32]),
     "arianna_debug_math": (C.c_int32, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
 }

@@ -68,8 +68,16 @@ struct arianna_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaStream_t copy_stream = nullptr;   // D2H of trajectory frames overlaps the next sweep
+    cudaStream_t copy_stream = nullptr;   // D2H: trajectory frames / host-job downloads overlap the next sweep
+    cudaStream_t h2d_stream = nullptr;    // H2D: host-job uploads (PCIe is full duplex: the two directions get a stream each)
     cudaEvent_t ev_snap = nullptr, ev_copy = nullptr;
+    cudaEvent_t ev_job[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] first/last upload, [2,3] first/last download of the last host job
+    bool job_timed[2] = {false, false};
+    int64_t job_bytes[2] = {0, 0};
+    cudaStream_t coll_stream = nullptr;   // the tiny all-reduces of a series run beside the next sweep
+    cudaEvent_t ev_coll_src = nullptr, ev_coll_done = nullptr;
+    double *d_coll_series = nullptr;      // snapshot of d_series the asynchronous all-reduce works on
+    int64_t coll_series_cap = 0;
     cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};   // device-time brackets: [0,1] last sweep/series/job, [2,3] last estimator pass
     bool timed[2] = {false, false};
     double *d_snap = nullptr;             // device snapshot of x the copy stream reads from
@@ -375,9 +383,16 @@ int32_t arianna_destroy(arianna_handle *h)
     cudaFree(h->d_ki); cudaFree(h->d_wi); cudaFree(h->d_fi); cudaFree(h->d_partials); cudaFree(h->d_ticket);
     cudaFree(h->d_sums); cudaFree(h->d_gd); cudaFree(h->d_csum); cudaFree(h->d_scratch); cudaFree(h->d_tables);
     cudaFree(h->d_series); cudaFree(h->d_series_partials);
+    if (h->coll_stream) cudaStreamSynchronize(h->coll_stream);
     if (h->comm) { nccl::g_api.CommDestroy(h->comm); h->comm = nullptr; }
     cudaFree(h->d_coll);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->h2d_stream) { cudaStreamSynchronize(h->h2d_stream); cudaStreamDestroy(h->h2d_stream); }
+    if (h->coll_stream) { cudaStreamSynchronize(h->coll_stream); cudaStreamDestroy(h->coll_stream); }
+    cudaFree(h->d_coll_series);
+    if (h->ev_coll_src) cudaEventDestroy(h->ev_coll_src);
+    if (h->ev_coll_done) cudaEventDestroy(h->ev_coll_done);
+    for (auto &e : h->ev_job) if (e) cudaEventDestroy(e);
     for (auto &e : h->ev_t) if (e) cudaEventDestroy(e);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
@@ -441,6 +456,8 @@ static int32_t ensure_copy_stream(arianna_handle *h)
 {
     if (h->copy_stream) return ARIANNA_OK;
     CU_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU_TRY(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    for (auto &e : h->ev_job) CU_TRY(h, cudaEventCreate(&e));
     CU_TRY(h, cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
     CU_TRY(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
     CU_TRY(h, cudaEventRecord(h->ev_copy, h->copy_stream));
@@ -733,9 +750,10 @@ int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t 
     return ARIANNA_OK;
 }
 
-// A whole callbacks-only job with HOST buffers, pipelined over slices of the chains: the upload of slice i+1 and the
-// download of slice i-1 run on the copy stream while slice i sweeps through ALL the store intervals on the compute
-// stream (chains are independent, so slice-major order gives the same chains and the same records as time-major).
+// A whole callbacks-only job with HOST buffers, pipelined over slices of the chains: the upload of slice i+1 (H2D
+// stream) and the download of slice i-1 (D2H stream) run while slice i sweeps through ALL the store intervals on the
+// compute stream (chains are independent, so slice-major order gives the same chains and the same records as
+// time-major).  PCIe is full duplex: uploads and downloads never queue behind each other.
 int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_stores, const int64_t *K, double *records,
                              double *x_out, int32_t n_slices)
 {
@@ -752,7 +770,12 @@ int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_st
     per = (per + kBlock - 1) / kBlock * kBlock;
     const int ns = (int)((h->M + per - 1) / per);
     std::vector<cudaEvent_t> up(ns, nullptr), done(ns, nullptr);
+    bool queued = false;
     auto cleanup = [&]() {
+        if (queued) {   // a failure after work was queued: drain it so that no copy outlives the caller's buffers
+            cudaStreamSynchronize(h->h2d_stream); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->copy_stream);
+            h->sums_valid = false;
+        }
         for (auto e : up) if (e) cudaEventDestroy(e);
         for (auto e : done) if (e) cudaEventDestroy(e);
     };
@@ -761,34 +784,51 @@ int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_st
         cudaError_t _e = (expr);                                                                              \
         if (_e != cudaSuccess) {                                                                              \
             cleanup();                                                                                        \
-            return fail(h, ARIANNA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+            return fail(h, ARIANNA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) +             \
+                        (queued ? " (the job was partly executed: chain state is undefined)" : ""));          \
         }                                                                                                     \
     } while (0)
+    h->job_timed[0] = h->job_timed[1] = false;
+    h->job_bytes[0] = x_in ? (int64_t)sizeof(double) * h->M : 0;
+    h->job_bytes[1] = x_out ? (int64_t)sizeof(double) * h->M : 0;
     // everything already queued on the compute stream must be done with x before the uploads overwrite it
     JOB_TRY(cudaEventRecord(h->ev_snap, h->stream));
+    JOB_TRY(cudaStreamWaitEvent(h->h2d_stream, h->ev_snap, 0));
     JOB_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
     for (int i = 0; i < ns; ++i) {
         JOB_TRY(cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming));
         JOB_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-        const int64_t off = (int64_t)i * per, m = (h->M - off < per) ? h->M - off : per;
-        if (x_in) {
-            JOB_TRY(cudaMemcpyAsync(h->d_x + off, x_in + off, sizeof(double) * m, cudaMemcpyHostToDevice, h->copy_stream));
-            JOB_TRY(cudaEventRecord(up[i], h->copy_stream));
+    }
+    if (x_in) {
+        JOB_TRY(cudaEventRecord(h->ev_job[0], h->h2d_stream));
+        for (int i = 0; i < ns; ++i) {
+            const int64_t off = (int64_t)i * per, m = (h->M - off < per) ? h->M - off : per;
+            queued = true;
+            JOB_TRY(cudaMemcpyAsync(h->d_x + off, x_in + off, sizeof(double) * m, cudaMemcpyHostToDevice, h->h2d_stream));
+            JOB_TRY(cudaEventRecord(up[i], h->h2d_stream));
         }
+        JOB_TRY(cudaEventRecord(h->ev_job[1], h->h2d_stream));
+        h->job_timed[0] = true;
     }
     time_mark(h, 0, true);
     for (int i = 0; i < ns; ++i) {
         const int64_t off = (int64_t)i * per, m = (h->M - off < per) ? h->M - off : per;
         if (x_in) JOB_TRY(cudaStreamWaitEvent(h->stream, up[i], 0));
         if (n_stores > 0) {
+            queued = true;
             rc = series_range(h, off, m, h->steps_done, n_stores, K, i > 0);
             if (rc) { cleanup(); return rc; }
         }
         if (x_out) {
             JOB_TRY(cudaEventRecord(done[i], h->stream));
             JOB_TRY(cudaStreamWaitEvent(h->copy_stream, done[i], 0));
+            if (i == 0) JOB_TRY(cudaEventRecord(h->ev_job[2], h->copy_stream));
             JOB_TRY(cudaMemcpyAsync(x_out + off, h->d_x + off, sizeof(double) * m, cudaMemcpyDeviceToHost, h->copy_stream));
         }
+    }
+    if (x_out) {
+        JOB_TRY(cudaEventRecord(h->ev_job[3], h->copy_stream));
+        h->job_timed[1] = true;
     }
     time_mark(h, 0, false);
     h->steps_done += total;
@@ -799,8 +839,28 @@ int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_st
     JOB_TRY(cudaEventRecord(h->ev_copy, h->copy_stream));
     JOB_TRY(cudaStreamSynchronize(h->stream));
     JOB_TRY(cudaStreamSynchronize(h->copy_stream));
+    JOB_TRY(cudaStreamSynchronize(h->h2d_stream));
 #undef JOB_TRY
+    queued = false;
     cleanup();
+    return ARIANNA_OK;
+}
+
+int32_t arianna_job_timing(arianna_handle *h, double *h2d_ms, double *h2d_gbs, double *d2h_ms, double *d2h_gbs)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    double *ms[2] = {h2d_ms, d2h_ms}, *gbs[2] = {h2d_gbs, d2h_gbs};
+    for (int w = 0; w < 2; ++w) {
+        if (ms[w]) *ms[w] = std::nan("");
+        if (gbs[w]) *gbs[w] = std::nan("");
+        if (!h->job_timed[w]) continue;
+        CU_TRY(h, cudaEventSynchronize(h->ev_job[2 * w + 1]));
+        float t = 0.f;
+        CU_TRY(h, cudaEventElapsedTime(&t, h->ev_job[2 * w], h->ev_job[2 * w + 1]));
+        if (ms[w]) *ms[w] = t;
+        if (gbs[w]) *gbs[w] = t > 0.f ? (double)h->job_bytes[w] / (t * 1e-3) / 1e9 : std::nan("");
+    }
     return ARIANNA_OK;
 }
 
@@ -1043,6 +1103,54 @@ int32_t arianna_series_global(arianna_handle *h, int32_t n_stores, double *recor
     return ARIANNA_OK;
 }
 
+// The same all-reduce without stalling the compute stream: the records of the last series are snapshotted (D2D on the
+// compute stream, microseconds), and the all-reduce + the D2H copy into page-locked `records` run on a side stream
+// while the NEXT sweep already executes -- the next launch does not depend on callback means.
+// arianna_series_global_wait() (or arianna_synchronize) completes it.  One operation in flight per handle: a second
+// begin waits (on the device) for the first.
+int32_t arianna_series_global_begin(arianna_handle *h, int32_t n_stores, double *records_pinned)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, records_pinned != nullptr && n_stores >= 0 && n_stores <= h->series_n,
+            "arianna_series_global_begin: n_stores exceeds the last arianna_sweep_series call");
+    if (n_stores == 0) return ARIANNA_OK;
+    DeviceGuard guard(h->device);
+    if (!h->coll_stream) {
+        CU_TRY(h, cudaStreamCreateWithFlags(&h->coll_stream, cudaStreamNonBlocking));
+        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_coll_src, cudaEventDisableTiming));
+        CU_TRY(h, cudaEventCreateWithFlags(&h->ev_coll_done, cudaEventDisableTiming));
+        CU_TRY(h, cudaEventRecord(h->ev_coll_done, h->coll_stream));
+    }
+    if (h->coll_series_cap < h->series_cap) {
+        CU_TRY(h, cudaStreamSynchronize(h->coll_stream));
+        cudaFree(h->d_coll_series);
+        h->d_coll_series = nullptr;
+        h->coll_series_cap = 0;
+        CU_TRY(h, cudaMalloc(&h->d_coll_series, sizeof(double) * 3 * h->series_cap));
+        h->coll_series_cap = h->series_cap;
+    }
+    const size_t n = (size_t)3 * n_stores;
+    CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_coll_done, 0));     // the previous operation has left the snapshot
+    CU_TRY(h, cudaMemcpyAsync(h->d_coll_series, h->d_series, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(h, cudaEventRecord(h->ev_coll_src, h->stream));
+    CU_TRY(h, cudaStreamWaitEvent(h->coll_stream, h->ev_coll_src, 0));
+    if (h->comm)
+        NCCL_TRY(h, nccl::g_api.AllReduce(h->d_coll_series, h->d_coll_series, n, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->comm,
+                                          h->coll_stream));
+    CU_TRY(h, cudaMemcpyAsync(records_pinned, h->d_coll_series, sizeof(double) * n, cudaMemcpyDeviceToHost, h->coll_stream));
+    CU_TRY(h, cudaEventRecord(h->ev_coll_done, h->coll_stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_series_global_wait(arianna_handle *h)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    if (!h->coll_stream) return ARIANNA_OK;
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaEventSynchronize(h->ev_coll_done));
+    return ARIANNA_OK;
+}
+
 int32_t arianna_pgmc_read_global(arianna_handle *h, arianna_gradient_data *out, int32_t n_learn)
 {
     if (!h) return ARIANNA_ERR_INVALID;
@@ -1194,6 +1302,8 @@ int32_t arianna_synchronize(arianna_handle *h)
     DeviceGuard guard(h->device);
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     if (h->copy_stream) CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    if (h->h2d_stream) CU_TRY(h, cudaStreamSynchronize(h->h2d_stream));
+    if (h->coll_stream) CU_TRY(h, cudaStreamSynchronize(h->coll_stream));
     return ARIANNA_OK;
 }
 

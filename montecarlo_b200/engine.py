@@ -176,6 +176,12 @@ class CudaEnsemble:
                                                 _ptr(rec), ptr(x_out), int(n_slices)))
         return rec
 
+    def job_timing(self):
+        """PCIe view of the last run_host_job: {"h2d_ms", "h2d_gbs", "d2h_ms", "d2h_gbs"} (arianna_job_timing)."""
+        v = [C.c_double() for _ in range(4)]
+        self._ck(self._lib.arianna_job_timing(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("h2d_ms", "h2d_gbs", "d2h_ms", "d2h_gbs"), (x.value for x in v)))
+
     @property
     def series_per_launch(self) -> int:
         """Store intervals one sweep_series launch fuses for this ensemble (arianna_series_per_launch)."""
@@ -196,6 +202,14 @@ class CudaEnsemble:
         rec = np.empty((int(n_stores), 3), dtype=np.float64)
         self._ck(self._lib.arianna_series_global(self._h, int(n_stores), _ptr(rec)))
         return rec
+
+    def series_global_begin(self, n_stores: int, records_pinned_ptr: int):
+        """Asynchronous series_global: all-reduce + D2H into page-locked memory on a side stream, overlapping the next
+        sweep (arianna_series_global_begin); series_global_wait() / synchronize() completes it."""
+        self._ck(self._lib.arianna_series_global_begin(self._h, int(n_stores), C.c_void_p(int(records_pinned_ptr))))
+
+    def series_global_wait(self):
+        self._ck(self._lib.arianna_series_global_wait(self._h))
 
     def sweep_replay(self, u_cat, z, u_acc, want_decisions: bool = False):
         z = np.ascontiguousarray(z, dtype=np.float64)

@@ -580,6 +580,17 @@ AO_API void ao_pgmc_xoshiro(int64_t M, int q_batch, int n_learn, const int *lear
     }
 }
 
+/* Team size of the OpenMP loops above; launchers such as torchrun export OMP_NUM_THREADS=1, which the CPU arm of
+ * bench.py must override to time the reference path on ALL host cores. */
+AO_API void ao_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 AO_API int ao_num_threads(void)
 {
 #ifdef _OPENMP

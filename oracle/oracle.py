@@ -247,3 +247,7 @@ def ziggurat_tables():
 
 def num_threads():
     return lib().ao_num_threads()
+
+
+def set_num_threads(n: int):
+    lib().ao_set_num_threads(C.c_int(int(n)))

@@ -25,7 +25,9 @@ def test_bench_line_contract(series):
     assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert "C3" in d["config"]["workload"] and d["config"]["chains_per_gpu"] == 1 << 22
     assert d["value"] > 1e10 and abs(d["value"] - (1 << 22) * 10 * 25 / (d["ms_per_step"] * 25e-3)) < 1e-6 * d["value"]
-    assert d["gpu_launches"] >= 25 // max(1, d["config"]["stores_per_launch"])
+    assert d["gpu_launches"] >= 25 // max(1, d["engine"]["stores_per_launch"])
+    assert "stores_per_launch" not in d["config"] and sum(d["engine"]["launch_plan"]) == 25
+    assert d["roofline"]["kernel_launches_averaged"] >= 2
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     r = d["roofline"]
     assert r["bound"] in ("fp64", "hbm", "tensor") and r["unit"] == "TFLOP/s" and "traffic" in r
@@ -35,5 +37,11 @@ def test_bench_line_contract(series):
     assert e["unit"] == d["unit"] and 0 < e["value"] <= 1.05 * d["value"]
     assert e["h2d_bytes_per_step"] >= 8 * (1 << 22) // 25 and e["d2h_bytes_per_step"] >= 8 * (1 << 22) // 25
     assert abs(d["mean_energy"] - e["energy"]) < 0.02          # both runs sample the same ensemble a little later
+    if series == "0":
+        assert e["pcie_rank0"]["h2d_gbs"] > 1 and e["pcie_rank0"]["d2h_gbs"] > 1
+    assert d["strong"]["chains_total"] == 1 << 22 and d["strong"]["value"] == d["value"]
+    p = d["parity"]
+    assert p["ok"] is True and p["accepted_sums_equal_oracle"] is True and p["energy_sum_max_rel_err_vs_oracle"] <= 1e-12
+    assert p["x_bits_checksum_equals_1gpu"] in (True, None)
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == d["unit"] and c["sample"]

@@ -300,10 +300,25 @@ def test_host_job_pipelined_over_slices(n_slices):
         np.testing.assert_allclose(rec_a, rec_b, rtol=1e-13)
         assert np.array_equal(rec_a[:, 2], np.full(len(Ks), float(M))) and a.steps_done == b.steps_done == sum(Ks)
         np.testing.assert_array_equal(a.callback_sums(), rec_a[-1])
+        jt = a.job_timing()
+        assert jt["h2d_ms"] > 0 and jt["d2h_ms"] > 0 and jt["h2d_gbs"] > 0.05 and jt["d2h_gbs"] > 0.05
         # a second job continues from the resident state (x_in = None) and may skip the download
         rec_a2 = a.run_host_job([4, 4], n_slices=n_slices)
         rec_b2 = b.sweep_series([4, 4])
         np.testing.assert_allclose(rec_a2, rec_b2, rtol=1e-13)
+        assert np.array_equal(a.get_state(), b.get_state())
+        # PCIe view of the job (both directions were used by the first job, none by the second)
+        jt = a.job_timing()
+        assert all(math.isnan(v) for v in jt.values())
+        # the asynchronous records route: snapshot + (all-reduce) + D2H on a side stream while the next sweep runs
+        pinned = torch.empty((2, 3), dtype=torch.float64).pin_memory()
+        a.sweep_series([4, 4], read=False)
+        a.series_global_begin(2, pinned.data_ptr())
+        a.sweep(6)                                                  # overlaps the copy; must not disturb the records
+        a.series_global_wait()
+        rec_b3 = b.sweep_series([4, 4])
+        b.sweep(6)
+        np.testing.assert_allclose(pinned.numpy(), rec_b3, rtol=1e-13)
         assert np.array_equal(a.get_state(), b.get_state())
         # the overlapped trajectory write-back shares the copy stream with the host job
         a.get_state_async(xout.data_ptr())

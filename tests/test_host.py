@@ -465,10 +465,29 @@ def test_bench_reference_arm_prints_the_contract_line():
     import json
     import subprocess
     import sys
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the arm must still use ALL host cores
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
-                          "--warmup", "1", "--ref-log2-chains", "12"], capture_output=True, text=True, timeout=300)
+                          "--warmup", "1", "--ref-log2-chains", "12"], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert out.returncode == 0, out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["sample"]["chains"] == 1 << 12 and line["sample"]["full_per_gpu_ensemble"] is False
+    assert "2^12 chains" in line["cpu_baseline"]["sample"]
+    # the workload description is the one our arm prints for the same flags (the driver compares the two)
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    ours = bench.workload_config(argparse.Namespace(log2_chains=27, scaling="weak", mc_steps=10), 1)
+    assert line["config"] == ours and "stores_per_launch" not in ours
+    assert bench.launch_plan(20, 11) == [10, 10] and bench.launch_plan(110, 11) == [11] * 10
+    assert bench.launch_plan(25, 11) == [9, 9, 7] and bench.launch_plan(3, 11) == [3] and bench.launch_plan(5, 1) == [1] * 5
+    # without an explicit sample size the arm sizes it to the time budget (here: tiny budget -> a bounded sample)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--ref-seconds", "0.05"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    auto = json.loads(out.stdout.strip().splitlines()[-1])
+    assert 1 << 10 <= auto["sample"]["chains"] < 1 << 27 and auto["config"] == ours
     assert line["impl"] == "reference" and line["metric"] == "metropolis_chain_steps_per_sec"
     assert line["unit"] == "chain-steps/s" and line["higher_is_better"] is True and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
