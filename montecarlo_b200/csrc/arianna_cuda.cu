@@ -585,17 +585,23 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
         xp.M = h->M; xp.K = K; xp.rng = h->d_rng; xp.ki = h->d_ki; xp.wi = h->d_wi; xp.fi = h->d_fi;
         xp.tables = h->d_tables;
         xp.pool = h->pool;
-        dispatch_pot(h->cfg.potential, [&](auto pot) {
+        // static tables (~25 KB) + 2 KB of counters per move: pools of 12+ moves pass the 48 KB default and must opt in
+        auto launch = [&](auto kernel, size_t dyn) -> int32_t {
+            cudaFuncAttributes fa{};
+            CU_TRY(h, cudaFuncGetAttributes(&fa, kernel));
+            if (fa.sharedSizeBytes + dyn > 48 * 1024)
+                CU_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            kernel<<<wave_grid(h, kernel, dyn, h->M), kBlock, dyn, h->stream>>>(xp);
+            return ARIANNA_OK;
+        };
+        const int32_t rc = dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
             constexpr int POT = decltype(pot)::value;
-            if (exact) {
-                if (multi) sweep_xoshiro_kernel<POT, ARITH_EXACT, true><<<wave_grid(h, sweep_xoshiro_kernel<POT, ARITH_EXACT, true>, smem, h->M), kBlock, smem, h->stream>>>(xp);
-                else sweep_xoshiro_kernel<POT, ARITH_EXACT, false><<<wave_grid(h, sweep_xoshiro_kernel<POT, ARITH_EXACT, false>, 0, h->M), kBlock, 0, h->stream>>>(xp);
-            } else {
-                if (multi) sweep_xoshiro_kernel<POT, ARITH_FAST, true><<<wave_grid(h, sweep_xoshiro_kernel<POT, ARITH_FAST, true>, smem, h->M), kBlock, smem, h->stream>>>(xp);
-                else sweep_xoshiro_kernel<POT, ARITH_FAST, false><<<wave_grid(h, sweep_xoshiro_kernel<POT, ARITH_FAST, false>, 0, h->M), kBlock, 0, h->stream>>>(xp);
-            }
-            return 0;
+            if (exact) return multi ? launch(sweep_xoshiro_kernel<POT, ARITH_EXACT, true>, smem)
+                                    : launch(sweep_xoshiro_kernel<POT, ARITH_EXACT, false>, 0);
+            return multi ? launch(sweep_xoshiro_kernel<POT, ARITH_FAST, true>, smem)
+                         : launch(sweep_xoshiro_kernel<POT, ARITH_FAST, false>, 0);
         });
+        if (rc) return rc;
     }
     CU_TRY(h, cudaGetLastError());
     ++h->launches;
@@ -892,14 +898,19 @@ int32_t arianna_sweep_replay(arianna_handle *h, int64_t K, const double *u_cat, 
         rp.M = h->M; rp.K = k; rp.u_cat = multi ? duc : nullptr; rp.z = dz; rp.u_acc = dua; rp.decisions = ddec;
         rp.tables = h->d_tables;
         rp.pool = h->pool;
-        dispatch_pot(h->cfg.potential, [&](auto pot) {
+        auto go = [&](auto kernel, size_t dyn) -> int32_t {
+            cudaFuncAttributes fa{};
+            CU_TRY(h, cudaFuncGetAttributes(&fa, kernel));
+            if (fa.sharedSizeBytes + dyn > 48 * 1024)
+                CU_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            kernel<<<wave_grid(h, kernel, dyn, h->M), kBlock, dyn, h->stream>>>(rp);
+            return ARIANNA_OK;
+        };
+        const int32_t rc = dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
             constexpr int POT = decltype(pot)::value;
-            if (multi)
-                sweep_replay_kernel<POT, true><<<wave_grid(h, sweep_replay_kernel<POT, true>, smem, h->M), kBlock, smem, h->stream>>>(rp);
-            else
-                sweep_replay_kernel<POT, false><<<wave_grid(h, sweep_replay_kernel<POT, false>, 0, h->M), kBlock, 0, h->stream>>>(rp);
-            return 0;
+            return multi ? go(sweep_replay_kernel<POT, true>, smem) : go(sweep_replay_kernel<POT, false>, 0);
         });
+        if (rc) return rc;
         CU_TRY(h, cudaGetLastError());
         ++h->launches;
         return ARIANNA_OK;

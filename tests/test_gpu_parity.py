@@ -72,6 +72,42 @@ def test_replay_golden_fixtures(golden_dir, name):
         np.testing.assert_allclose(ma, g["acceptance"], rtol=1e-13, equal_nan=True)
 
 
+def test_sixteen_move_pool_all_generators():
+    """ARIANNA_MAX_MOVES moves: the multi-move kernels keep 2 KB of counters per move in shared memory next to their
+    tables, which passes the 48 KB default for 12+ moves (opt-in required) -- replay, XOSHIRO and native Philox."""
+    M, K, beta = 3001, 23, 2.0
+    sigma = [0.05 * (k + 1) for k in range(16)]
+    weight = [1.0 / 16] * 16
+    x0 = O.init_synthetic(3, 0, M)
+    uc, z, ua = _xoshiro_draws(x0, beta, sigma, weight, K)
+    ref = O.Ensemble(x0, beta, sigma, weight)
+    dref, _, _ = ref.sweep_replay(uc, z, ua, want_decisions=True)
+    with mb.CudaEnsemble(M, beta, sigma, weight, arith="exact") as eng:                    # replay
+        eng.set_state(x0)
+        assert np.array_equal(eng.sweep_replay(uc, z, ua, want_decisions=True), dref)
+        assert np.array_equal(eng.get_state(), ref.x)
+        acc, tot = eng.chain_counters()
+        assert np.array_equal(acc.astype(np.int64), ref.acc) and np.array_equal(tot.astype(np.int64), ref.tot)
+    with mb.CudaEnsemble(M, beta, sigma, weight, rng="xoshiro", arith="exact") as eng:     # device xoshiro256++
+        gen = O.Ensemble(x0, beta, sigma, weight)
+        gen.seed_xoshiro(42)
+        eng.set_state(x0)
+        eng.set_rng_state(gen.states)
+        eng.set_ziggurat_tables(*O.ziggurat_tables())
+        eng.sweep(K)
+        assert np.max(np.abs(eng.get_state() - ref.x)) < 1e-12      # ziggurat tail samples go through log/exp (≤ 1 ulp)
+        assert np.array_equal(eng.chain_counters()[0].astype(np.int64), ref.acc)
+    uc, z, ua = O.draws_philox(3, 0, M, 0, K)
+    ref = O.Ensemble(x0, beta, sigma, weight)
+    ref.sweep_replay(uc, z, ua)
+    with mb.CudaEnsemble(M, beta, sigma, weight, seed=3, arith="fast") as eng:             # native Philox
+        eng.init_synthetic()
+        eng.sweep(K)
+        assert np.max(np.abs(eng.get_state() - ref.x)) < 1e-12
+        acc, tot = eng.chain_counters()
+        assert np.array_equal(acc.astype(np.int64), ref.acc) and np.array_equal(tot.astype(np.int64), ref.tot)
+
+
 def test_replay_per_chain_beta_and_chunked_calls():
     M, K = 4099, 40
     x0 = O.init_synthetic(5, 0, M)
