@@ -139,10 +139,11 @@ ARIANNA_API int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags);
  * interval ON THE DEVICE.  Equivalent to  for i: arianna_sweep(h, K[i], ARIANNA_SWEEP_REDUCE); arianna_callback_sums
  * but the chains stay in registers across up to ARIANNA_MAX_SERIES intervals per launch, nothing is copied to the
  * host between stores and the multi-GPU host all-reduces the whole series at once.  records (optional, host):
- * [n_stores][3] = (Σ e, Σ_c acc_c/tot_c, local chain count) per store, local shard; NULL = leave them on the device
- * (arianna_series_device; asynchronous).  arianna_series_global all-reduces the device records of the LAST
- * arianna_sweep_series call over the communicator (arianna_comm_init) and returns ensemble-wide records.
- * Single-move pools with the native Philox stream only (ARIANNA_ERR_UNSUPPORTED otherwise: use arianna_sweep). */
+ * [n_stores][2 + n_moves] = (Σ e, Σ_c acc_ck/tot_ck for every move k, local chain count) per store, local shard --
+ * callback_acceptance is a per-move vector (metropolis.jl:319-321), NaN while some chain never tried a move; NULL =
+ * leave them on the device (arianna_series_device; asynchronous).  arianna_series_global all-reduces the device
+ * records of the LAST arianna_sweep_series call over the communicator (arianna_comm_init) and returns ensemble-wide
+ * records.  Native Philox stream only (ARIANNA_ERR_UNSUPPORTED otherwise: use arianna_sweep). */
 #define ARIANNA_MAX_SERIES 64
 ARIANNA_API int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t *K, double *records);
 ARIANNA_API int32_t arianna_series_device(arianna_handle *h, double **dptr, int32_t *n_doubles);
@@ -152,7 +153,7 @@ ARIANNA_API int32_t arianna_series_global(arianna_handle *h, int32_t n_stores, d
 ARIANNA_API int32_t arianna_series_per_launch(arianna_handle *h, int32_t *n);
 
 /* The same stretch as a complete job with HOST buffers: chains in (x_in, [n_chains], NULL = keep the resident state),
- * n_stores store intervals, records out ([n_stores][3] local-shard sums, may be NULL), chains out (x_out, may be
+ * n_stores store intervals, records out ([n_stores][2 + n_moves] local-shard sums, may be NULL), chains out (x_out, may be
  * NULL) -- i.e. `chains = [...]; run!(Simulation(chains, (Metropolis, StoreCallbacks, StoreLastFrames), steps))`
  * (src/simulation.jl:175-204) in one call.  The ensemble is cut into n_slices slices of chains that go through ALL the
  * store intervals one slice after the other, so that the upload of the next slice and the download of the previous
@@ -238,7 +239,7 @@ ARIANNA_API int32_t arianna_nccl_unique_id(void *id128);
 ARIANNA_API int32_t arianna_comm_init(arianna_handle *h, const void *id128, int32_t rank, int32_t n_ranks);
 ARIANNA_API int32_t arianna_callbacks_global(arianna_handle *h, double *mean_energy, double *acc_per_move);
 /* arianna_series_global without stalling the compute stream: the records of the last series call are snapshotted and
- * the all-reduce + the copy into `records_pinned` (page-locked host memory, [n_stores][3]) run on a side stream while
+ * the all-reduce + the copy into `records_pinned` (page-locked host memory, [n_stores][2 + n_moves]) run on a side stream while
  * the NEXT sweep already executes -- the next launch does not depend on the callback means of this one.
  * arianna_series_global_wait (or arianna_synchronize) completes it; one operation in flight per handle. */
 ARIANNA_API int32_t arianna_series_global_begin(arianna_handle *h, int32_t n_stores, double *records_pinned);

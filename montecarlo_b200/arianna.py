@@ -252,8 +252,7 @@ class ParticleEnsemble(AriannaSystem):
             self.pending += n
 
     def _series_supported(self):
-        return (self._lookahead is not None and len(self.pool) == 1 and self.rng == "philox"
-                and hasattr(self.engine, "sweep_series"))
+        return self._lookahead is not None and self.rng == "philox" and hasattr(self.engine, "sweep_series")
 
     def _run_series(self, Ks):
         """One arianna_sweep_series call for [pending, K_1, K_2, ...]; every record lands in the cache."""
@@ -264,9 +263,9 @@ class ParticleEnsemble(AriannaSystem):
             import torch
             self.engine.sweep_series(Ks, read=False)
             with torch.cuda.stream(self.engine.torch_stream()):
-                rec = allreduce_sums(None, self.engine.series_tensor()).reshape(len(Ks), 3)   # ONE all-reduce
+                rec = allreduce_sums(None, self.engine.series_tensor()).reshape(len(Ks), 2 + nm)   # ONE all-reduce
         else:
-            rec = allreduce_sums(self.engine.sweep_series(Ks).reshape(-1)).reshape(len(Ks), 3)
+            rec = allreduce_sums(self.engine.sweep_series(Ks).reshape(-1)).reshape(len(Ks), 2 + nm)
         done = self.engine.steps_done - int(sum(Ks))
         self._series_cache = {}
         for K, r in zip(Ks, rec):

@@ -104,7 +104,11 @@ struct arianna_handle {
 
     double *d_series = nullptr;     // [series_cap][3] callback records of the last arianna_sweep_series call
     int64_t series_cap = 0, series_n = 0;
-    double *d_series_partials = nullptr;   // [max grid][kMaxSeries + 1][2]
+    double *d_series_partials = nullptr;   // single-move: [grid][n + 1][2]; multi-move: [grid][n][1 + n_moves] (grow-only)
+    size_t series_partials_cap = 0;        // doubles
+    uint8_t *d_cat_table = nullptr;        // multi-move pools: move index by the top 12 bits of the categorical word
+    uint32_t cat_thr[kMaxMoves] = {};      // T_j = min(ceil(cp_j 2^32), 2^32 - 1)
+    int cat_n = 0;                         // thresholds below 2^32 (the reachable ones)
 
     nccl::Comm comm = nullptr;      // optional: set by arianna_comm_init
     int comm_rank = 0, comm_size = 1;
@@ -202,6 +206,39 @@ void make_zig_tables(uint64_t *ki, double *wi, double *fi)
     ki[1] = 0;
 }
 
+// Doubles per callback record: [Σe, Σ_c acc/tot per move, count]
+inline int record_stride(const arianna_handle *h) { return 2 + h->pool.n_moves; }
+
+// Categorical(weights) as integer thresholds + a bucket table (kernels_multi.cuh).  cp_j is summed in binary64 exactly
+// as Distributions' scan does (`cp += p[i += 1]` [EXT]); cp <= w 2^-32  <=>  w >= ceil(cp 2^32).  Table entry of the
+// bucket of the top 12 bits: k (no threshold inside) | 0x80 + j (exactly one, T_j) | 0xFF (several).
+int build_cat_table(const double *weight, int nm, uint32_t *thr32, uint8_t *table)
+{
+    unsigned long long thr[kMaxMoves];
+    double cp = weight[0];
+    int n_reach = 0;
+    for (int j = 0; j < kMaxMoves; ++j) thr32[j] = 0xffffffffu;
+    for (int j = 0; j < nm - 1; ++j) {
+        if (j > 0) cp = cp + weight[j];
+        const double t = std::ceil(cp * 4294967296.0);
+        thr[j] = t <= 0.0 ? 0ull : (t >= 4294967296.0 ? (1ull << 32) : (unsigned long long)t);
+        if (thr[j] < (1ull << 32)) { thr32[j] = (uint32_t)thr[j]; n_reach = j + 1; }   // non-decreasing: a prefix
+    }
+    auto pick = [&](unsigned long long w) {
+        int k = 0;
+        for (int j = 0; j < nm - 1; ++j) k += (w >= thr[j]) ? 1 : 0;
+        return k;
+    };
+    for (int b = 0; b < kCatBuckets; ++b) {
+        const unsigned long long lo = (unsigned long long)b << 20, hi = lo + ((1ull << 20) - 1);
+        const int k0 = pick(lo), k1 = pick(hi);
+        table[b] = k0 == k1 ? (uint8_t)k0 : (k1 == k0 + 1 ? (uint8_t)(0x80 | k0) : (uint8_t)0xff);
+    }
+    return n_reach;
+}
+
+int32_t ensure_series_partials(arianna_handle *h, size_t n_doubles);
+
 // Grid of the grid-stride kernels: an integer number of FULL resident waves (occupancy API x SM count x kGridWaves).
 // One wave is the worst choice for these kernels: all CTAs start together, their warps run the Philox phase and the
 // FP64 phase in lockstep (bursts of contention on one pipe at a time) and the SM drains unevenly at the end.  With
@@ -222,6 +259,22 @@ int wave_grid(const arianna_handle *h, K kernel, size_t smem, int64_t M)
     int waves = env_waves > 0 ? env_waves : kGridWaves;
     if (waves > kMaxGridWaves) waves = kMaxGridWaves;
     return grid_for(h, M, per_sm * waves);
+}
+
+int32_t ensure_series_partials(arianna_handle *h, size_t n_doubles)
+{
+    if (h->series_partials_cap >= n_doubles) return ARIANNA_OK;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) cudaGetLastError();
+    cudaFree(h->d_series_partials);
+    h->d_series_partials = nullptr;
+    h->series_partials_cap = 0;
+    if (cudaMalloc(&h->d_series_partials, sizeof(double) * n_doubles) != cudaSuccess) {
+        cudaGetLastError();
+        h->err = "series partials allocation failed";
+        return ARIANNA_ERR_NOMEM;
+    }
+    h->series_partials_cap = n_doubles;
+    return ARIANNA_OK;
 }
 
 template <typename F>
@@ -334,6 +387,11 @@ int32_t arianna_create(const arianna_config *cfg, arianna_handle **out)
     if (nm > 1) {
         CU_CREATE(cudaMalloc(&h->d_tot, sizeof(uint32_t) * h->M * nm));
         CU_CREATE(cudaMemsetAsync(h->d_tot, 0, sizeof(uint32_t) * h->M * nm, h->stream));
+        std::vector<uint8_t> table(kCatBuckets);
+        h->cat_n = build_cat_table(h->pool.weight, nm, h->cat_thr, table.data());
+        CU_CREATE(cudaMalloc(&h->d_cat_table, kCatBuckets));
+        CU_CREATE(cudaMemcpyAsync(h->d_cat_table, table.data(), kCatBuckets, cudaMemcpyHostToDevice, h->stream));
+        CU_CREATE(cudaStreamSynchronize(h->stream));
     }
     CU_CREATE(cudaMemsetAsync(h->d_x, 0, sizeof(double) * h->M, h->stream));
     const int max_grid = h->sm_count * 8 * kMaxGridWaves;  // partials of the largest grid wave_grid() can return
@@ -382,7 +440,7 @@ int32_t arianna_destroy(arianna_handle *h)
     cudaFree(h->d_x); cudaFree(h->d_acc); cudaFree(h->d_tot); cudaFree(h->d_betas); cudaFree(h->d_rng);
     cudaFree(h->d_ki); cudaFree(h->d_wi); cudaFree(h->d_fi); cudaFree(h->d_partials); cudaFree(h->d_ticket);
     cudaFree(h->d_sums); cudaFree(h->d_gd); cudaFree(h->d_csum); cudaFree(h->d_scratch); cudaFree(h->d_tables);
-    cudaFree(h->d_series); cudaFree(h->d_series_partials);
+    cudaFree(h->d_series); cudaFree(h->d_series_partials); cudaFree(h->d_cat_table);
     if (h->coll_stream) cudaStreamSynchronize(h->coll_stream);
     if (h->comm) { nccl::g_api.CommDestroy(h->comm); h->comm = nullptr; }
     cudaFree(h->d_coll);
@@ -536,6 +594,68 @@ static int32_t launch_callback_reduce(arianna_handle *h)
     return ARIANNA_OK;
 }
 
+// One launch of the multi-move sweep over chains [off, off + m): n_int intervals of K[i] steps starting at MC step t0,
+// with a callback record after each when `out` != NULL (records go to out[0 .. n_int) x record_stride, added when
+// `accumulate`; the last one is also copied to `sums` when given).  Asynchronous on h->stream.
+static int32_t launch_multi(arianna_handle *h, int64_t off, int64_t m, int64_t t0, int n_int, const int64_t *K,
+                            double *out, double *sums, int accumulate)
+{
+    const bool exact = h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
+    const int nm = h->pool.n_moves;
+    MultiParams mp{};
+    mp.x = h->d_x + off; mp.acc = h->d_acc + off; mp.tot = h->d_tot + off;
+    mp.betas = h->d_betas ? h->d_betas + off : nullptr; mp.beta = h->cfg.beta;
+    // the per-move counter arrays are [n_moves][M] of the WHOLE handle: a slice keeps that row pitch
+    mp.M = m; mp.t0 = t0;
+    mp.sid0 = (uint64_t)(h->cfg.seed + h->cfg.chain_offset + off);
+    mp.tables = h->d_tables;
+    mp.cat_table = h->d_cat_table;
+    for (int j = 0; j < kMaxMoves; ++j) mp.cat_thr[j] = h->cat_thr[j];
+    mp.cat_n = h->cat_n;
+    mp.pool = h->pool;
+    mp.n_int = n_int; mp.record = out ? 1 : 0;
+    bool even = (t0 & 1) == 0;
+    for (int i = 0; i < n_int; ++i) {
+        mp.K[i] = (int)K[i];
+        even = even && K[i] > 0 && (K[i] & 1) == 0;
+    }
+    mp.K[n_int] = 0;
+    mp.even = even ? 1 : 0;
+    mp.pitch = h->M;
+    // two counter buffers (prefetch of the next chain's counters) when that still leaves ARIANNA_MULTI_MINB CTAs per SM
+    mp.dbuf = multi_smem_bytes(nm, n_int, mp.record, 1) + 1024 <= h->smem_per_sm / ARIANNA_MULTI_MINB ? 1 : 0;
+    if (const char *e = getenv("ARIANNA_MULTI_DBUF")) mp.dbuf = atoi(e) ? 1 : 0;
+    const size_t smem = multi_smem_bytes(nm, n_int, mp.record, mp.dbuf);
+    int grid = 0;
+    int32_t rc = dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
+        constexpr int POT = decltype(pot)::value;
+        auto go = [&](auto kernel) -> int32_t {
+            CU_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            grid = wave_grid(h, kernel, smem, m);
+            if (mp.record) {
+                const int32_t r = ensure_series_partials(h, (size_t)grid * n_int * (1 + nm));
+                if (r) return r;
+                mp.partials = h->d_series_partials;
+            }
+            kernel<<<grid, kBlock, smem, h->stream>>>(mp);
+            return ARIANNA_OK;
+        };
+        if (h->d_betas)
+            return exact ? go(sweep_multi_kernel<POT, ARITH_EXACT, true>) : go(sweep_multi_kernel<POT, ARITH_FAST, true>);
+        return exact ? go(sweep_multi_kernel<POT, ARITH_EXACT, false>) : go(sweep_multi_kernel<POT, ARITH_FAST, false>);
+    });
+    if (rc) return rc;
+    CU_TRY(h, cudaGetLastError());
+    ++h->launches;
+    if (mp.record) {
+        series_fold_multi_kernel<<<n_int, kBlock, 0, h->stream>>>(h->d_series_partials, grid, n_int, nm, m, out, sums,
+                                                                 accumulate);
+        CU_TRY(h, cudaGetLastError());
+        ++h->launches;
+    }
+    return ARIANNA_OK;
+}
+
 int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
 {
     if (!h) return ARIANNA_ERR_INVALID;
@@ -549,18 +669,28 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
     const bool exact = h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
     time_mark(h, 0, true);
 
+    if (h->cfg.rng_mode == ARIANNA_RNG_PHILOX && multi) {
+        // multi-move pools: the record (when asked for) is reduced inside the sweep, per move
+        REQUIRE(h, K < (int64_t(1) << 31), "arianna_sweep: K must be < 2^31");
+        const int32_t rc = launch_multi(h, 0, h->M, h->steps_done, 1, &K, want_reduce ? h->d_sums : nullptr, nullptr, 0);
+        if (rc) return rc;
+        h->steps_done += K;
+        h->sums_valid = want_reduce;
+        time_mark(h, 0, false);
+        return ARIANNA_OK;
+    }
     if (h->cfg.rng_mode == ARIANNA_RNG_PHILOX) {
 
         SweepParams sp{};
         sp.x = h->d_x; sp.acc = h->d_acc; sp.tot = h->d_tot; sp.betas = h->d_betas; sp.beta = h->cfg.beta;
         sp.M = h->M; sp.K = K; sp.t0 = h->steps_done;
         sp.sid0 = (uint64_t)(h->cfg.seed + h->cfg.chain_offset);
-        sp.reduce = (want_reduce && !multi) ? 1 : 0;
+        sp.reduce = want_reduce ? 1 : 0;
         sp.partials = h->d_partials; sp.ticket = h->d_ticket; sp.sums = h->d_sums;
         sp.tables = h->d_tables;
         sp.pool = h->pool;
-        // the Philox sweep keeps its math tables in dynamic shared memory too (one pinned base register, kernels.cuh)
-        const size_t psmem = smem + sizeof(m64::MathTables);
+        // the Philox sweep keeps its math tables in dynamic shared memory (one pinned base register, kernels.cuh)
+        const size_t psmem = sizeof(m64::MathTables);
         auto launch = [&](auto kernel) -> int32_t {
             if (psmem > 48 * 1024)
                 CU_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
@@ -570,13 +700,11 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
         const int32_t rc = dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
             constexpr int POT = decltype(pot)::value;
             if (exact) {
-                if (multi) return launch(sweep_philox_kernel<POT, ARITH_EXACT, true>);
-                if (h->d_betas) return launch(sweep_philox_kernel<POT, ARITH_EXACT, false>);
-                return launch(sweep_philox_kernel<POT, ARITH_EXACT, false, false, false>);
+                if (h->d_betas) return launch(sweep_philox_kernel<POT, ARITH_EXACT>);
+                return launch(sweep_philox_kernel<POT, ARITH_EXACT, false, false>);
             }
-            if (multi) return launch(sweep_philox_kernel<POT, ARITH_FAST, true>);
-            if (h->d_betas) return launch(sweep_philox_kernel<POT, ARITH_FAST, false>);
-            return launch(sweep_philox_kernel<POT, ARITH_FAST, false, false, false>);
+            if (h->d_betas) return launch(sweep_philox_kernel<POT, ARITH_FAST>);
+            return launch(sweep_philox_kernel<POT, ARITH_FAST, false, false>);
         });
         if (rc) return rc;
     } else {
@@ -609,7 +737,7 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
     h->sums_valid = false;
     int32_t rc_red = ARIANNA_OK;
     if (want_reduce) {
-        if (!multi && h->cfg.rng_mode == ARIANNA_RNG_PHILOX) h->sums_valid = true;  // fused at the sweep's tail
+        if (h->cfg.rng_mode == ARIANNA_RNG_PHILOX) h->sums_valid = true;  // fused at the sweep's tail
         else rc_red = launch_callback_reduce(h);
     }
     time_mark(h, 0, false);
@@ -625,10 +753,19 @@ static int series_per_launch(const arianna_handle *h)
     const char *e = getenv("ARIANNA_SERIES_PER_LAUNCH");   // test / tuning override
     const int env = e ? atoi(e) : 0;
     if (env > 0) return env < kMaxSeries ? env : kMaxSeries;
+    if (h->pool.n_moves > 1) {
+        // multi-move pools: one warp-accumulator row of (1 + n_moves) doubles per interval and warp; as many intervals
+        // as keep ARIANNA_MULTI_MINB CTAs per SM, at most 32 (the per-CTA partials grow with it)
+        const long budget = (long)(h->smem_per_sm / ARIANNA_MULTI_MINB) - 1024 - (long)multi_smem_bytes(h->pool.n_moves, 0, 0, 1);
+        long n = budget / (long)(kWarpsPerBlock * (1 + h->pool.n_moves) * 8);
+        if (n < 1) n = 1;
+        if (n > 32) n = 32;
+        return (int)n;
+    }
     if (h->M <= (int64_t)kBlock * h->sm_count) return kMaxSeries;
     cudaFuncAttributes fa{};
     size_t stat = 1024;
-    if (cudaFuncGetAttributes(&fa, sweep_philox_kernel<POT_HARMONIC, ARITH_FAST, false, true, false>) == cudaSuccess)
+    if (cudaFuncGetAttributes(&fa, sweep_philox_kernel<POT_HARMONIC, ARITH_FAST, true, false>) == cudaSuccess)
         stat = fa.sharedSizeBytes;
     else
         cudaGetLastError();
@@ -656,8 +793,15 @@ static int32_t series_range(arianna_handle *h, int64_t off, int64_t m, int64_t t
 {
     const bool exact = h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
     const int per_launch = series_per_launch(h);
+    const int stride = record_stride(h);
     for (int32_t s0 = 0; s0 < n_stores; s0 += per_launch) {
         const int ns = n_stores - s0 < per_launch ? n_stores - s0 : per_launch;
+        if (h->pool.n_moves > 1) {
+            const int32_t rc = launch_multi(h, off, m, t0, ns, K + s0, h->d_series + (size_t)stride * s0, h->d_sums, accumulate);
+            if (rc) return rc;
+            for (int i = 0; i < ns; ++i) t0 += K[s0 + i];
+            continue;
+        }
         SweepParams sp{};
         sp.x = h->d_x + off; sp.acc = h->d_acc + off; sp.tot = nullptr;
         sp.betas = h->d_betas ? h->d_betas + off : nullptr; sp.beta = h->cfg.beta;
@@ -666,7 +810,6 @@ static int32_t series_range(arianna_handle *h, int64_t off, int64_t m, int64_t t
         sp.tables = h->d_tables;
         sp.pool = h->pool;
         sp.n_series = ns;
-        sp.series_partials = h->d_series_partials;
         SeriesK sk{};
         int64_t k_launch = 0;
         bool even = (t0 & 1) == 0;
@@ -685,14 +828,17 @@ static int32_t series_range(arianna_handle *h, int64_t off, int64_t m, int64_t t
             auto go = [&](auto kernel) -> int32_t {
                 CU_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 grid = wave_grid(h, kernel, smem, m);
+                const int32_t r = ensure_series_partials(h, (size_t)grid * (ns + 1) * 2);
+                if (r) return r;
+                sp.series_partials = h->d_series_partials;
                 kernel<<<grid, kBlock, smem, h->stream>>>(sp);
                 return ARIANNA_OK;
             };
             if (h->d_betas)
-                return exact ? go(sweep_philox_kernel<POT, ARITH_EXACT, false, true, true>)
-                             : go(sweep_philox_kernel<POT, ARITH_FAST, false, true, true>);
-            return exact ? go(sweep_philox_kernel<POT, ARITH_EXACT, false, true, false>)
-                         : go(sweep_philox_kernel<POT, ARITH_FAST, false, true, false>);
+                return exact ? go(sweep_philox_kernel<POT, ARITH_EXACT, true, true>)
+                             : go(sweep_philox_kernel<POT, ARITH_FAST, true, true>);
+            return exact ? go(sweep_philox_kernel<POT, ARITH_EXACT, true, false>)
+                         : go(sweep_philox_kernel<POT, ARITH_FAST, true, false>);
         });
         if (rc) return rc;
         CU_TRY(h, cudaGetLastError());
@@ -708,9 +854,8 @@ static int32_t series_range(arianna_handle *h, int64_t off, int64_t m, int64_t t
 static int32_t series_prepare(arianna_handle *h, const char *who, int32_t n_stores, const int64_t *K, int64_t *total_out)
 {
     REQUIRE(h, n_stores >= 0 && (n_stores == 0 || K != nullptr), std::string(who) + ": bad arguments");
-    if (h->pool.n_moves != 1 || h->cfg.rng_mode != ARIANNA_RNG_PHILOX)
-        return fail(h, ARIANNA_ERR_UNSUPPORTED,
-                    std::string(who) + ": single-move pools with the native Philox stream only (use arianna_sweep)");
+    if (h->cfg.rng_mode != ARIANNA_RNG_PHILOX)
+        return fail(h, ARIANNA_ERR_UNSUPPORTED, std::string(who) + ": the native Philox stream only (use arianna_sweep)");
     int64_t total = 0;
     for (int32_t i = 0; i < n_stores; ++i) {
         REQUIRE(h, K[i] >= 0 && K[i] < (int64_t(1) << 31), std::string(who) + ": K[i] must be in [0, 2^31)");
@@ -726,12 +871,9 @@ static int32_t series_prepare(arianna_handle *h, const char *who, int32_t n_stor
         h->d_series = nullptr;
         h->series_cap = 0;
         const int64_t cap = n_stores < 1024 ? 1024 : n_stores;
-        CU_TRY(h, cudaMalloc(&h->d_series, sizeof(double) * 3 * cap));
+        CU_TRY(h, cudaMalloc(&h->d_series, sizeof(double) * record_stride(h) * cap));
         h->series_cap = cap;
     }
-    if (!h->d_series_partials)
-        CU_TRY(h, cudaMalloc(&h->d_series_partials,
-                             sizeof(double) * 2 * (kMaxSeries + 1) * (size_t)h->sm_count * 8 * kMaxGridWaves));
     return ARIANNA_OK;
 }
 
@@ -750,7 +892,7 @@ int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t 
     h->series_n = n_stores;
     h->sums_valid = true;   // the last record doubles as the callback sums of the current state
     if (records) {
-        CU_TRY(h, cudaMemcpyAsync(records, h->d_series, sizeof(double) * 3 * n_stores, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(records, h->d_series, sizeof(double) * record_stride(h) * n_stores, cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(h, cudaStreamSynchronize(h->stream));
     }
     return ARIANNA_OK;
@@ -841,7 +983,7 @@ int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_st
     h->series_n = n_stores;
     h->sums_valid = n_stores > 0;
     if (records && n_stores > 0)
-        JOB_TRY(cudaMemcpyAsync(records, h->d_series, sizeof(double) * 3 * n_stores, cudaMemcpyDeviceToHost, h->stream));
+        JOB_TRY(cudaMemcpyAsync(records, h->d_series, sizeof(double) * record_stride(h) * n_stores, cudaMemcpyDeviceToHost, h->stream));
     JOB_TRY(cudaEventRecord(h->ev_copy, h->copy_stream));
     JOB_TRY(cudaStreamSynchronize(h->stream));
     JOB_TRY(cudaStreamSynchronize(h->copy_stream));
@@ -875,7 +1017,7 @@ int32_t arianna_series_device(arianna_handle *h, double **dptr, int32_t *n_doubl
     if (!h) return ARIANNA_ERR_INVALID;
     REQUIRE(h, dptr && n_doubles, "arianna_series_device: NULL output");
     *dptr = h->d_series;
-    *n_doubles = (int32_t)(3 * h->series_n);
+    *n_doubles = (int32_t)(record_stride(h) * h->series_n);
     return ARIANNA_OK;
 }
 
@@ -1107,9 +1249,9 @@ int32_t arianna_series_global(arianna_handle *h, int32_t n_stores, double *recor
     DeviceGuard guard(h->device);
     // in place on the series buffer: ONE all-reduce for the whole stretch of the schedule
     if (h->comm)
-        NCCL_TRY(h, nccl::g_api.AllReduce(h->d_series, h->d_series, (size_t)3 * n_stores, /*ncclDouble*/ 8,
+        NCCL_TRY(h, nccl::g_api.AllReduce(h->d_series, h->d_series, (size_t)record_stride(h) * n_stores, /*ncclDouble*/ 8,
                                           /*ncclSum*/ 0, h->comm, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(records, h->d_series, sizeof(double) * 3 * n_stores, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(records, h->d_series, sizeof(double) * record_stride(h) * n_stores, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return ARIANNA_OK;
 }
@@ -1137,10 +1279,10 @@ int32_t arianna_series_global_begin(arianna_handle *h, int32_t n_stores, double 
         cudaFree(h->d_coll_series);
         h->d_coll_series = nullptr;
         h->coll_series_cap = 0;
-        CU_TRY(h, cudaMalloc(&h->d_coll_series, sizeof(double) * 3 * h->series_cap));
+        CU_TRY(h, cudaMalloc(&h->d_coll_series, sizeof(double) * record_stride(h) * h->series_cap));
         h->coll_series_cap = h->series_cap;
     }
-    const size_t n = (size_t)3 * n_stores;
+    const size_t n = (size_t)record_stride(h) * n_stores;
     CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_coll_done, 0));     // the previous operation has left the snapshot
     CU_TRY(h, cudaMemcpyAsync(h->d_coll_series, h->d_series, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
     CU_TRY(h, cudaEventRecord(h->ev_coll_src, h->stream));

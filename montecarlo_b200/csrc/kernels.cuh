@@ -293,8 +293,7 @@ __device__ __forceinline__ void block_reduce_and_finish(const double *vals, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K1: fused sweep, native Philox.  MULTI = pool with more than one move (categorical pick, per-move counters in
-// shared memory so that the dynamically indexed counters never spill to local memory).
+// K1: fused sweep, native Philox, single-move pools (multi-move pools: sweep_multi_kernel below).
 // ---------------------------------------------------------------------------------------------------------
 //
 // SERIES (single-move pools): the launch covers n_series consecutive store intervals.  The chain stays in registers
@@ -303,23 +302,13 @@ __device__ __forceinline__ void block_reduce_and_finish(const double *vals, int 
 // interval as u32 -- then block-reduced once at the end of the launch into series_partials; series_fold_kernel
 // turns the partials into one [Σe, Σacc/t, count] record per store.  No host round trip and no second launch per
 // store: StoreCallbacks at every 10th step costs the same as one K = 10·n_series sweep.
-template <int POT, int ARITH, bool MULTI, bool SERIES = false, bool BETAS = true>
+template <int POT, int ARITH, bool SERIES = false, bool BETAS = true>
 __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(const SweepParams p)
 {
-    static_assert(!(MULTI && SERIES), "series mode is implemented for single-move pools");
     // dynamic shared memory: [MathTables][kernel-specific arrays] -- ONE symbol, so one pinned base register serves
     // the math tables and the series accumulators alike
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr uint32_t kTabBytes = (uint32_t)sizeof(m64::MathTables);
-    // MULTI: [n_moves][kBlock] acc, [n_moves][kBlock] tot (u32)
-    uint32_t *s_acc = reinterpret_cast<uint32_t *>(smem_raw + kTabBytes);
-    uint32_t *s_tot = s_acc + (MULTI ? p.pool.n_moves * kBlock : 0);
-    __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves];
-    if (threadIdx.x < kMaxMoves) {
-        s_sigma[threadIdx.x] = p.pool.sigma[threadIdx.x];
-        s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
-        s_lognorm[threadIdx.x] = p.pool.lognorm[threadIdx.x];
-    }
     load_tables(reinterpret_cast<m64::MathTables *>(smem_raw), p.tables);
     __syncthreads();
     const m64::Tab tb = shared_tab(smem_raw);
@@ -335,7 +324,6 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         sts_u64(a_base, 0ull);
     }
 
-    const int nm = p.pool.n_moves;
     const int64_t tend = p.t0 + p.K;
     double sum_e = 0.0;
     unsigned long long sum_acc = 0ull;   // Σ accepted_calls: exact in integers; every chain shares tot = tend
@@ -353,7 +341,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
     // are worth more to the loop body)
     constexpr bool PREFETCH = !SERIES;
     double x_next = (PREFETCH && c < p.M) ? p.x[c] : 0.0;
-    uint32_t acc_next = (PREFETCH && !MULTI && c < p.M) ? p.acc[c] : 0u;
+    uint32_t acc_next = (PREFETCH && c < p.M) ? p.acc[c] : 0u;
     for (; c < p.M; c += stride) {
         double x;
         uint32_t acc;
@@ -362,26 +350,19 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
             acc = acc_next;
             if (c + stride < p.M) {
                 x_next = p.x[c + stride];
-                if constexpr (!MULTI) acc_next = p.acc[c + stride];
+                acc_next = p.acc[c + stride];
             }
         } else {
             x = p.x[c];
-            acc = MULTI ? 0u : p.acc[c];
+            acc = p.acc[c];
         }
         double e = potential<POT, ARITH>(x);
         // BETAS = false: β is a kernel-parameter constant (a constant-bank operand, no registers)
         const double beta = BETAS ? (p.betas ? p.betas[c] : p.beta) : p.beta;
         const uint64_t sid = p.sid0 + (uint64_t)c;
-        if constexpr (MULTI) {
-            for (int k = 0; k < nm; ++k) {
-                s_acc[k * kBlock + threadIdx.x] = p.acc[(size_t)k * p.M + c];
-                s_tot[k * kBlock + threadIdx.x] = p.tot[(size_t)k * p.M + c];
-            }
-        }
 
         // chain-only halves of the first three Philox rounds (rng.cuh); the rare refinement block is generated unhoisted
         const PhiloxChain<kTagMetropolis, 0> ph(sid);
-        const PhiloxChain<kTagMetropolis, MULTI ? 2 : 0> ph_cat(sid);   // (unused -> eliminated when !MULTI)
         // Draws of one pair of steps (a pure function of the pair index, independent of the chain state).
         // ONE Philox block feeds the pair: words B0/B1 give the two 53-bit Box-Muller uniforms (top 53 bits) and,
         // in their low 11 bits, the PREFIXES of the two accept uniforms.  The remaining 42 bits of an accept
@@ -390,7 +371,6 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
             double z0, z1;
             uint32_t f0, f1;   // 12-bit / 11-bit prefixes of u_acc(2p), u_acc(2p+1)
             uint64_t pr;
-            U64Pair b2;        // categorical uniforms (multi-move pools)
         };
         auto gen_pair = [&](uint64_t pr) {
             PairDraws d;
@@ -399,8 +379,6 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
             d.f0 = b0.a_lo & 0xfffu;   // 12 bits: the radius uniform takes A >> 12
             d.f1 = b0.b_lo & 0x7ffu;
             d.pr = pr;
-            d.b2 = U64Pair{};
-            if constexpr (MULTI) d.b2 = ph_cat.block((uint32_t)pr);
             return d;
         };
         // the two (state-dependent, serial) Metropolis steps of a pair; DO0 / DO1 are compile-time
@@ -411,16 +389,8 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                     return m64::u53_prefix_refine<12>(d.f0, r.a_lo, r.a_hi);
                 };
                 const CellP<12> ulo{d.f0};
-                if constexpr (MULTI) {
-                    const int k = categorical(nm, s_weight, u53(d.b2.a_lo, d.b2.a_hi));
-                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z0, ulo,
-                                                       exact_u, tb);
-                    if (a) s_acc[k * kBlock + threadIdx.x] += 1;
-                    s_tot[k * kBlock + threadIdx.x] += 1;
-                } else {
-                    const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, ulo, exact_u, tb);
-                    count_if(acc, a);
-                }
+                const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, ulo, exact_u, tb);
+                count_if(acc, a);
             }
             if constexpr (decltype(do1)::value) {
                 auto exact_u = [&]() {
@@ -428,16 +398,8 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                     return m64::u53_prefix_refine<11>(d.f1, r.b_lo, r.b_hi);
                 };
                 const CellP<11> ulo{d.f1};
-                if constexpr (MULTI) {
-                    const int k = categorical(nm, s_weight, u53(d.b2.b_lo, d.b2.b_hi));
-                    const bool a = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], d.z1, ulo,
-                                                       exact_u, tb);
-                    if (a) s_acc[k * kBlock + threadIdx.x] += 1;
-                    s_tot[k * kBlock + threadIdx.x] += 1;
-                } else {
-                    const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, ulo, exact_u, tb);
-                    count_if(acc, a);
-                }
+                const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, ulo, exact_u, tb);
+                count_if(acc, a);
             }
         };
         using T_ = std::true_type;
@@ -506,18 +468,11 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         }
 
         p.x[c] = x;
-        if constexpr (MULTI) {
-            for (int k = 0; k < nm; ++k) {
-                p.acc[(size_t)k * p.M + c] = s_acc[k * kBlock + threadIdx.x];
-                p.tot[(size_t)k * p.M + c] = s_tot[k * kBlock + threadIdx.x];
-            }
-        } else {
-            p.acc[c] = acc;
-            if (p.reduce) {
-                sum_e += potential<POT, ARITH>(x);   // callback_energy: Σ system.e, e == potential(x) always
-                sum_acc += acc;      // callback_acceptance: Σ_c acc_c/tot with tot == tend for every chain
-                ++cnt;
-            }
+        p.acc[c] = acc;
+        if (p.reduce) {
+            sum_e += potential<POT, ARITH>(x);   // callback_energy: Σ system.e, e == potential(x) always
+            sum_acc += acc;      // callback_acceptance: Σ_c acc_c/tot with tot == tend for every chain
+            ++cnt;
         }
     }
 
@@ -549,13 +504,11 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         }
         return;
     }
-    if constexpr (!MULTI) {
-        if (p.reduce) {
-            // Σ acc_c / tot == (Σ acc_c) / tot exactly in real arithmetic; the integer sum is exact in binary64 (< 2^53)
-            // and ONE division replaces a DDIV per chain.  0/0 = NaN at t = 0, like the reference's store_first record.
-            double vals[3] = {sum_e, (double)sum_acc / (double)tend, (double)cnt};
-            block_reduce_and_finish<3>(vals, 3, p.partials, p.ticket, p.sums, false);
-        }
+    if (p.reduce) {
+        // Σ acc_c / tot == (Σ acc_c) / tot exactly in real arithmetic; the integer sum is exact in binary64 (< 2^53)
+        // and ONE division replaces a DDIV per chain.  0/0 = NaN at t = 0, like the reference's store_first record.
+        double vals[3] = {sum_e, (double)sum_acc / (double)tend, (double)cnt};
+        block_reduce_and_finish<3>(vals, 3, p.partials, p.ticket, p.sums, false);
     }
 }
 
@@ -1048,3 +1001,5 @@ __global__ void __launch_bounds__(kBlock) dfma_peak_kernel(double *out, int iter
 }
 
 }  // namespace arianna
+
+#include "kernels_multi.cuh"

@@ -150,10 +150,10 @@ class CudaEnsemble:
 
     def sweep_series(self, Ks: Sequence[int], read: bool = True):
         """len(Ks) consecutive store intervals of Ks[i] mc steps, the callback record taken after each ON THE DEVICE
-        (arianna_sweep_series).  read=True returns the local-shard records [n][3] = (Σe, Σ acc/tot, count);
-        read=False leaves them on the device (series_tensor / series_global)."""
+        (arianna_sweep_series).  read=True returns the local-shard records [n][2 + n_moves] = (Σe, Σ acc/tot per move,
+        count); read=False leaves them on the device (series_tensor / series_global)."""
         ks = np.ascontiguousarray(Ks, dtype=np.int64)
-        rec = np.empty((ks.size, 3), dtype=np.float64) if read else None
+        rec = np.empty((ks.size, 2 + self.n_moves), dtype=np.float64) if read else None
         self._ck(self._lib.arianna_sweep_series(self._h, int(ks.size), ks.ctypes.data_as(C.POINTER(C.c_int64)),
                                                 _ptr(rec)))
         return rec
@@ -163,7 +163,7 @@ class CudaEnsemble:
         (arianna_run_host_job): chains in, len(Ks) store intervals, records out, chains out.  x_in / x_out: numpy
         arrays or raw pointers of page-locked host memory ([n_chains] f64), or None."""
         ks = np.ascontiguousarray(Ks, dtype=np.int64)
-        rec = np.empty((ks.size, 3), dtype=np.float64) if read else None
+        rec = np.empty((ks.size, 2 + self.n_moves), dtype=np.float64) if read else None
 
         def ptr(a):
             if a is None:
@@ -199,7 +199,7 @@ class CudaEnsemble:
 
     def series_global(self, n_stores: int):
         """Records of the last sweep_series call all-reduced inside the library (arianna_comm_init)."""
-        rec = np.empty((int(n_stores), 3), dtype=np.float64)
+        rec = np.empty((int(n_stores), 2 + self.n_moves), dtype=np.float64)
         self._ck(self._lib.arianna_series_global(self._h, int(n_stores), _ptr(rec)))
         return rec
 

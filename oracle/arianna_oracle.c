@@ -110,7 +110,9 @@ AO_API void ao_init_synthetic(int64_t seed, int64_t chain_offset, int64_t M, dou
  *                     sub-block 1: A>>23 -> 41 refinement bits of u_acc(2p), B>>22 -> 42 of u_acc(2p+1)
  *                                 u_acc = ((prefix << (53 - bits)) | refinement) * 2^-53   (the engine only generates
  *                                 this block when its FP32 filter cannot decide from the prefix alone)
- *                     sub-block 2: A -> u_cat(2p), B -> u_cat(2p+1)      (only consumed when n_moves > 1)
+ *   quad q = t >> 2:  block (q, sub-block 2): its four 32-bit output words w0..w3 are the categorical uniforms of
+ *                                 steps 4q .. 4q+3:  u_cat(t) = w[t & 3] * 2^-32   (only consumed when n_moves > 1; one
+ *                                 block serves four steps -- layout v4)
  *   z(2p) = r cos(2π u2), z(2p+1) = r sin(2π u2).
  * u_cat may be NULL (single-move pools do not consume it in native mode). */
 AO_API void ao_draws_philox(int64_t seed, int64_t chain_offset, int64_t M, int64_t t0, int64_t K,
@@ -135,8 +137,10 @@ AO_API void ao_draws_philox(int64_t seed, int64_t chain_offset, int64_t M, int64
             u_acc[s * M + c] = (double)((prefix << (odd ? 42 : 41)) | refine) * 0x1.0p-53;
             if (u_cat) {
                 uint64_t A2, B2;
-                philox_block(sid, p, 2, AO_TAG_METROPOLIS, &A2, &B2);
-                u_cat[s * M + c] = u53(odd ? B2 : A2);
+                philox_block(sid, t >> 2, 2, AO_TAG_METROPOLIS, &A2, &B2);
+                uint64_t half = (t & 2) ? B2 : A2;                       /* words (w0, w1) = A, (w2, w3) = B */
+                uint32_t w = (t & 1) ? (uint32_t)(half >> 32) : (uint32_t)half;
+                u_cat[s * M + c] = (double)w * 0x1.0p-32;
             }
         }
     }

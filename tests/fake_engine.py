@@ -58,10 +58,8 @@ class OracleEngine:
 
     def sweep_series(self, Ks, read=True):
         """arianna_sweep_series: len(Ks) store intervals in ONE call (counted as one launch), a record after each."""
-        if self.n_moves != 1:
-            raise RuntimeError("sweep_series: single-move pools only")
         n0 = self.launch_count
-        rec = np.empty((len(Ks), 3))
+        rec = np.empty((len(Ks), 2 + self.n_moves))
         for i, K in enumerate(Ks):
             self.sweep(int(K))
             rec[i] = self.callback_sums()

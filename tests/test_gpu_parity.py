@@ -317,6 +317,91 @@ def test_series_equals_per_store_sweeps(arith, per_launch, even, monkeypatch):
         np.testing.assert_allclose(a.series_global(2), np.stack([s1, s2]), rtol=1e-13)
 
 
+@pytest.mark.parametrize("arith", ["exact", "fast"])
+@pytest.mark.parametrize("even", [False, True])
+@pytest.mark.parametrize("sigma,weight", [([0.2] * 7, [0.4] + [0.1] * 6), ([0.1, 0.3, 0.9], [0.5, 0.25, 0.25])])
+def test_series_multi_move_pools(arith, even, sigma, weight, monkeypatch):
+    """Series mode for multi-move pools: the record of every store carries callback_acceptance as the reference defines
+    it -- one entry PER MOVE, the mean over chains of accepted_calls/total_calls, NaN while some chain never tried the
+    move (metropolis.jl:319-321) -- and equals the standalone reduction over the same state and the oracle's callbacks;
+    chains and per-move counters are bit-identical to the per-store sweeps.  C4's pool is the 7-move case
+    (pgmc_test.jl:17-25)."""
+    monkeypatch.setenv("ARIANNA_SERIES_PER_LAUNCH", "5")
+    M, seed, nm = 30011, 13, len(sigma)
+    Ks = [1, 10, 7, 0, 10, 3, 12, 1, 0, 4, 10, 9]
+    pre = 3
+    if even:
+        Ks, pre = [2, 10, 8, 4, 10, 6, 12, 2, 2, 4, 10, 8], 2
+    x0 = O.init_synthetic(seed, 0, M)
+    ref = O.Ensemble(x0, 2.0, sigma, weight)
+    with mb.CudaEnsemble(M, 2.0, sigma, weight, seed=seed, arith=arith) as a, \
+            mb.CudaEnsemble(M, 2.0, sigma, weight, seed=seed, arith=arith) as b:
+        a.init_synthetic(); b.init_synthetic()
+        a.sweep(pre); b.sweep(pre)
+        rec = a.sweep_series(Ks)
+        assert rec.shape == (len(Ks), 2 + nm) and a.steps_done == pre + sum(Ks)
+        uc, z, ua = O.draws_philox(seed, 0, M, 0, pre)
+        ref.sweep_replay(uc, z, ua)
+        done = pre
+        for i, K in enumerate(Ks):
+            b.sweep(K, reduce=True)                                 # fused per-move record of ONE interval
+            sb = b.callback_sums()
+            np.testing.assert_allclose(rec[i], sb, rtol=1e-13, equal_nan=True, err_msg=f"store {i}")
+            if K:
+                uc, z, ua = O.draws_philox(seed, 0, M, done, K)
+                ref.sweep_replay(uc, z, ua)
+                done += K
+            assert rec[i, -1] == M
+            assert abs(rec[i, 0] / M / ref.callback_energy() - 1) < 1e-12
+            np.testing.assert_allclose(rec[i, 1:-1] / M, ref.callback_acceptance(), rtol=1e-12, equal_nan=True)
+        # early stores: some chain has not tried every move yet -> NaN entries, exactly like the reference's mean
+        assert np.isnan(rec[0, 1:-1]).any()
+        assert np.array_equal(a.get_state(), b.get_state())
+        for u, v in zip(a.chain_counters(), b.chain_counters()):
+            assert np.array_equal(u, v)
+        acc, tot = a.chain_counters()
+        assert np.max(np.abs(a.get_state() - ref.x)) < 1e-12
+        assert np.array_equal(acc.astype(np.int64), ref.acc) and np.array_equal(tot.astype(np.int64), ref.tot)
+        # the last record doubles as the current callback sums; the standalone reduction agrees
+        np.testing.assert_array_equal(a.callback_sums(), rec[-1])
+        a.sweep(0, reduce=True)
+        np.testing.assert_allclose(a.callback_sums(), rec[-1], rtol=1e-13)
+        me, ma = a.callbacks()
+        np.testing.assert_allclose(ma, ref.callback_acceptance(), rtol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("weight", [[0.1234567, 0.3, 0.0765433, 0.5],        # thresholds off the bucket grid
+                                    [0.5, 1e-5, 2e-5, 0.49997],              # two thresholds inside ONE bucket
+                                    [0.25, 0.25, 0.5, 0.0]])                 # on bucket edges; a move that is never picked
+def test_multi_move_host_job_and_pick_table(weight):
+    """The pipelined host job for a multi-move pool (slices keep the row pitch of the per-move counter arrays), and the
+    categorical pick: thresholds that fall inside a bucket of the 4096-entry table take the exact-compare paths."""
+    import torch
+    M, seed = 50021, 4
+    sigma = [0.1, 0.2, 0.4, 0.8]
+    Ks = [10, 10, 5, 10]
+    x0 = O.init_synthetic(seed, 0, M)
+    xin = torch.from_numpy(x0.copy()).pin_memory()
+    xout = torch.empty(M, dtype=torch.float64).pin_memory()
+    ref = O.Ensemble(x0, 2.0, sigma, weight)
+    uc, z, ua = O.draws_philox(seed, 0, M, 0, sum(Ks))
+    _, mov, _ = ref.sweep_replay(uc, z, ua, want_decisions=True)
+    with mb.CudaEnsemble(M, 2.0, sigma, weight, seed=seed) as a, mb.CudaEnsemble(M, 2.0, sigma, weight, seed=seed) as b:
+        b.set_state(x0)
+        rec_b = b.sweep_series(Ks)
+        rec_a = a.run_host_job(Ks, x_in=xin.data_ptr(), x_out=xout.data_ptr(), n_slices=3)
+        np.testing.assert_allclose(rec_a, rec_b, rtol=1e-13)
+        assert np.array_equal(xout.numpy(), b.get_state())
+        for u, v in zip(a.chain_counters(), b.chain_counters()):
+            assert np.array_equal(u, v)
+        acc, tot = a.chain_counters()
+        # tot is the histogram of the picked moves: identical to the oracle's scan over the same 32-bit uniforms
+        assert np.array_equal(tot.astype(np.int64), ref.tot) and np.array_equal(acc.astype(np.int64), ref.acc)
+        assert np.array_equal(tot.sum(axis=0), np.full(M, sum(Ks)))
+    frac = np.bincount(mov.ravel(), minlength=4) / mov.size
+    assert np.max(np.abs(frac - np.array(weight))) < 5 * np.sqrt(0.25 / mov.size)
+
+
 @pytest.mark.parametrize("n_slices", [1, 3, 8])
 def test_host_job_pipelined_over_slices(n_slices):
     """arianna_run_host_job == set_state + sweep_series + get_state: chains and counters bit-identical (chains are
@@ -417,7 +502,7 @@ def test_c_host_example(tmp_path):
 
 
 def test_series_small_ensemble_and_errors():
-    """M = 10 (BASELINE config 1's width): up to ARIANNA_MAX_SERIES stores per launch; multi-move pools refuse."""
+    """M = 10 (BASELINE config 1's width): up to ARIANNA_MAX_SERIES stores per launch; the XOSHIRO generator refuses."""
     M, seed = 10, 42
     x0 = O.init_synthetic(seed, 0, M)
     ref = O.Ensemble(x0, 2.0, [0.1])
@@ -441,6 +526,8 @@ def test_series_small_ensemble_and_errors():
             eng.run_host_job([10], n_slices=0)
         assert eng.run_host_job([], n_slices=2).shape == (0, 3)      # nothing to do is not an error
     with mb.CudaEnsemble(M, 2.0, [0.1, 0.2], seed=seed) as eng:
+        assert eng.sweep_series([10]).shape == (1, 4)               # multi-move pools: per-move records
+    with mb.CudaEnsemble(M, 2.0, [0.1], seed=seed, rng="xoshiro") as eng:
         with pytest.raises(mb.AriannaError) as ei:
             eng.sweep_series([10])
         assert ei.value.code == 4                                   # ARIANNA_ERR_UNSUPPORTED
