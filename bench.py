@@ -377,6 +377,14 @@ def run_ours(args):
                 ids = [mb.CudaEnsemble.nccl_unique_id() if rank == 0 else None]
                 dist.broadcast_object_list(ids, src=0)
                 eng.comm_init(ids[0], rank, world)
+            # W untimed warm-up store intervals through the SAME route: the first host job creates the copy streams and
+            # events, the first in-library all-reduce connects the NCCL communicator (about a second)
+            if main["g_max"] == 1:
+                eng.sweep(S, reduce=True)
+                _ = eng.callbacks_global() if world > 1 else eng.callback_sums()
+            else:
+                eng.run_host_job([S] * W, x_in=x_in.data_ptr(), x_out=x_out.data_ptr(), n_slices=args.slices, read=False)
+                _ = eng.series_global(W)
             barrier()
             barrier()
             t0 = time.perf_counter()
