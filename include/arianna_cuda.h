@@ -116,8 +116,11 @@ ARIANNA_API int32_t arianna_init_synthetic(arianna_handle *h, int64_t seed);
 ARIANNA_API int32_t arianna_get_state(arianna_handle *h, double *x, double *e);
 /* Asynchronous variant for StoreTrajectories at scale (algorithms.jl:198-203): snapshots x on the device and
  * drains the snapshot into caller-pinned memory on a second stream, so the PCIe transfer overlaps the next sweep;
- * arianna_synchronize() completes it. */
+ * arianna_copy_wait() / arianna_synchronize() complete it. */
 ARIANNA_API int32_t arianna_get_state_async(arianna_handle *h, double *x_pinned);
+/* Waits for the LAST arianna_get_state_async frame only (not for sweeps queued after it): the host writes frame i to
+ * disk while sweep i + 1 runs. */
+ARIANNA_API int32_t arianna_copy_wait(arianna_handle *h);
 ARIANNA_API int32_t arianna_set_beta(arianna_handle *h, double beta);
 ARIANNA_API int32_t arianna_set_betas(arianna_handle *h, const double *betas); /* per-chain β, [n_chains] host */
 

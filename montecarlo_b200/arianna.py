@@ -500,8 +500,10 @@ class StoreTrajectories(AriannaAlgorithm):
 
     The reference writes one text file per chain ("$t $(x)" per line, particle_1d.jl:63-66), which cannot scale
     to 2^26 chains.  Here every rank appends (t, x[n_local]) frames to ONE binary file
-    `trajectories/rank<r>.bin` (int64 t, then n_local float64) through an asynchronous D2H copy into pinned
-    memory; for ensembles of at most `text_limit` chains the reference's per-chain text layout
+    `trajectories/rank<r>.bin` (int64 t, then n_local float64).  A frame leaves the GPU through
+    arianna_get_state_async -- a device-side snapshot drained into one of two page-locked host buffers on the copy
+    stream -- and is written to disk at the NEXT store (or in finalise), i.e. while the following sweep already runs.
+    For ensembles of at most `text_limit` chains the reference's per-chain text layout
     `trajectories/<c>/trajectory.dat` is ALSO produced so reference post-processing scripts keep working."""
 
     def __init__(self, chains, *, path=None, fmt=None, store_first: bool = True, store_last: bool = False,
@@ -520,6 +522,7 @@ class StoreTrajectories(AriannaAlgorithm):
                 os.makedirs(d, exist_ok=True)
                 self.text_paths.append(os.path.join(d, "trajectory" + self.fmt.extension))
         self.frames = 0
+        self._bufs, self._pending, self._cur = None, None, 0
 
     def initialise(self, simulation):
         self.bin = open(self.bin_path, "wb")
@@ -527,21 +530,45 @@ class StoreTrajectories(AriannaAlgorithm):
         if self.store_first:
             self.make_step(simulation)
 
-    def make_step(self, simulation):
-        x = simulation.chains.x                                  # flushes pending steps; D2H of the shard
-        self.bin.write(np.int64(simulation.t).tobytes())
+    def _write(self, t, x):
+        self.bin.write(np.int64(t).tobytes())
         self.bin.write(x.tobytes())
         self.frames += 1
         for f, v in zip(self.text_files, x):
-            f.write(f"{simulation.t} {_jl(float(v))}\n")        # store_trajectory, particle_1d.jl:63-66
+            f.write(f"{t} {_jl(float(v))}\n")                   # store_trajectory, particle_1d.jl:63-66
             f.flush()
+
+    def _drain(self, engine):
+        if self._pending is not None:
+            t, i = self._pending
+            engine.copy_wait()                                   # that frame only, not the sweep queued after it
+            self._write(t, self._bufs[i].numpy())
+            self._pending = None
+
+    def make_step(self, simulation):
+        ch = simulation.chains
+        eng = ch.engine
+        if not hasattr(eng, "get_state_async"):                  # test doubles: plain synchronous read
+            self._write(simulation.t, ch.x)
+            return
+        ch.flush()                                               # launches the pending sweep (asynchronous) ...
+        self._drain(eng)                                         # ... and writes the previous frame while it runs
+        if self._bufs is None:
+            import torch
+            self._bufs = [torch.empty(self.n_local, dtype=torch.float64).pin_memory() for _ in range(2)]
+        eng.get_state_async(self._bufs[self._cur].data_ptr())
+        self._pending = (simulation.t, self._cur)
+        self._cur ^= 1
 
     def finalise(self, simulation):
         if self.store_last:
             self.make_step(simulation)
+        if self._pending is not None:
+            self._drain(simulation.chains.engine)
         self.bin.close()
         for f in self.text_files:
             f.close()
+        self._bufs = None
 
     @staticmethod
     def read_binary(path: str, n_local: int):

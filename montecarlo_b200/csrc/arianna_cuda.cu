@@ -541,6 +541,15 @@ int32_t arianna_get_state_async(arianna_handle *h, double *x_pinned)
     return ARIANNA_OK;
 }
 
+int32_t arianna_copy_wait(arianna_handle *h)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    if (!h->copy_stream) return ARIANNA_OK;
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaEventSynchronize(h->ev_copy));
+    return ARIANNA_OK;
+}
+
 int32_t arianna_set_beta(arianna_handle *h, double beta)
 {
     if (!h) return ARIANNA_ERR_INVALID;

@@ -114,6 +114,10 @@ class CudaEnsemble:
     def get_state_async(self, x_pinned_ptr: int):
         self._ck(self._lib.arianna_get_state_async(self._h, C.c_void_p(x_pinned_ptr)))
 
+    def copy_wait(self):
+        """Wait for the last get_state_async frame only (arianna_copy_wait)."""
+        self._ck(self._lib.arianna_copy_wait(self._h))
+
     def set_state_from_ptr(self, host_ptr: int):
         """set_state from a raw (e.g. pinned) host pointer holding n_chains float64."""
         self._ck(self._lib.arianna_set_state(self._h, C.c_void_p(host_ptr)))
