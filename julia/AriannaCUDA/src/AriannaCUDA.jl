@@ -74,23 +74,34 @@ mutable struct CudaEnsemble{T<:AbstractFloat} <: AriannaSystem
     # look-ahead over callback-only stores (plan!): MC steps already executed beyond the driver's time, the records
     # of the stores inside that stretch keyed by "MC steps done", and the planner closure installed by plan!
     ahead::Int
-    series::Dict{Int,Tuple{Float64,Float64}}
+    series::Dict{Int,Tuple{Float64,Vector{Float64}}}
     lookahead::Any
 end
 
 function CudaEnsemble(x0::Vector{Float64}, β::Float64, pool; seed::Int=1, potential::Symbol=:harmonic,
-                      arith::Symbol=:fast, chain_offset::Int=0, n_total::Int=length(x0), device::Int=-1)
+                      arith::Symbol=:fast, rng::Symbol=:philox, chain_offset::Int=0, n_total::Int=length(x0),
+                      device::Int=-1)
     nm = length(pool)
     nm <= MAX_MOVES || throw(ArgumentError("at most $MAX_MOVES moves per pool"))
     pad(v) = ntuple(k -> k <= nm ? Float64(v[k]) : 0.0, MAX_MOVES)
     cfg = AriannaConfig(UInt32(sizeof(AriannaConfig)), Int32(device), length(x0), chain_offset, n_total, seed, β,
                         POT[potential], Int32(nm), pad([m.parameters.σ for m in pool]), pad([m.weight for m in pool]),
-                        Int32(0), Int32(arith == :exact ? 0 : 1), C_NULL)
+                        Int32(rng == :xoshiro ? 1 : 0), Int32(arith == :exact ? 0 : 1), C_NULL)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(C_NULL, ccall((:arianna_create, libarianna[]), Int32, (Ref{AriannaConfig}, Ref{Ptr{Cvoid}}), cfg, h))
     ens = CudaEnsemble{Float64}(h[], length(x0), β, pool, 0, -1, NaN, fill(NaN, nm), 0,
-                                Dict{Int,Tuple{Float64,Float64}}(), nothing)
+                                Dict{Int,Tuple{Float64,Vector{Float64}}}(), nothing)
     check(ens.handle, ccall((:arianna_set_state, libarianna[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), ens.handle, x0))
+    if rng == :xoshiro
+        # the reference's own generators, rngs = [Xoshiro(seed + c - 1) for c in 1:M] (metropolis.jl:262-263), run on the
+        # device: upload their states (xoshiro256++ s0..s3); the ziggurat tables default to the engine's own
+        states = Matrix{UInt64}(undef, 4, length(x0))
+        for c in 1:length(x0)
+            r = Xoshiro(seed + chain_offset + c - 1)
+            states[1, c], states[2, c], states[3, c], states[4, c] = r.s0, r.s1, r.s2, r.s3
+        end
+        check(ens.handle, ccall((:arianna_set_rng_state, libarianna[]), Int32, (Ptr{Cvoid}, Ptr{UInt64}), ens.handle, states))
+    end
     finalizer(e -> ccall((:arianna_destroy, libarianna[]), Int32, (Ptr{Cvoid},), e.handle), ens)
     return ens
 end
@@ -173,17 +184,17 @@ function plan!(simulation::Simulation)
 end
 
 """
-    run_host_job!(ens, x_in, Ks; x_out=nothing, n_slices=8) -> records::Matrix{Float64} (3 × length(Ks))
+    run_host_job!(ens, x_in, Ks; x_out=nothing, n_slices=16) -> records::Matrix{Float64} ((2 + nmoves) × length(Ks))
 
 A whole callbacks-only job with host buffers in one call (arianna_run_host_job): chains in, `length(Ks)` store
-intervals of `Ks[i]` Metropolis steps, `(Σe, Σacc/tot, count)` per store out, final chains out; the library pipelines
+intervals of `Ks[i]` Metropolis steps, `(Σe, Σacc/tot per move, count)` per store out, final chains out; the library pipelines
 slices of chains so that the PCIe copies overlap the sweeps.  With a communicator the records are all-reduced.
 """
 function run_host_job!(ens::CudaEnsemble, x_in::Union{Nothing,Vector{Float64}}, Ks::Vector{Int64};
-                       x_out::Union{Nothing,Vector{Float64}}=nothing, n_slices::Int=8)
+                       x_out::Union{Nothing,Vector{Float64}}=nothing, n_slices::Int=16)
     flush!(ens)
     n = length(Ks)
-    rec = Matrix{Float64}(undef, 3, n)
+    rec = Matrix{Float64}(undef, 2 + length(ens.pool), n)
     check(ens.handle, ccall((:arianna_run_host_job, libarianna[]), Int32,
                             (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Int32), ens.handle,
                             x_in === nothing ? C_NULL : pointer(x_in), n, Ks, C_NULL,
@@ -198,7 +209,8 @@ end
 function run_series!(ens::CudaEnsemble, Ks::Vector{Int64})
     push_params!(ens)
     n = length(Ks)
-    rec = Matrix{Float64}(undef, 3, n)
+    nm = length(ens.pool)
+    rec = Matrix{Float64}(undef, 2 + nm, n)            # per store: Σe, Σ_c acc_ck/tot_ck for every move k, chain count
     check(ens.handle, ccall((:arianna_sweep_series, libarianna[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Float64}),
                             ens.handle, n, Ks, C_NULL))
     check(ens.handle, ccall((:arianna_series_global, libarianna[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}),
@@ -209,7 +221,7 @@ function run_series!(ens::CudaEnsemble, Ks::Vector{Int64})
     empty!(ens.series)
     for i in 1:n
         done += Ks[i]
-        ens.series[done] = (rec[1, i] / rec[3, i], rec[2, i] / rec[3, i])
+        ens.series[done] = (rec[1, i] / rec[2 + nm, i], rec[2:1 + nm, i] ./ rec[2 + nm, i])
     end
     ens.pending, ens.ahead, ens.cache_t = 0, sum(Ks[2:end]), -1
     return nothing
@@ -243,7 +255,8 @@ function reduce_callbacks!(ens::CudaEnsemble)
         check(ens.handle, ccall((:arianna_steps_done, libarianna[]), Int32, (Ptr{Cvoid}, Ref{Int64}), ens.handle, t))
         hit = get(ens.series, t[] - ens.ahead, nothing)
         if hit !== nothing
-            ens.energy, ens.acceptance[1], ens.cache_t = hit[1], hit[2], ens.ahead == 0 ? t[] : -1
+            ens.energy, ens.cache_t = hit[1], ens.ahead == 0 ? t[] : -1
+            ens.acceptance .= hit[2]
             return nothing
         end
         ens.ahead == 0 || error("look-ahead plan violated: callbacks requested at an unplanned time")

@@ -40,4 +40,11 @@ function main(M, steps, out)
         end
     end
 end
+# Seeding check for montecarlo_b200/julia_rng.py and oracle/arianna_oracle.c:ao_xoshiro_seed_julia (SHA-256 of the seed's
+# 32-bit limbs, Julia 1.7 - 1.10): they compute Xoshiro(42) = (a379de7eeeb2a4e8, 953dccb6b532b3af, f597b8ff8cfd652a,
+# ccd7337c571680d1); a different line here means this Julia version seeds differently (1.11+) and the device xoshiro
+# mode must be fed uploaded states (CudaEnsemble(...; rng=:xoshiro) of the shim does exactly that).
+let r = Xoshiro(42)
+    println("Xoshiro(42) state: ", join(string.((r.s0, r.s1, r.s2, r.s3), base=16), " "))
+end
 main(parse(Int, ARGS[1]), parse(Int, ARGS[2]), ARGS[3])

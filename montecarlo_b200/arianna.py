@@ -223,6 +223,15 @@ class ParticleEnsemble(AriannaSystem):
             self.engine.init_synthetic(seed if self.init_seed is None else self.init_seed)
         if self.betas is not None:
             self.engine.set_betas(self.betas[self.offset:self.offset + self.n_local])
+        if self.rng == "xoshiro" and hasattr(self.engine, "set_rng_state"):
+            # rngs = [Xoshiro(seed + c - 1) for c in 1:M] (metropolis.jl:262-263): Julia 1.7-1.10's own seeding, hashed on
+            # the host in chunks and uploaded (julia_rng.py; [EXT], unverified without a Julia toolchain)
+            from .julia_rng import xoshiro_states
+            st = np.empty((self.n_local, 4), dtype=np.uint64)
+            for a in range(0, self.n_local, 1 << 20):
+                b = min(self.n_local, a + (1 << 20))
+                st[a:b] = xoshiro_states(np.arange(seed + self.offset + a, seed + self.offset + b, dtype=np.int64))
+            self.engine.set_rng_state(st)
 
     def _push_params(self):
         for k, m in enumerate(self.pool):

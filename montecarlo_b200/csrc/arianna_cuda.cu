@@ -158,6 +158,13 @@ double host_lognorm(double sigma)
     return std::log(6.283185307179586 * s2) / 2.0;
 }
 
+// RN(1 / (2·(σ·σ))) for kernels.cuh:exact_div, or 0 when 2σ² is outside the range its error analysis covers
+double host_inv2s2(double sigma)
+{
+    const double d = 2.0 * (sigma * sigma);
+    return (d >= 0x1p-300 && d <= 0x1p300) ? 1.0 / d : 0.0;
+}
+
 int grid_for(const arianna_handle *h, int64_t M, int ctas_per_sm)
 {
     // at most `cap` CTAs, and every thread gets the same number of chains (to within one): with only a few chains
@@ -379,6 +386,7 @@ int32_t arianna_create(const arianna_config *cfg, arianna_handle **out)
         h->pool.sigma[k] = k < nm ? cfg->sigma[k] : 1.0;
         h->pool.weight[k] = k < nm ? cfg->weight[k] : 0.0;
         h->pool.lognorm[k] = host_lognorm(h->pool.sigma[k]);
+        h->pool.inv2s2[k] = host_inv2s2(h->pool.sigma[k]);
     }
 
     CU_CREATE(cudaMalloc(&h->d_x, sizeof(double) * h->M));
@@ -580,6 +588,7 @@ int32_t arianna_set_params(arianna_handle *h, int32_t move_id, const double *the
     // kernel parameters are passed by value at launch: updating the host copy is all that is needed
     h->pool.sigma[move_id] = theta[0];
     h->pool.lognorm[move_id] = log_norm ? *log_norm : host_lognorm(theta[0]);
+    h->pool.inv2s2[move_id] = host_inv2s2(theta[0]);
     return ARIANNA_OK;
 }
 
@@ -1057,8 +1066,26 @@ int32_t arianna_sweep_replay(arianna_handle *h, int64_t K, const double *u_cat, 
             kernel<<<wave_grid(h, kernel, dyn, h->M), kBlock, dyn, h->stream>>>(rp);
             return ARIANNA_OK;
         };
+        // bulk-copy (TMA) path: cp.async.bulk needs 16-byte aligned rows, i.e. an even number of chains and 16-byte
+        // aligned arrays; ragged shapes take the per-thread-load kernel (same arithmetic, same results)
+        auto aligned16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+        static const int env_tma = getenv("ARIANNA_REPLAY_TMA") ? atoi(getenv("ARIANNA_REPLAY_TMA")) : 1;
+        const bool tma = env_tma && (h->M % 2 == 0) && aligned16(dz) && aligned16(dua) && (!multi || aligned16(duc));
+        auto go_tma = [&](auto kernel) -> int32_t {
+            const size_t dyn = replay_tma_smem_bytes(h->pool.n_moves);
+            CU_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kReplayThreads, dyn) != cudaSuccess || per_sm < 1) {
+                cudaGetLastError();
+                per_sm = 1;
+            }
+            const int64_t nblocks = (h->M + kReplayChains - 1) / kReplayChains, cap = (int64_t)h->sm_count * per_sm;
+            kernel<<<(int)(nblocks < cap ? nblocks : cap), kReplayThreads, dyn, h->stream>>>(rp);   // persistent CTAs
+            return ARIANNA_OK;
+        };
         const int32_t rc = dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
             constexpr int POT = decltype(pot)::value;
+            if (tma) return multi ? go_tma(sweep_replay_tma_kernel<POT, true>) : go_tma(sweep_replay_tma_kernel<POT, false>);
             return multi ? go(sweep_replay_kernel<POT, true>, smem) : go(sweep_replay_kernel<POT, false>, 0);
         });
         if (rc) return rc;

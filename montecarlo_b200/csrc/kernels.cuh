@@ -55,6 +55,7 @@ struct PoolParams {
     double sigma[kMaxMoves];
     double weight[kMaxMoves];
     double lognorm[kMaxMoves];  // log((2π)·(σ·σ))/2, host-computed (particle_1d.jl:53)
+    double inv2s2[kMaxMoves];   // RN(1 / (2·(σ·σ))), host-computed, or 0 when σ is outside the range exact_div covers
 };
 
 struct SweepParams {
@@ -144,16 +145,16 @@ __device__ __forceinline__ double potential(double x)
 // ---------------------------------------------------------------------------------------------------------
 template <int POT>
 __device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, double sigma, double lognorm,
-                                             double z, double u_acc, m64::Tab tb)
+                                             double inv2s2, double z, double u_acc, m64::Tab tb)
 {
     double delta = __dadd_rn(0.0, __dmul_rn(sigma, z));                       // particle_1d.jl:57
     double s2 = __dmul_rn(sigma, sigma);
-    double t1 = __ddiv_rn(-__dmul_rn(delta, delta), __dmul_rn(2.0, s2));      // :53
+    double t1 = m64::exact_div(-__dmul_rn(delta, delta), __dmul_rn(2.0, s2), inv2s2);   // :53
     double lqf = __dsub_rn(t1, lognorm);                                      // metropolis.jl:178
     double e1 = e;                                                            // particle_1d.jl:31
-    x = __dadd_rn(x, delta);                                                  // :32
-    e = potential<POT, ARITH_EXACT>(x);                                       // :33
-    double dlogp = __dsub_rn(__dmul_rn(-e, beta), __dmul_rn(-e1, beta));      // metropolis.jl:98
+    const double xn = __dadd_rn(x, delta);                                    // :32
+    const double en = potential<POT, ARITH_EXACT>(xn);                        // :33
+    double dlogp = __dsub_rn(__dmul_rn(-en, beta), __dmul_rn(-e1, beta));     // metropolis.jl:98
     delta = -delta;                                                           // particle_1d.jl:38
     double lqb = lqf;  // log_proposal_density of -δ: only (-δ)·(-δ) == δ·δ enters -> bitwise equal (metropolis.jl:182)
     double arg = __dsub_rn(__dadd_rn(dlogp, lqb), lqf);                       // :183, NOT simplified to dlogp
@@ -161,10 +162,14 @@ __device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, 
     // evaluation of exp (≤1 ulp, like Julia's / glibc's) would, through the FP32 filter of m64::exp_accept
     float ulo, uhi;
     m64::ucell_from_double(u_acc, ulo, uhi);
-    if (m64::exp_accept(arg, ulo, uhi, [&]() { return u_acc; }, tb)) return 1;
-    x = __dadd_rn(x, delta);                                                  // :187 re-applied negated move:
-    e = potential<POT, ARITH_EXACT>(x);                                       //      x = fl(fl(x+δ)-δ), not a restore
-    return 0;
+    const bool a = m64::exp_accept(arg, ulo, uhi, [&]() { return u_acc; }, tb);
+    // reject: the negated move is re-applied (:187), x = fl(fl(x+δ)-δ) -- not a restore.  Both outcomes are computed and
+    // selected (no branch: two chains of one thread can then be interleaved by the scheduler)
+    const double xr = __dadd_rn(xn, delta);
+    const double er = potential<POT, ARITH_EXACT>(xr);
+    x = a ? xn : xr;
+    e = a ? en : er;
+    return a ? 1 : 0;
 }
 
 // FAST: symmetric proposal => log q terms cancel; α > u  <=>  exp(β(e - e')) > u  because u < 1; reject restores x.
@@ -201,11 +206,11 @@ __device__ __forceinline__ bool mc_step_fast(double &x, double &e, double beta, 
 }
 
 template <int POT, int ARITH, class Cell, class ExactU>
-__device__ __forceinline__ bool mc_step(double &x, double &e, double beta, double sigma, double lognorm, double z,
-                                        Cell cell, ExactU exact_u, m64::Tab tb)
+__device__ __forceinline__ bool mc_step(double &x, double &e, double beta, double sigma, double lognorm, double inv2s2,
+                                        double z, Cell cell, ExactU exact_u, m64::Tab tb)
 {
     if constexpr (ARITH == ARITH_EXACT)
-        return mc_step_exact<POT>(x, e, beta, sigma, lognorm, z, exact_u(), tb) != 0;
+        return mc_step_exact<POT>(x, e, beta, sigma, lognorm, inv2s2, z, exact_u(), tb) != 0;
     else
         return mc_step_fast<POT>(x, e, beta, sigma, z, cell, exact_u, tb);
 }
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
     double sum_e = 0.0;
     unsigned long long sum_acc = 0ull;   // Σ accepted_calls: exact in integers; every chain shares tot = tend
     uint32_t cnt = 0;
-    const double sigma0 = p.pool.sigma[0], lognorm0 = p.pool.lognorm[0];
+    const double sigma0 = p.pool.sigma[0], lognorm0 = p.pool.lognorm[0], inv0 = p.pool.inv2s2[0];
     // Steps are consumed in Box-Muller pairs (pair index = step >> 1).  A run of steps [ta, tb) that starts on an odd
     // step uses only the sine half of its first pair and one that ends on an even step only the cosine half of its
     // last, so the result does not depend on how the steps are chunked into launches or store intervals.
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                     return m64::u53_prefix_refine<12>(d.f0, r.a_lo, r.a_hi);
                 };
                 const CellP<12> ulo{d.f0};
-                const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z0, ulo, exact_u, tb);
+                const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, inv0, d.z0, ulo, exact_u, tb);
                 count_if(acc, a);
             }
             if constexpr (decltype(do1)::value) {
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                     return m64::u53_prefix_refine<11>(d.f1, r.b_lo, r.b_hi);
                 };
                 const CellP<11> ulo{d.f1};
-                const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, d.z1, ulo, exact_u, tb);
+                const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, inv0, d.z1, ulo, exact_u, tb);
                 count_if(acc, a);
             }
         };
@@ -579,11 +584,12 @@ __global__ void __launch_bounds__(kBlock) sweep_replay_kernel(const ReplayParams
     extern __shared__ unsigned char smem_raw[];
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *s_tot = s_acc + (MULTI ? p.pool.n_moves * kBlock : 0);
-    __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves];
+    __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves], s_inv[kMaxMoves];
     if (threadIdx.x < kMaxMoves) {
         s_sigma[threadIdx.x] = p.pool.sigma[threadIdx.x];
         s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
         s_lognorm[threadIdx.x] = p.pool.lognorm[threadIdx.x];
+        s_inv[threadIdx.x] = p.pool.inv2s2[threadIdx.x];
     }
     __shared__ m64::MathTables s_T;
     load_tables(&s_T, p.tables);
@@ -625,11 +631,11 @@ __global__ void __launch_bounds__(kBlock) sweep_replay_kernel(const ReplayParams
                     int d;
                     if constexpr (MULTI) {
                         const int k = categorical(nm, s_weight, uc[i]);
-                        d = mc_step_exact<POT>(x, e, beta, s_sigma[k], s_lognorm[k], zz[i], ua[i], tb);
+                        d = mc_step_exact<POT>(x, e, beta, s_sigma[k], s_lognorm[k], s_inv[k], zz[i], ua[i], tb);
                         s_acc[k * kBlock + threadIdx.x] += d;
                         s_tot[k * kBlock + threadIdx.x] += 1;
                     } else {
-                        d = mc_step_exact<POT>(x, e, beta, s_sigma[0], s_lognorm[0], zz[i], ua[i], tb);
+                        d = mc_step_exact<POT>(x, e, beta, s_sigma[0], s_lognorm[0], s_inv[0], zz[i], ua[i], tb);
                         acc += d;
                     }
                     if (p.decisions) __stcs(p.decisions + (size_t)(s0 + i) * p.M + c, (uint8_t)d);
@@ -674,7 +680,7 @@ __global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroPara
     extern __shared__ unsigned char smem_raw[];
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *s_tot = s_acc + (MULTI ? p.pool.n_moves * kBlock : 0);
-    __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves];
+    __shared__ double s_sigma[kMaxMoves], s_weight[kMaxMoves], s_lognorm[kMaxMoves], s_inv[kMaxMoves];
     __shared__ uint64_t s_ki[256];
     __shared__ double s_wi[256], s_fi[256];
     __shared__ m64::MathTables s_T;
@@ -683,6 +689,7 @@ __global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroPara
         s_sigma[threadIdx.x] = p.pool.sigma[threadIdx.x];
         s_weight[threadIdx.x] = p.pool.weight[threadIdx.x];
         s_lognorm[threadIdx.x] = p.pool.lognorm[threadIdx.x];
+        s_inv[threadIdx.x] = p.pool.inv2s2[threadIdx.x];
     }
     for (int i = threadIdx.x; i < 256; i += kBlock) {
         s_ki[i] = p.ki[i];
@@ -719,13 +726,13 @@ __global__ void __launch_bounds__(kBlock) sweep_xoshiro_kernel(const XoshiroPara
             const CellF ulo{m64::ulo_from_word23(ua_hi), 0x1p-23f};
             if constexpr (MULTI) {
                 const int k = categorical(nm, s_weight, uc);
-                const bool d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], zz, ulo, exact_u,
+                const bool d = mc_step<POT, ARITH>(x, e, beta, s_sigma[k], s_lognorm[k], s_inv[k], zz, ulo, exact_u,
                                                    tb);
                 if (d) s_acc[k * kBlock + threadIdx.x] += 1;
                 s_tot[k * kBlock + threadIdx.x] += 1;
             } else {
                 (void)uc;
-                if (mc_step<POT, ARITH>(x, e, beta, s_sigma[0], s_lognorm[0], zz, ulo, exact_u, tb))
+                if (mc_step<POT, ARITH>(x, e, beta, s_sigma[0], s_lognorm[0], s_inv[0], zz, ulo, exact_u, tb))
                     ++acc;
             }
         }
@@ -1003,3 +1010,4 @@ __global__ void __launch_bounds__(kBlock) dfma_peak_kernel(double *out, int iter
 }  // namespace arianna
 
 #include "kernels_multi.cuh"
+#include "kernels_replay.cuh"

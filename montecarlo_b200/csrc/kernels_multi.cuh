@@ -81,7 +81,7 @@ __device__ __forceinline__ double ratio_fast(double a, double t)
 // shared-memory footprint of one CTA of the kernel below
 __host__ __device__ constexpr size_t multi_smem_bytes(int n_moves, int n_int, int record, int dbuf)
 {
-    return sizeof(m64::MathTables) + kCatBuckets + (8 + 8 + 4) * (size_t)kMaxMoves +
+    return sizeof(m64::MathTables) + kCatBuckets + (8 + 8 + 8 + 4) * (size_t)kMaxMoves +
            (size_t)n_moves * 8 * kBlock * (dbuf ? 2 : 1) + (record ? (size_t)kWarpsPerBlock * n_int * (1 + n_moves) * 8 : 0);
 }
 
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MULTI_MINB) sweep_multi_kernel
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr uint32_t kTabBytes = (uint32_t)sizeof(m64::MathTables);
     constexpr uint32_t kOffCat = kTabBytes, kOffSigma = kOffCat + kCatBuckets, kOffLognorm = kOffSigma + 8 * kMaxMoves,
-                       kOffThr = kOffLognorm + 8 * kMaxMoves, kOffCnt = kOffThr + 4 * kMaxMoves;
+                       kOffInv = kOffLognorm + 8 * kMaxMoves, kOffThr = kOffInv + 8 * kMaxMoves, kOffCnt = kOffThr + 4 * kMaxMoves;
     const int nm = p.pool.n_moves, V = 1 + nm;
     const uint32_t cnt_bytes = 8u * kBlock * (uint32_t)nm;            // one counter buffer: [move][tot|acc][thread] u32
     const uint32_t off_rec = kOffCnt + cnt_bytes * (p.dbuf ? 2u : 1u);
@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MULTI_MINB) sweep_multi_kernel
         if (threadIdx.x < kMaxMoves) {
             reinterpret_cast<double *>(smem_raw + kOffSigma)[threadIdx.x] = p.pool.sigma[threadIdx.x];
             reinterpret_cast<double *>(smem_raw + kOffLognorm)[threadIdx.x] = p.pool.lognorm[threadIdx.x];
+            reinterpret_cast<double *>(smem_raw + kOffInv)[threadIdx.x] = p.pool.inv2s2[threadIdx.x];
             reinterpret_cast<uint32_t *>(smem_raw + kOffThr)[threadIdx.x] = p.cat_thr[threadIdx.x];
         }
         if (p.record)
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MULTI_MINB) sweep_multi_kernel
     __syncthreads();
     const m64::Tab tb = shared_tab(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t a_cat = tb.s + kOffCat, a_sigma = tb.s + kOffSigma, a_lognorm = tb.s + kOffLognorm, a_thr = tb.s + kOffThr;
+    const uint32_t a_cat = tb.s + kOffCat, a_sigma = tb.s + kOffSigma, a_lognorm = tb.s + kOffLognorm, a_inv = tb.s + kOffInv, a_thr = tb.s + kOffThr;
     const uint32_t a_rec = tb.s + off_rec + 8u * (uint32_t)(warp * p.n_int * V);
     const uint32_t buf_flip = p.dbuf ? cnt_bytes : 0u;
     const size_t pitch_b = (size_t)p.pitch * 4;
@@ -177,7 +178,8 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MULTI_MINB) sweep_multi_kernel
             const uint32_t k = pick(w);
             const double sigma = lds_f64(a_sigma + 8u * k);
             const double lognorm = ARITH == ARITH_EXACT ? lds_f64(a_lognorm + 8u * k) : 0.0;
-            const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma, lognorm, z, cell, exact_u, tb) ? 1u : 0u;
+            const double inv = ARITH == ARITH_EXACT ? lds_f64(a_inv + 8u * k) : 0.0;
+            const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma, lognorm, inv, z, cell, exact_u, tb) ? 1u : 0u;
             const uint32_t ak = a_cnt + 8u * kBlock * k;
             red_shared_add(ak, 1u);                      // total_calls += 1          (metropolis.jl:209)
             red_shared_add(ak + 4u * kBlock, a);         // accepted_calls += mc_step! (:208)

@@ -399,6 +399,33 @@ AM_FN bool exp_accept_ref(double x, double u, Tab tb)
     return c == kExpOne || (c == kExpCore && exp_core(x, tb) > u);
 }
 
+// ---- exact division by a per-move constant --------------------------------------------------------------------
+// n / d, correctly rounded, for a divisor whose correctly rounded reciprocal y = RN(1/d) is known (d = 2σ² of
+// log_proposal_density, particle_1d.jl:53).  q0 = RN(n·y) is within 2 ulp of n/d; one residual step makes it faithful
+// (< 1 ulp), and by Markstein's theorem a second residual step from a faithful quotient with y = RN(1/d) returns
+// RN(n/d) exactly -- as long as nothing over/underflows on the way: |n| ∈ [2^-400, 2^400] (checked here on the
+// exponent field) and d ∈ [2^-300, 2^300] (checked by the host, which passes y = 0 otherwise).  5 FP64 instructions
+// and no branch in the common case instead of the ~20 + slow-path call of an IEEE division; bit-identical results
+// (tests/test_math64.py::test_exact_div; the replay tests compare every decision and position with the oracle's `/`).
+AM_FN double exact_div(double n, double d, double y)
+{
+    const uint32_t ex = (double2hi(n) >> 20) & 0x7ffu;
+    if (y != 0.0 && ex - 623u <= 800u) {
+#if AM_DEV
+        double q = __dmul_rn(n, y);
+#else
+        double q = n * y;
+#endif
+        q = fma64(fma64(-d, q, n), y, q);
+        return fma64(fma64(-d, q, n), y, q);
+    }
+#if AM_DEV
+    return __ddiv_rn(n, d);
+#else
+    return n / d;
+#endif
+}
+
 // ---- −2·ln(n·2^-53) --------------------------------------------------------------------------------------
 // Core: u = m·2^E with m ∈ [√½, √2) given by its words (hx, lx) after fdlibm's fold; i = mantissa interval.
 AM_FN double neg2log_core(uint32_t hx_folded, uint32_t lx, int negE, Tab tb)

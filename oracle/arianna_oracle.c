@@ -435,6 +435,83 @@ AO_API void ao_xoshiro_seed(uint64_t seed, uint64_t s[4])
     }
 }
 
+/* Julia's own seeding of `Xoshiro(n::Integer)` [EXT Random stdlib, Julia 1.7 - 1.10; UNVERIFIED here -- no Julia]:
+ *   seed!(rng, n) = seed!(rng, make_seed(n));  make_seed(n) = the 32-bit limbs of n, least significant first;
+ *   seed!(rng, v::Vector{UInt32}): s0..s3 = reinterpret(UInt64, sha256(reinterpret(UInt8, v)))
+ * i.e. the SHA-256 digest of the limbs' little-endian bytes read as four little-endian 64-bit words.  This is what
+ * `rngs = [Xoshiro(seed + c - 1) ...]` (metropolis.jl:262-263) evaluates to.  SHA-256 per FIPS 180-4 (KATs in
+ * tests/test_oracle.py).  Julia 1.11 changed the scheme. */
+static const uint32_t sha_k[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+    0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+    0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+    0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+    0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+    0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+static inline uint32_t rotr32(uint32_t v, int k) { return (v >> k) | (v << (32 - k)); }
+
+static void sha256_block(uint32_t h[8], const uint8_t blk[64])
+{
+    uint32_t w[64];
+    for (int i = 0; i < 16; ++i)
+        w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) | blk[4 * i + 3];
+    for (int i = 16; i < 64; ++i) {
+        uint32_t s0 = rotr32(w[i - 15], 7) ^ rotr32(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        uint32_t s1 = rotr32(w[i - 2], 17) ^ rotr32(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    for (int i = 0; i < 64; ++i) {
+        uint32_t t1 = hh + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + sha_k[i] + w[i];
+        uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+/* SHA-256 of an arbitrary message -> 32 digest bytes. */
+AO_API void ao_sha256(const uint8_t *msg, int64_t len, uint8_t out[32])
+{
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    int64_t off = 0;
+    for (; off + 64 <= len; off += 64) sha256_block(h, msg + off);
+    uint8_t blk[128];
+    int64_t rem = len - off;
+    memset(blk, 0, sizeof blk);
+    memcpy(blk, msg + off, (size_t)rem);
+    blk[rem] = 0x80;
+    int nb = rem + 9 <= 64 ? 1 : 2;
+    uint64_t bits = (uint64_t)len * 8;
+    for (int i = 0; i < 8; ++i) blk[64 * nb - 1 - i] = (uint8_t)(bits >> (8 * i));
+    for (int i = 0; i < nb; ++i) sha256_block(h, blk + 64 * i);
+    for (int i = 0; i < 8; ++i) {
+        out[4 * i] = (uint8_t)(h[i] >> 24); out[4 * i + 1] = (uint8_t)(h[i] >> 16);
+        out[4 * i + 2] = (uint8_t)(h[i] >> 8); out[4 * i + 3] = (uint8_t)h[i];
+    }
+}
+
+AO_API void ao_xoshiro_seed_julia(uint64_t seed, uint64_t s[4])
+{
+    uint8_t msg[8], dig[32];
+    int len = (seed >> 32) ? 8 : 4;                         /* make_seed: one limb unless n >= 2^32 */
+    for (int i = 0; i < len; ++i) msg[i] = (uint8_t)(seed >> (8 * i));
+    ao_sha256(msg, len, dig);
+    for (int k = 0; k < 4; ++k) {
+        uint64_t v = 0;
+        for (int i = 0; i < 8; ++i) v |= (uint64_t)dig[8 * k + i] << (8 * i);
+        s[k] = v;
+    }
+}
+
+/* states: [M][4]; chain c (0-based) gets Xoshiro(seed + chain_offset + c) == the reference's seed + c - 1 (1-based) */
+AO_API void ao_xoshiro_seed_chains_julia(int64_t seed, int64_t chain_offset, int64_t M, uint64_t *states)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < M; ++c) ao_xoshiro_seed_julia((uint64_t)(seed + chain_offset + c), states + 4 * c);
+}
+
 #define ZIG_R 3.6541528853610088
 #define ZIG_INV_R 0.27366123732975828
 #define ZIG_AREA 0.00492867323399

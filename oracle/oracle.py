@@ -175,10 +175,12 @@ class Ensemble:
         return gd
 
     # --- "Julia-like" generator front-end (CPU baseline / replay-stream manufacture) ---------------------
-    def seed_xoshiro(self, seed, chain_offset=0):
+    def seed_xoshiro(self, seed, chain_offset=0, julia=False):
+        """Per-chain generator states for seeds seed + c - 1 (metropolis.jl:262-263).  julia=True: Julia 1.7-1.10's
+        own SHA-256 seeding of Xoshiro(n) [EXT, unverified]; default: a splitmix64 stand-in."""
         self.states = np.zeros((self.M, 4), dtype=np.uint64)
-        lib().ao_xoshiro_seed_chains(C.c_int64(seed), C.c_int64(chain_offset), C.c_int64(self.M),
-                                     _p(self.states, C.c_uint64))
+        fn = lib().ao_xoshiro_seed_chains_julia if julia else lib().ao_xoshiro_seed_chains
+        fn(C.c_int64(seed), C.c_int64(chain_offset), C.c_int64(self.M), _p(self.states, C.c_uint64))
 
     def sweep_xoshiro(self, K):
         ln = lognorm(self.sigma)
@@ -230,6 +232,19 @@ def xoshiro_seed(seed):
     s = np.zeros(4, dtype=np.uint64)
     lib().ao_xoshiro_seed(C.c_uint64(seed), _p(s, C.c_uint64))
     return s
+
+
+def xoshiro_seed_julia(seed):
+    s = np.zeros(4, dtype=np.uint64)
+    lib().ao_xoshiro_seed_julia(C.c_uint64(seed), _p(s, C.c_uint64))
+    return s
+
+
+def sha256(msg: bytes) -> bytes:
+    out = (C.c_uint8 * 32)()
+    buf = (C.c_uint8 * max(1, len(msg))).from_buffer_copy(msg or b"\0")
+    lib().ao_sha256(buf, C.c_int64(len(msg)), out)
+    return bytes(out)
 
 
 def xoshiro_randn_stream(state, n):

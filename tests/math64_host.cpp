@@ -45,6 +45,13 @@ void m64_accept(const double *x, const uint64_t *w, const uint64_t *r, int mode,
         }
     }
 }
+void m64_exact_div(const double *n, const double *d, double *out, long cnt)
+{
+    for (long i = 0; i < cnt; ++i) {
+        const double y = (d[i] >= 0x1p-300 && d[i] <= 0x1p300) ? 1.0 / d[i] : 0.0;    // host_inv2s2 of arianna_cuda.cu
+        out[i] = exact_div(n[i], d[i], y);
+    }
+}
 void m64_u53(const uint64_t *w, double *out, long n) { for (long i = 0; i < n; ++i) out[i] = u53_words((uint32_t)w[i], (uint32_t)(w[i] >> 32)); }
 void m64_tables(double *out) { init(); __builtin_memcpy(out, &T, sizeof T); }
 }

@@ -32,8 +32,9 @@ def _xoshiro_draws(x0, beta, sigma, weight, K, seed=42):
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("pot", ["harmonic", "quartic", "double_well"])
 @pytest.mark.parametrize("sigma,weight", [([0.1], [1.0]), ([0.2] * 7, [0.4] + [0.1] * 6), ([1.5, 0.01], [0.3, 0.7])])
-def test_replay_bit_exact(pot, sigma, weight):
-    M, K, beta = 10007, 67, 2.0                       # ragged M (not a multiple of the block), K not a multiple of 4
+@pytest.mark.parametrize("M", [10007, 10006, 512])        # odd M: per-thread loads; even M: bulk-copy (TMA) tiles
+def test_replay_bit_exact(pot, sigma, weight, M):
+    K, beta = 67, 2.0                                 # ragged M (not a multiple of the block), K not a multiple of 4 or 8
     x0 = O.init_synthetic(11, 0, M)
     uc, z, ua = _xoshiro_draws(x0, beta, sigma, weight, K)
     ref = O.Ensemble(x0, beta, sigma, weight, potential=POTS[pot])

@@ -150,3 +150,36 @@ def test_fp32_filter_never_changes_a_decision(lib, mode):
     # the FP64 decision itself differs from the infinitely precise one only on ulp-level ties of exp()
     assert (truth != ref.astype(bool)).sum() <= 20
     assert list(ref[-11:]) == [1, 1, 1, 1, 0, 0, 0, 0, 0, 1, 1]
+
+
+def test_exact_div(lib):
+    """exact_div(n, d, RN(1/d)) == n / d bit for bit: random and adversarial mantissas (all ones, all zeros, few bits)
+    over the exponent range the fast path covers, and the fall-back outside it (zeros, infinities, NaN, subnormals)."""
+    rng = np.random.default_rng(7)
+    N = 4_000_000
+
+    def rnd(emin, emax, n):
+        m = rng.integers(0, 2 ** 52, size=n, dtype=np.uint64)
+        e = rng.integers(emin + 1023, emax + 1024, size=n, dtype=np.uint64)
+        kind = rng.integers(0, 8, size=n)
+        low = rng.integers(0, 256, size=n, dtype=np.uint64)
+        m = np.where(kind == 0, np.uint64(2 ** 52 - 1) ^ low, m)          # mantissa of (almost) all ones
+        m = np.where(kind == 1, low, m)                                   # (almost) all zeros
+        m = np.where(kind == 2, m & ~np.uint64(2 ** 40 - 1), m)           # few significant bits
+        return ((e << np.uint64(52)) | m).view(np.float64)
+
+    n = -rnd(-400, 399, N)
+    d = rnd(-300, 299, N)
+    sig = rng.random(1000) * 3 + 1e-3                                     # d = 2σ² of real pools, δ = σ z
+    n[:100000] = -((sig[rng.integers(0, 1000, 100000)] * rng.standard_normal(100000)) ** 2)
+    d[:100000] = 2 * sig[rng.integers(0, 1000, 100000)] ** 2
+    out = np.empty(N)
+    lib.m64_exact_div(P(n), P(d), P(out), C.c_long(N))
+    assert np.array_equal(out, n / d)
+    # outside the fast range: the IEEE division itself
+    with np.errstate(all="ignore"):
+        n2 = np.array([0.0, -0.0, -np.inf, np.nan, -1e-320, -1e300, -1e-200, -4.0, -1.0, -1e308])
+        d2 = np.array([0.02, 0.02, 0.02, 0.02, 0.02, 0.02, 0.02, 1e-320, 1e305, 3.0])
+        o2 = np.empty(n2.size)
+        lib.m64_exact_div(P(n2), P(d2), P(o2), C.c_long(n2.size))
+        assert np.array_equal(o2, n2 / d2, equal_nan=True) and np.array_equal(np.signbit(o2), np.signbit(n2 / d2))

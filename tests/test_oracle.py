@@ -306,3 +306,37 @@ def test_build_schedule_restatement():
     assert N.build_schedule(100, 0, [0, 3, 10])[:5] == [0, 3, 10, 13, 20]
     with pytest.raises(ValueError):
         N.build_schedule(1000, 10, 1.5)
+
+
+def test_sha256_and_julia_xoshiro_seeding():
+    """Xoshiro(n) of Julia 1.7-1.10 [EXT, unverified without Julia]: SHA-256 of n's 32-bit little-endian limbs, digest
+    read as four little-endian UInt64 (metropolis.jl:262-263 builds Xoshiro(seed + c - 1) per chain).  The oracle's C
+    SHA-256, hashlib and the product's vectorised numpy hash (montecarlo_b200/julia_rng.py) agree; SHA-256 itself is
+    pinned by the FIPS 180-4 known answers."""
+    import hashlib
+    import struct
+    from montecarlo_b200 import julia_rng as J
+    kat = {b"abc": "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad",
+           b"": "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855",
+           b"abcdbcdecdefdefgefghfghighijhijkijkljklmklmnlmnomnopnopq":
+               "248d6a61d20638b8e5c026930c3e6039a33ce45964ff2167f6ecedd419db06c1"}
+    for m, h in kat.items():
+        assert O.sha256(m).hex() == h == hashlib.sha256(m).hexdigest()
+    for m in (b"a" * 55, b"a" * 56, b"a" * 64, b"a" * 119, bytes(range(200))):      # padding edge cases
+        assert O.sha256(m) == hashlib.sha256(m).digest()
+    assert J.make_seed(42) == [42] and J.make_seed(2 ** 32) == [0, 1] and J.make_seed(0) == [0]
+    seeds = np.array([0, 1, 42, 43, 2 ** 32 - 1, 2 ** 32, 2 ** 40 + 17, 2 ** 63 - 1], dtype=np.uint64)
+    st = J.xoshiro_states(seeds)
+    for sd, row in zip(seeds, st):
+        limbs = J.make_seed(int(sd))
+        d = hashlib.sha256(struct.pack("<%dI" % len(limbs), *limbs)).digest()
+        assert np.array_equal(np.frombuffer(d, dtype="<u8"), row)
+        assert np.array_equal(O.xoshiro_seed_julia(int(sd)), row)
+    assert np.array_equal(J.xoshiro_state(2 ** 70 + 3), np.frombuffer(
+        hashlib.sha256(struct.pack("<3I", 3, 0, 64)).digest(), dtype="<u8"))           # three limbs: hashlib route
+    # per-chain seeds seed + c - 1: the oracle's chain seeding == the product's
+    ens = O.Ensemble(np.zeros(100), 2.0, [0.1])
+    ens.seed_xoshiro(42, chain_offset=7, julia=True)
+    assert np.array_equal(ens.states, J.xoshiro_states(np.arange(49, 149)))
+    with pytest.raises(ValueError):
+        J.make_seed(-1)
