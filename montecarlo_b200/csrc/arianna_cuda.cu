@@ -97,6 +97,9 @@ struct arianna_handle {
     unsigned int *d_ticket = nullptr;
     double *d_sums = nullptr;       // [kMaxOut]
     double *d_gd = nullptr;         // [kMaxMoves][5]
+    double *d_pgmc_partials = nullptr;     // [n_learn][grid][5] of the estimator kernel (grow-only)
+    size_t pgmc_partials_cap = 0;
+    unsigned int *d_pgmc_ticket = nullptr; // [kMaxMoves]
     unsigned long long *d_csum = nullptr;  // [2 * kMaxMoves]
     m64::MathTables *d_tables = nullptr;   // exp/log tables of csrc/math64.cuh
     double *d_scratch = nullptr;    // e[] staging for get_state / dfma out
@@ -449,6 +452,7 @@ int32_t arianna_destroy(arianna_handle *h)
     cudaFree(h->d_ki); cudaFree(h->d_wi); cudaFree(h->d_fi); cudaFree(h->d_partials); cudaFree(h->d_ticket);
     cudaFree(h->d_sums); cudaFree(h->d_gd); cudaFree(h->d_csum); cudaFree(h->d_scratch); cudaFree(h->d_tables);
     cudaFree(h->d_series); cudaFree(h->d_series_partials); cudaFree(h->d_cat_table);
+    cudaFree(h->d_pgmc_partials); cudaFree(h->d_pgmc_ticket);
     if (h->coll_stream) cudaStreamSynchronize(h->coll_stream);
     if (h->comm) { nccl::g_api.CommDestroy(h->comm); h->comm = nullptr; }
     cudaFree(h->d_coll);
@@ -1404,26 +1408,46 @@ static int32_t pgmc_impl(arianna_handle *h, int32_t q_batch, const int32_t *lear
         dz = h->d_scratch;
     }
     time_mark(h, 1, true);
-    for (int l = 0; l < n_learn; ++l) {
-        const int k = learn_ids[l];
+    {
+        // ONE launch for all the learnable moves (the loop over moves runs inside the kernel)
         PgmcParams pp{};
         pp.x = h->d_x; pp.betas = h->d_betas; pp.beta = h->cfg.beta; pp.M = h->M; pp.q_batch = q_batch;
-        pp.q0 = h->pgmc_samples + (int64_t)l * q_batch;
+        pp.n_learn = n_learn;
+        pp.q0 = h->pgmc_samples;
         pp.sid0 = (uint64_t)(h->cfg.seed + h->cfg.chain_offset);
-        pp.sigma = h->pool.sigma[k]; pp.lognorm = h->pool.lognorm[k];
-        pp.z = replay ? dz + (size_t)l * q_batch * h->M : nullptr;
-        pp.partials = h->d_partials; pp.ticket = h->d_ticket; pp.gd = h->d_gd + 5 * l;
+        for (int l = 0; l < n_learn; ++l) {
+            pp.sigma[l] = h->pool.sigma[learn_ids[l]];
+            pp.lognorm[l] = h->pool.lognorm[learn_ids[l]];
+        }
+        pp.z = replay ? dz : nullptr;
+        pp.gd = h->d_gd;
         pp.tables = h->d_tables;
-        dispatch_pot(h->cfg.potential, [&](auto pot) {
+        if (!h->d_pgmc_ticket) {
+            CU_TRY(h, cudaMalloc(&h->d_pgmc_ticket, sizeof(unsigned int) * kMaxMoves));
+            CU_TRY(h, cudaMemsetAsync(h->d_pgmc_ticket, 0, sizeof(unsigned int) * kMaxMoves, h->stream));
+        }
+        pp.ticket = h->d_pgmc_ticket;
+        const int32_t rc = dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
             constexpr int POT = decltype(pot)::value;
-            if (replay)
-                pgmc_kernel<POT, ARITH_EXACT, true><<<wave_grid(h, pgmc_kernel<POT, ARITH_EXACT, true>, 0, h->M), kBlock, 0, h->stream>>>(pp);
-            else if (exact)
-                pgmc_kernel<POT, ARITH_EXACT, false><<<wave_grid(h, pgmc_kernel<POT, ARITH_EXACT, false>, 0, h->M), kBlock, 0, h->stream>>>(pp);
-            else
-                pgmc_kernel<POT, ARITH_FAST, false><<<wave_grid(h, pgmc_kernel<POT, ARITH_FAST, false>, 0, h->M), kBlock, 0, h->stream>>>(pp);
-            return 0;
+            auto go = [&](auto kernel) -> int32_t {
+                const int grid = wave_grid(h, kernel, 0, h->M);
+                const size_t need = (size_t)n_learn * grid * 5;
+                if (h->pgmc_partials_cap < need) {
+                    CU_TRY(h, cudaStreamSynchronize(h->stream));
+                    cudaFree(h->d_pgmc_partials);
+                    h->d_pgmc_partials = nullptr;
+                    h->pgmc_partials_cap = 0;
+                    CU_TRY(h, cudaMalloc(&h->d_pgmc_partials, sizeof(double) * need));
+                    h->pgmc_partials_cap = need;
+                }
+                pp.partials = h->d_pgmc_partials;
+                kernel<<<grid, kBlock, 0, h->stream>>>(pp);
+                return ARIANNA_OK;
+            };
+            if (replay) return go(pgmc_kernel<POT, ARITH_EXACT, true>);
+            return exact ? go(pgmc_kernel<POT, ARITH_EXACT, false>) : go(pgmc_kernel<POT, ARITH_FAST, false>);
         });
+        if (rc) return rc;
         CU_TRY(h, cudaGetLastError());
         ++h->launches;
     }

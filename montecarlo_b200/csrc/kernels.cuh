@@ -821,10 +821,12 @@ __global__ void __launch_bounds__(kBlock) counter_sum_kernel(const uint32_t *acc
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K3: PGMC estimator for ONE learnable move per launch (the reference's outer loop, estimator.jl:112).
-// Per chain: q_batch x pgmc_estimate (gradients.jl:93-109) with the analytic ∂σ log q; sums of
-// (j, ∇j, ∇logq_forward, g, n) are block-reduced and ADDED to gd[5] by the last block (gradients_data[k] += gd,
-// estimator.jl:130).  REPLAY reads z[q_batch][M] instead of the Philox estimator stream.
+// K3: PGMC estimator, ALL learnable moves in one launch (the reference's outer loop, estimator.jl:112, runs inside the
+// kernel: one launch and one tail per estimator pass instead of n_learn).  Per learnable move and chain: q_batch x
+// pgmc_estimate (gradients.jl:93-109) with the analytic ∂σ log q; sums of (j, ∇j, ∇logq_forward, g, n) are
+// block-reduced and ADDED to gd[l][5] by the last block (gradients_data[k] += gd, estimator.jl:130).  Every thread
+// visits the same chains for every move, so the EXACT variant's perform/undo drift of x carries from move to move
+// exactly as in the reference's sequential loop.  REPLAY reads z[n_learn][q_batch][M] instead of the estimator stream.
 // ---------------------------------------------------------------------------------------------------------
 struct PgmcParams {
     double *x;
@@ -832,14 +834,15 @@ struct PgmcParams {
     double beta;
     int64_t M;
     int q_batch;
-    int64_t q0;           // estimator samples already drawn per chain (draw index base)
+    int n_learn;
+    int64_t q0;           // estimator samples already drawn per chain (draw index base of the first learnable move)
     uint64_t sid0;
-    double sigma;
-    double lognorm;
+    double sigma[kMaxMoves];     // of the learnable moves, in order
+    double lognorm[kMaxMoves];
     const double *z;      // replay only
-    double *partials;
-    unsigned int *ticket;
-    double *gd;           // [5] accumulators of this learnable move
+    double *partials;     // [n_learn][gridDim.x][5]
+    unsigned int *ticket; // [n_learn]
+    double *gd;           // [n_learn][5] accumulators
     const m64::MathTables *tables;
 };
 
@@ -889,45 +892,50 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_PGMC_MINB) pgmc_kernel(const P
     load_tables(&s_T, p.tables);
     __syncthreads();
     const m64::Tab tb = shared_tab(&s_T);
-    double sj = 0.0, sdj = 0.0, sgf = 0.0, sg = 0.0, sn = 0.0;
-    const int64_t qend = p.q0 + p.q_batch;
-    for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
-        double x = p.x[c];
-        double e = potential<POT, ARITH>(x);
-        const double beta = p.betas ? p.betas[c] : p.beta;
-        if constexpr (REPLAY) {
-            for (int b = 0; b < p.q_batch; ++b)
-                pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, __ldcs(p.z + (size_t)b * p.M + c), sj, sdj,
-                                        sgf, sg, tb);
-        } else {
-            const uint64_t sid = p.sid0 + (uint64_t)c;
-            const PhiloxChain<kTagEstimator, 0> ph(sid);
-            // samples [q0, q1) of this chain's estimator stream, two per Box-Muller pair; only the first / last pair
-            // of a launch can be split (q < 2^33, host check)
-            auto pair = [&](uint32_t pr, bool do0, bool do1) {
-                const U64Pair blk = ph.block(pr);
-                double z0, z1;
-                m64::box_muller_u64(u64_of(blk.a_lo, blk.a_hi), u64_of(blk.b_lo, blk.b_hi), tb, z0, z1);
-                if (do0) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z0, sj, sdj, sgf, sg, tb);
-                if (do1) pgmc_sample<POT, ARITH>(x, e, beta, p.sigma, p.lognorm, z1, sj, sdj, sgf, sg, tb);
-            };
-            const bool lead = (p.q0 & 1) != 0, trail = (qend & 1) != 0;
-            uint32_t pr = (uint32_t)(p.q0 >> 1);
-            const uint32_t pr_end = (uint32_t)(qend >> 1);      // first pair that is not complete
-            if (lead) { pair(pr, false, true); ++pr; }
 #pragma unroll 1
-            for (; pr < pr_end; ++pr) pair(pr, true, true);
-            if (trail) pair(pr, true, false);
+    for (int l = 0; l < p.n_learn; ++l) {
+        const double sigma = p.sigma[l], lognorm = p.lognorm[l];
+        const int64_t q0 = p.q0 + (int64_t)l * p.q_batch, qend = q0 + p.q_batch;
+        double sj = 0.0, sdj = 0.0, sgf = 0.0, sg = 0.0, sn = 0.0;
+        for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
+            double x = p.x[c];
+            double e = potential<POT, ARITH>(x);
+            const double beta = p.betas ? p.betas[c] : p.beta;
+            if constexpr (REPLAY) {
+                const double *zl = p.z + (size_t)l * p.q_batch * p.M;
+                for (int b = 0; b < p.q_batch; ++b)
+                    pgmc_sample<POT, ARITH>(x, e, beta, sigma, lognorm, __ldcs(zl + (size_t)b * p.M + c), sj, sdj, sgf, sg, tb);
+            } else {
+                const uint64_t sid = p.sid0 + (uint64_t)c;
+                const PhiloxChain<kTagEstimator, 0> ph(sid);
+                // samples [q0, qend) of this chain's estimator stream, two per Box-Muller pair; only the first / last
+                // pair of a move can be split (q < 2^33, host check)
+                auto pair = [&](uint32_t pr, bool do0, bool do1) {
+                    const U64Pair blk = ph.block(pr);
+                    double z0, z1;
+                    m64::box_muller_u64(u64_of(blk.a_lo, blk.a_hi), u64_of(blk.b_lo, blk.b_hi), tb, z0, z1);
+                    if (do0) pgmc_sample<POT, ARITH>(x, e, beta, sigma, lognorm, z0, sj, sdj, sgf, sg, tb);
+                    if (do1) pgmc_sample<POT, ARITH>(x, e, beta, sigma, lognorm, z1, sj, sdj, sgf, sg, tb);
+                };
+                const bool lead = (q0 & 1) != 0, trail = (qend & 1) != 0;
+                uint32_t pr = (uint32_t)(q0 >> 1);
+                const uint32_t pr_end = (uint32_t)(qend >> 1);      // first pair that is not complete
+                if (lead) { pair(pr, false, true); ++pr; }
+#pragma unroll 1
+                for (; pr < pr_end; ++pr) pair(pr, true, true);
+                if (trail) pair(pr, true, false);
+            }
+            sn += (double)p.q_batch;
+            if constexpr (ARITH == ARITH_EXACT) p.x[c] = x;  // perform/undo rounding drift is part of the reference
         }
-        sn += (double)p.q_batch;
-        if constexpr (ARITH == ARITH_EXACT) p.x[c] = x;  // perform/undo rounding drift is part of the reference
+        if constexpr (ARITH == ARITH_FAST) {   // the powers of σ factored out of pgmc_sample
+            const double s1 = sigma, i1 = 1.0 / sigma;
+            sj *= s1 * s1; sdj *= s1; sgf *= i1; sg *= i1 * i1;
+        }
+        double vals[5] = {sj, sdj, sgf, sg, sn};
+        __syncthreads();                       // the reduction's shared scratch is reused from move to move
+        block_reduce_and_finish<5>(vals, 5, p.partials + (size_t)l * gridDim.x * 5, p.ticket + l, p.gd + 5 * l, true);
     }
-    if constexpr (ARITH == ARITH_FAST) {   // the powers of σ factored out of pgmc_sample
-        const double s1 = p.sigma, i1 = 1.0 / p.sigma;
-        sj *= s1 * s1; sdj *= s1; sgf *= i1; sg *= i1 * i1;
-    }
-    double vals[5] = {sj, sdj, sgf, sg, sn};
-    block_reduce_and_finish<5>(vals, 5, p.partials, p.ticket, p.gd, true);
 }
 
 // K5: synthetic initial condition x0 = 4u − 2 (MC_harmonic_oscillator.jl:13) from stream tag 0.

@@ -69,6 +69,60 @@ __host__ __device__ constexpr size_t replay_tma_smem_bytes(int n_moves)
            (n_moves > 1 ? (size_t)n_moves * 8 * kReplayChains : 0);
 }
 
+// N chains of one thread through one EXACT Metropolis step, phase by phase: the arithmetic of every chain is the
+// straight-line common case of mc_step_exact (exact_div's fast path, the FP32 accept filter deciding), written so that
+// the N dependency chains sit in ONE basic block and the scheduler interleaves them (a single chain leaves the FP64
+// pipe waiting on its own previous result: `wait` was the top stall).  A chain whose divisor / dividend is outside
+// exact_div's range or whose filter is ambiguous is flagged and redone by the scalar mc_step_exact from its ORIGINAL
+// state -- same functions, same operation order, so the results are bit-identical to the scalar kernel.
+template <int POT, int N>
+__device__ __forceinline__ void mc_step_exact_ilp(double (&x)[N], double (&e)[N], const double (&beta)[N],
+                                                  const double (&sigma)[N], const double (&lognorm)[N],
+                                                  const double (&inv)[N], const double (&z)[N], const double (&ua)[N],
+                                                  int (&dec)[N], m64::Tab tb)
+{
+    double xn[N], en[N], ndelta[N];
+    bool acc[N], slow[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        const double delta = __dadd_rn(0.0, __dmul_rn(sigma[q], z[q]));            // particle_1d.jl:57
+        const double dd = __dmul_rn(2.0, __dmul_rn(sigma[q], sigma[q]));
+        const double n = -__dmul_rn(delta, delta);
+        const uint32_t ex = ((uint32_t)__double2hiint(n) >> 20) & 0x7ffu;
+        const bool div_ok = inv[q] != 0.0 && ex - 623u <= 800u;                      // m64::exact_div's fast range
+        double t1 = __dmul_rn(n, inv[q]);
+        t1 = __fma_rn(__fma_rn(-dd, t1, n), inv[q], t1);
+        t1 = __fma_rn(__fma_rn(-dd, t1, n), inv[q], t1);                             // == n / dd (Markstein)
+        const double lqf = __dsub_rn(t1, lognorm[q]);                                // particle_1d.jl:53
+        xn[q] = __dadd_rn(x[q], delta);                                              // :32
+        en[q] = potential<POT, ARITH_EXACT>(xn[q]);                                  // :33
+        const double dlogp = __dsub_rn(__dmul_rn(-en[q], beta[q]), __dmul_rn(-e[q], beta[q]));   // metropolis.jl:98
+        ndelta[q] = -delta;                                                          // particle_1d.jl:38
+        const double arg = __dsub_rn(__dadd_rn(dlogp, lqf), lqf);                    // metropolis.jl:183 (lqb == lqf bitwise)
+        // the FP32 filter of m64::exp_accept, verbatim
+        float ulo, uhi;
+        m64::ucell_from_double(ua[q], ulo, uhi);
+        const float a = (float)arg;
+        const float E = m64::ex2_approx(a * 1.44269504f);
+        const float eps = fmaf(fabsf(a), 4.76837158e-07f, 4.76837158e-07f);
+        const float Elo = fmaf(-E, eps, E), Ehi = fmaf(E, eps, E);
+        acc[q] = (a >= 0.0f) || (Elo >= uhi);
+        slow[q] = !div_ok || !(acc[q] || (Ehi < ulo));
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        if (slow[q]) {                                       // rare: the scalar step, from the untouched state
+            dec[q] = mc_step_exact<POT>(x[q], e[q], beta[q], sigma[q], lognorm[q], inv[q], z[q], ua[q], tb);
+        } else {
+            const double xr = __dadd_rn(xn[q], ndelta[q]);   // reject: re-applied negated move (metropolis.jl:187)
+            const double er = potential<POT, ARITH_EXACT>(xr);
+            x[q] = acc[q] ? xn[q] : xr;
+            e[q] = acc[q] ? en[q] : er;
+            dec[q] = acc[q] ? 1 : 0;
+        }
+    }
+}
+
 template <int POT, bool MULTI>
 __global__ void __launch_bounds__(kReplayThreads, 2) sweep_replay_tma_kernel(const ReplayParams p)
 {
@@ -182,19 +236,29 @@ __global__ void __launch_bounds__(kReplayThreads, 2) sweep_replay_tma_kernel(con
             // both chains of the thread run unconditionally (a chain past the end of the ensemble computes on stale
             // shared memory and is never stored): straight-line code that the scheduler interleaves
             int d[kReplayIlp];
+            double zz[kReplayIlp], uu[kReplayIlp], sg[kReplayIlp], ln[kReplayIlp], iv[kReplayIlp];
+            int kk[kReplayIlp];
 #pragma unroll
             for (int q = 0; q < kReplayIlp; ++q) {
                 const uint32_t a = a0 + r * kRowBytes + q * (kBlock * 8u);
-                const double z = lds_f64(a);
-                const double ua = lds_f64(a + kArrBytes);
+                zz[q] = lds_f64(a);
+                uu[q] = lds_f64(a + kArrBytes);
+                if constexpr (MULTI) {
+                    kk[q] = categorical(nm, s_weight, lds_f64(a + 2 * kArrBytes));
+                    sg[q] = s_sigma[kk[q]]; ln[q] = s_lognorm[kk[q]]; iv[q] = s_inv[kk[q]];
+                } else {
+                    kk[q] = 0;
+                    sg[q] = sigma0; ln[q] = lognorm0; iv[q] = inv0;
+                }
+            }
+            mc_step_exact_ilp<POT, kReplayIlp>(x, e, beta, sg, ln, iv, zz, uu, d, tb);
+#pragma unroll
+            for (int q = 0; q < kReplayIlp; ++q) {
                 if constexpr (MULTI) {
                     const int lc = q * kBlock + threadIdx.x;
-                    const int k = categorical(nm, s_weight, lds_f64(a + 2 * kArrBytes));
-                    d[q] = mc_step_exact<POT>(x[q], e[q], beta[q], s_sigma[k], s_lognorm[k], s_inv[k], z, ua, tb);
-                    s_acc[k * kReplayChains + lc] += d[q];
-                    s_tot[k * kReplayChains + lc] += 1;
+                    s_acc[kk[q] * kReplayChains + lc] += d[q];
+                    s_tot[kk[q] * kReplayChains + lc] += 1;
                 } else {
-                    d[q] = mc_step_exact<POT>(x[q], e[q], beta[q], sigma0, lognorm0, inv0, z, ua, tb);
                     acc[q] += d[q];
                 }
             }
