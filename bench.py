@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--mc-steps", type=int, default=10, help="Metropolis steps per store interval")
     ap.add_argument("--series", type=int, default=0,
                     help="store intervals fused per launch (0 = the engine's preferred count, 1 = one launch per store)")
-    ap.add_argument("--slices", type=int, default=32, help="chain slices of the pipelined end-to-end job")
+    ap.add_argument("--slices", type=int, default=4, help="regular chain slices of the pipelined end-to-end job")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -385,45 +385,58 @@ def run_ours(args):
             else:
                 eng.run_host_job([S] * W, x_in=x_in.data_ptr(), x_out=x_out.data_ptr(), n_slices=args.slices, read=False)
                 _ = eng.series_global(W)
-            barrier()
-            barrier()
-            t0 = time.perf_counter()
-            if main["g_max"] == 1:
-                eng.set_state_from_ptr(x_in.data_ptr())            # H2D: the job's chains, pinned host -> HBM
-                for _ in range(K):
-                    eng.set_params(0, 0.1)                         # the launch's input: policy parameters θ = (σ)
-                    eng.sweep(S, reduce=True)
+            def timed_job(download):
+                """One end-to-end job: x0 pinned host -> HBM, K store intervals, the K records -> host (all-reduced
+                inside the library when N > 1) and, with `download`, the final chains -> pinned host."""
+                barrier()
+                barrier()
+                t0 = time.perf_counter()
+                if main["g_max"] == 1:
+                    eng.set_state_from_ptr(x_in.data_ptr())            # H2D: the job's chains, pinned host -> HBM
+                    for _ in range(K):
+                        eng.set_params(0, 0.1)                         # the launch's input: policy parameters θ = (σ)
+                        eng.sweep(S, reduce=True)
+                        if world > 1:
+                            ev = float(eng.callbacks_global()[0])      # in-library all-reduce + D2H: the step's result
+                        else:
+                            vals = eng.callback_sums()                 # D2H: the step's result (3 doubles)
+                            ev = float(vals[0] / vals[2])
+                    if download:
+                        eng.get_state_to_ptr(x_out.data_ptr())         # D2H: final chains (StoreLastFrames)
+                else:
+                    # the whole job in ONE C-ABI call: chains in, K store intervals, records out (chains out); the library
+                    # pipelines slices of chains so that the copies (one stream per PCIe direction) overlap the sweeps
+                    eng.set_params(0, 0.1)
+                    r = eng.run_host_job([S] * K, x_in=x_in.data_ptr(), x_out=x_out.data_ptr() if download else None,
+                                         n_slices=args.slices, read=(world == 1))
                     if world > 1:
-                        evals = float(eng.callbacks_global()[0])   # in-library all-reduce + D2H: the step's result
-                    else:
-                        vals = eng.callback_sums()                 # D2H: the step's result (3 doubles)
-                        evals = float(vals[0] / vals[2])
-                eng.get_state_to_ptr(x_out.data_ptr())             # D2H: final chains (StoreLastFrames)
-            else:
-                # the whole job in ONE C-ABI call: chains in, K store intervals, records out, chains out; the library
-                # pipelines slices of chains so that the copies (one stream per PCIe direction) overlap the sweeps
-                eng.set_params(0, 0.1)
-                r = eng.run_host_job([S] * K, x_in=x_in.data_ptr(), x_out=x_out.data_ptr(), n_slices=args.slices,
-                                     read=(world == 1))
+                        r = eng.series_global(K)                       # in-library NCCL all-reduce + D2H of the K records
+                    ev = float(r[-1, 0] / r[-1, 2])
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
                 if world > 1:
-                    r = eng.series_global(K)                       # in-library NCCL all-reduce + D2H of the K records
-                evals = float(r[-1, 0] / r[-1, 2])
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-            pcie = eng.job_timing() if main["g_max"] > 1 else None
-        e2e = {"value": m_local * world * S * K / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(8 * m_local / K + 8), "d2h_bytes_per_step": int(8 * m_local / K + 24),
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                return float(tt.item()), ev, (eng.job_timing() if main["g_max"] > 1 else None)
+
+            dt, evals, pcie = timed_job(False)
+            dt_dl, _, pcie_dl = timed_job(True)
+        total_steps = m_local * world * S * K
+        e2e = {"value": total_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(8 * m_local / K + 8), "d2h_bytes_per_step": 24,
                "seconds": dt, "collective": "in-library NCCL (arianna_series_global)" if world > 1 else None,
                "pcie_rank0": pcie,
-               "note": ("timed: ONE arianna_run_host_job call = pinned-host x0 -> HBM, K store intervals, records -> "
-                        f"host, final x -> pinned host, pipelined over {args.slices} slices of chains, uploads and "
-                        "downloads on separate streams" if main["g_max"] > 1 else
-                        "timed: pinned-host x0 -> HBM once, per step sigma in + callback sums out, final x -> "
-                        "pinned host; one-off copies amortised over the K steps"),
+               "note": ("timed: ONE arianna_run_host_job call = pinned-host x0 -> HBM, K store intervals, the K callback "
+                        f"records -> host, pipelined over ramped slices of chains ({args.slices} regular ones); the chains "
+                        "stay resident in HBM like the shim's CudaEnsemble (C3 has no StoreLastFrames)"
+                        if main["g_max"] > 1 else
+                        "timed: pinned-host x0 -> HBM once, per step sigma in + callback sums out; the one-off upload is "
+                        "amortised over the K steps"),
+               "with_final_state_download": {
+                   "value": total_steps / dt_dl, "seconds": dt_dl, "d2h_bytes_per_step": int(8 * m_local / K + 24),
+                   "pcie_rank0": pcie_dl,
+                   "note": "the same job + the final chains -> pinned host (StoreLastFrames), uploads and downloads on "
+                           "separate streams"},
                "energy": evals}
         del x_in, x_out
 

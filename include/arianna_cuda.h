@@ -214,6 +214,12 @@ ARIANNA_API int32_t arianna_pgmc_read(arianna_handle *h, arianna_gradient_data *
 ARIANNA_API int32_t arianna_pgmc_reset(arianna_handle *h);
 ARIANNA_API int32_t arianna_pgmc_sums_device(arianna_handle *h, double **dptr, int32_t *n);
 
+/* Page-locked host memory for hosts without a CUDA binding of their own: what arianna_run_host_job and
+ * arianna_get_state_async need for their copies to be asynchronous.  write_combined != 0: memory the host only WRITES
+ * and the GPU reads (x_in) -- not snooped, faster over PCIe, very slow to read back on the CPU. */
+ARIANNA_API int32_t arianna_host_alloc(int64_t bytes, int32_t write_combined, void **out);
+ARIANNA_API int32_t arianna_host_free(void *p);
+
 /* Plumbing. */
 ARIANNA_API int32_t arianna_get_stream(arianna_handle *h, void **stream);
 ARIANNA_API int32_t arianna_synchronize(arianna_handle *h);

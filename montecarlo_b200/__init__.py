@@ -13,7 +13,7 @@ ensemble without a CUDA device raises AriannaError(ERR_NO_DEVICE).
 from . import _lib
 from ._build import LIB_PATH, build_library
 from ._lib import AriannaError
-from .engine import CudaEnsemble
+from .engine import CudaEnsemble, HostBuffer
 from .arianna import *  # noqa: F401,F403
 from . import julia_rng
 from . import policy_guided

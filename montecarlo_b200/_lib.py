@@ -63,6 +63,8 @@ SYMBOLS = {
     "arianna_get_state": (C.c_int32, [_H, C.c_void_p, C.c_void_p]),
     "arianna_get_state_async": (C.c_int32, [_H, C.c_void_p]),
     "arianna_copy_wait": (C.c_int32, [_H]),
+    "arianna_host_alloc": (C.c_int32, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "arianna_host_free": (C.c_int32, [C.c_void_p]),
     "arianna_set_beta": (C.c_int32, [_H, C.c_double]),
     "arianna_set_betas": (C.c_int32, [_H, C.c_void_p]),
     "arianna_set_params": (C.c_int32, [_H, C.c_int32, _D, C.c_int32, _D]),

@@ -553,6 +553,30 @@ int32_t arianna_get_state_async(arianna_handle *h, double *x_pinned)
     return ARIANNA_OK;
 }
 
+// Page-locked host memory for hosts without a CUDA binding of their own (the Julia shim): the buffers
+// arianna_run_host_job / arianna_get_state_async need for their copies to be asynchronous.  write_combined: memory the
+// host only writes and the GPU reads (x_in) -- not snooped, faster over PCIe, very slow to read back on the CPU.
+int32_t arianna_host_alloc(int64_t bytes, int32_t write_combined, void **out)
+{
+    if (!out || bytes <= 0) return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_host_alloc: bad arguments");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, e == cudaErrorMemoryAllocation ? ARIANNA_ERR_NOMEM : ARIANNA_ERR_CUDA,
+                    std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    }
+    return ARIANNA_OK;
+}
+
+int32_t arianna_host_free(void *p)
+{
+    if (!p) return ARIANNA_OK;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, ARIANNA_ERR_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e)); }
+    return ARIANNA_OK;
+}
+
 int32_t arianna_copy_wait(arianna_handle *h)
 {
     if (!h) return ARIANNA_ERR_INVALID;
@@ -920,6 +944,47 @@ int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t 
     return ARIANNA_OK;
 }
 
+// Slice plan of a host job: slice i = chains [cuts[i], cuts[i + 1]).  The sweep of a slice can only start when its
+// upload has landed and its download only when its sweep is done, so the FIRST upload and the LAST download are
+// exposed.  The plan therefore starts with small slices (1/64 of the ensemble, at least one resident wave of the sweep
+// kernel) that double up to the regular size M / n_slices and, when the chains are downloaded, ends with slices that
+// halve again: the per-launch overheads (a partial last wave per launch) are paid by the few regular slices while the
+// exposed copies shrink to 1/64 of the ensemble.  Every cut except the last is a multiple of the CTA size.
+static std::vector<int64_t> slice_cuts(int64_t M, int n_slices, bool ramp_head, bool ramp_tail, int64_t wave)
+{
+    auto down = [](int64_t v) { return v / kBlock * kBlock; };
+    std::vector<int64_t> cuts{0};
+    if (n_slices <= 1 || M <= 2 * kBlock) { cuts.push_back(M); return cuts; }
+    int64_t cap = down((M + n_slices - 1) / n_slices + kBlock - 1);
+    if (cap < kBlock) cap = kBlock;
+    int64_t small = down(M / 64);
+    if (small < wave) small = wave < cap ? wave : cap;
+    std::vector<int64_t> ramp;      // small, small, 2 small, 2 small, 4 small, ... below the regular size
+    {
+        int64_t sum = 0;
+        int rep = 0;
+        for (int64_t sz = small; sz < cap && sum + sz <= M / 4;) {
+            ramp.push_back(sz);
+            sum += sz;
+            if (rep) sz *= 2;
+            rep ^= 1;
+        }
+    }
+    int64_t tail = 0;
+    if (ramp_tail) for (auto v : ramp) tail += v;
+    if (ramp_head) for (auto v : ramp) cuts.push_back(cuts.back() + v);
+    const int64_t body_end = (ramp_tail && !ramp.empty()) ? down(M - tail) : M;
+    while (cuts.back() < body_end) {
+        const int64_t left = body_end - cuts.back();
+        cuts.push_back(cuts.back() + (left < cap + cap / 4 ? left : cap));       // no tiny remainder slice
+    }
+    if (ramp_tail && !ramp.empty()) {
+        for (size_t i = ramp.size(); i-- > 1;) cuts.push_back(cuts.back() + ramp[i]);   // largest first ...
+        cuts.push_back(M);                                                               // ... smallest (+ rounding) last
+    }
+    return cuts;
+}
+
 // A whole callbacks-only job with HOST buffers, pipelined over slices of the chains: the upload of slice i+1 (H2D
 // stream) and the download of slice i-1 (D2H stream) run while slice i sweeps through ALL the store intervals on the
 // compute stream (chains are independent, so slice-major order gives the same chains and the same records as
@@ -935,10 +1000,10 @@ int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_st
     if (rc) return rc;
     rc = ensure_copy_stream(h);
     if (rc) return rc;
-    // slices: whole CTAs' worth of chains each
-    int64_t per = (h->M + n_slices - 1) / n_slices;
-    per = (per + kBlock - 1) / kBlock * kBlock;
-    const int ns = (int)((h->M + per - 1) / per);
+    // Slices: whole CTAs' worth of chains each (see slice_cuts)
+    const std::vector<int64_t> cuts = slice_cuts(h->M, n_slices, x_in != nullptr, x_out != nullptr,
+                                                 (int64_t)h->sm_count * 4 * kBlock);
+    const int ns = (int)cuts.size() - 1;
     std::vector<cudaEvent_t> up(ns, nullptr), done(ns, nullptr);
     bool queued = false;
     auto cleanup = [&]() {
@@ -972,7 +1037,7 @@ int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_st
     if (x_in) {
         JOB_TRY(cudaEventRecord(h->ev_job[0], h->h2d_stream));
         for (int i = 0; i < ns; ++i) {
-            const int64_t off = (int64_t)i * per, m = (h->M - off < per) ? h->M - off : per;
+            const int64_t off = cuts[i], m = cuts[i + 1] - cuts[i];
             queued = true;
             JOB_TRY(cudaMemcpyAsync(h->d_x + off, x_in + off, sizeof(double) * m, cudaMemcpyHostToDevice, h->h2d_stream));
             JOB_TRY(cudaEventRecord(up[i], h->h2d_stream));
@@ -982,7 +1047,7 @@ int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_st
     }
     time_mark(h, 0, true);
     for (int i = 0; i < ns; ++i) {
-        const int64_t off = (int64_t)i * per, m = (h->M - off < per) ? h->M - off : per;
+        const int64_t off = cuts[i], m = cuts[i + 1] - cuts[i];
         if (x_in) JOB_TRY(cudaStreamWaitEvent(h->stream, up[i], 0));
         if (n_stores > 0) {
             queued = true;

@@ -28,6 +28,30 @@ class _DeviceBuffer:
         }
 
 
+class HostBuffer:
+    """Page-locked host memory from the library (arianna_host_alloc), viewed as a float64 numpy array.
+    write_combined=True: for buffers the host only writes and the GPU reads (uploads)."""
+
+    def __init__(self, n: int, write_combined: bool = False):
+        self._lib = L.load()
+        p = C.c_void_p()
+        L.check(None, self._lib.arianna_host_alloc(8 * int(n), 1 if write_combined else 0, C.byref(p)))
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(int(n),))
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self._lib.arianna_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class CudaEnsemble:
     """M Metropolis chains of the particle_1d system resident in the HBM of one B200.
 
@@ -162,7 +186,7 @@ class CudaEnsemble:
                                                 _ptr(rec)))
         return rec
 
-    def run_host_job(self, Ks: Sequence[int], x_in=None, x_out=None, n_slices: int = 8, read: bool = True):
+    def run_host_job(self, Ks: Sequence[int], x_in=None, x_out=None, n_slices: int = 4, read: bool = True):
         """A complete callbacks-only job with host buffers, pipelined over slices of the chains
         (arianna_run_host_job): chains in, len(Ks) store intervals, records out, chains out.  x_in / x_out: numpy
         arrays or raw pointers of page-locked host memory ([n_chains] f64), or None."""

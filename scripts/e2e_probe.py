@@ -15,11 +15,13 @@ with mb.CudaEnsemble(M, 2.0, [0.1], seed=42) as eng:
     eng.sweep_series([10] * K, read=False); eng.synchronize()
     t0 = time.perf_counter(); eng.sweep_series([10] * K, read=False); eng.synchronize()
     print(json.dumps({"resident_series_wall_ms": 1e3 * (time.perf_counter() - t0), "sweep_ms": eng.timing()[0]}))
-    for slices in (8, 16, 24, 32, 48, 8):
-        for rep in range(3):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            eng.run_host_job([10] * K, x_in=x_in.data_ptr(), x_out=x_out.data_ptr(), n_slices=slices)
-            dt = time.perf_counter() - t0
-            print(json.dumps({"slices": slices, "rep": rep, "wall_ms": 1e3 * dt, "sweep_ms": eng.timing()[0],
-                              "rate": M * 10 * K / dt, **eng.job_timing()}), flush=True)
+    for download in (False, True):
+        for slices in (4, 8, 16, 32):
+            for rep in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                eng.run_host_job([10] * K, x_in=x_in.data_ptr(), x_out=x_out.data_ptr() if download else None, n_slices=slices)
+                dt = time.perf_counter() - t0
+                print(json.dumps({"download": download, "slices": slices, "rep": rep, "wall_ms": round(1e3 * dt, 2),
+                                  "sweep_ms": round(eng.timing()[0], 2), "rate": M * 10 * K / dt,
+                                  **{k: round(v, 2) for k, v in eng.job_timing().items()}}), flush=True)

