@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ARIANNA_ABI_VERSION 1
+#define ARIANNA_ABI_VERSION 2
 #if defined(__GNUC__)
 #define ARIANNA_API __attribute__((visibility("default")))
 #else
@@ -68,6 +68,16 @@ enum arianna_arith_mode {
                                     reject                                                                 */
 };
 
+/* Element type of the ensemble: `Particle{T<:AbstractFloat}` (particle_1d.jl:9-16) with matching action and parameter
+ * types.  F32 = Particle{Float32}, Displacement{Float32}, ComponentArray(σ = 0.1f0): state and proposal arithmetic in
+ * Float32, log-proposal constants and the accept test in Float64 exactly as Julia's promotion rules make the
+ * reference's generic code run (csrc/kernels_f32.cuh).  F32 handles: single-move pools, native Philox stream or replay,
+ * arianna_sweep / arianna_sweep_replay / the callbacks; series, host jobs, PGMC and XOSHIRO return UNSUPPORTED. */
+enum arianna_dtype {
+    ARIANNA_F64 = 0,
+    ARIANNA_F32 = 1
+};
+
 /* Flags of arianna_sweep */
 #define ARIANNA_SWEEP_REDUCE 1u  /* fuse the callback reductions (energy / acceptance sums) into the sweep  */
 
@@ -88,6 +98,8 @@ typedef struct arianna_config {
     int32_t rng_mode;            /* enum arianna_rng_mode                                                  */
     int32_t arith_mode;          /* enum arianna_arith_mode                                                */
     void *stream;                /* optional cudaStream_t to run on; NULL = the handle creates its own     */
+    int32_t dtype;               /* enum arianna_dtype                                                     */
+    int32_t reserved;            /* must be 0                                                              */
 } arianna_config;
 
 /* Summed GradientData record of one learnable move (gradients.jl:41-47), P = 1 parameter (σ). */
@@ -114,6 +126,10 @@ ARIANNA_API int32_t arianna_destroy(arianna_handle *h);
 ARIANNA_API int32_t arianna_set_state(arianna_handle *h, const double *x);
 ARIANNA_API int32_t arianna_init_synthetic(arianna_handle *h, int64_t seed);
 ARIANNA_API int32_t arianna_get_state(arianna_handle *h, double *x, double *e);
+/* The same for ARIANNA_F32 handles in their own element type (the Float64 entry points above also work on them:
+ * set rounds to Float32, get widens exactly). */
+ARIANNA_API int32_t arianna_set_state_f32(arianna_handle *h, const float *x);
+ARIANNA_API int32_t arianna_get_state_f32(arianna_handle *h, float *x, float *e);
 /* Asynchronous variant for StoreTrajectories at scale (algorithms.jl:198-203): snapshots x on the device and
  * drains the snapshot into caller-pinned memory on a second stream, so the PCIe transfer overlaps the next sweep;
  * arianna_copy_wait() / arianna_synchronize() complete it. */
@@ -158,12 +174,15 @@ ARIANNA_API int32_t arianna_series_per_launch(arianna_handle *h, int32_t *n);
 /* The same stretch as a complete job with HOST buffers: chains in (x_in, [n_chains], NULL = keep the resident state),
  * n_stores store intervals, records out ([n_stores][2 + n_moves] local-shard sums, may be NULL), chains out (x_out, may be
  * NULL) -- i.e. `chains = [...]; run!(Simulation(chains, (Metropolis, StoreCallbacks, StoreLastFrames), steps))`
- * (src/simulation.jl:175-204) in one call.  The ensemble is cut into n_slices slices of chains that go through ALL the
- * store intervals one slice after the other, so that the upload of the next slice and the download of the previous
- * one overlap the sweep of the current one (pass page-locked buffers for the copies to be asynchronous).  Chains are
- * independent: the final chains and counters are bit-identical to arianna_set_state + arianna_sweep_series +
- * arianna_get_state, the records equal up to the order of the slice sums.  Synchronous: host buffers are complete /
- * reusable on return.  Multi-GPU hosts all-reduce the device records afterwards (arianna_series_global). */
+ * (src/simulation.jl:175-204) in one call.  The ensemble is cut into slices of chains that go through ALL the store
+ * intervals one slice after the other, so that the upload of the next slice (H2D stream) and the download of the
+ * previous one (D2H stream) overlap the sweep of the current one (pass page-locked buffers -- arianna_host_alloc -- for
+ * the copies to be asynchronous).  n_slices is the number of REGULAR slices (size n_chains / n_slices); the plan starts
+ * with smaller slices (1/64 of the ensemble, doubling) and, when x_out is given, ends with slices that halve again, so
+ * that the exposed first upload and last download are short.  Chains are independent: the final chains and counters
+ * are bit-identical to arianna_set_state + arianna_sweep_series + arianna_get_state, the records equal up to the order
+ * of the slice sums.  Synchronous: host buffers are complete / reusable on return.  Multi-GPU hosts all-reduce the
+ * device records afterwards (arianna_series_global). */
 ARIANNA_API int32_t arianna_run_host_job(arianna_handle *h, const double *x_in, int32_t n_stores, const int64_t *K,
                                          double *records, double *x_out, int32_t n_slices);
 /* PCIe view of the LAST arianna_run_host_job call: device time (ms, first copy start -> last copy end on the upload /

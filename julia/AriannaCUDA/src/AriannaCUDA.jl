@@ -38,6 +38,8 @@ struct AriannaConfig
     rng_mode::Int32
     arith_mode::Int32
     stream::Ptr{Cvoid}
+    dtype::Int32                  # 0 = Float64, 1 = Float32 (Particle{Float32}, σ = 0.1f0)
+    reserved::Int32
 end
 
 struct GradientRecord            # arianna_gradient_data
@@ -86,7 +88,7 @@ function CudaEnsemble(x0::Vector{Float64}, β::Float64, pool; seed::Int=1, poten
     pad(v) = ntuple(k -> k <= nm ? Float64(v[k]) : 0.0, MAX_MOVES)
     cfg = AriannaConfig(UInt32(sizeof(AriannaConfig)), Int32(device), length(x0), chain_offset, n_total, seed, β,
                         POT[potential], Int32(nm), pad([m.parameters.σ for m in pool]), pad([m.weight for m in pool]),
-                        Int32(rng == :xoshiro ? 1 : 0), Int32(arith == :exact ? 0 : 1), C_NULL)
+                        Int32(rng == :xoshiro ? 1 : 0), Int32(arith == :exact ? 0 : 1), C_NULL, Int32(0), Int32(0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(C_NULL, ccall((:arianna_create, libarianna[]), Int32, (Ref{AriannaConfig}, Ref{Ptr{Cvoid}}), cfg, h))
     ens = CudaEnsemble{Float64}(h[], length(x0), β, pool, 0, -1, NaN, fill(NaN, nm), 0,

@@ -18,6 +18,7 @@ SWEEP_REDUCE = 1
 POTENTIALS = {"harmonic": POT_HARMONIC, "quartic": POT_QUARTIC, "double_well": POT_DOUBLE_WELL}
 RNG_MODES = {"philox": RNG_PHILOX, "xoshiro": RNG_XOSHIRO}
 ARITH_MODES = {"exact": ARITH_EXACT, "fast": ARITH_FAST}
+DTYPES = {"f64": 0, "f32": 1}
 
 
 class Config(C.Structure):
@@ -36,6 +37,8 @@ class Config(C.Structure):
         ("rng_mode", C.c_int32),
         ("arith_mode", C.c_int32),
         ("stream", C.c_void_p),
+        ("dtype", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -61,6 +64,8 @@ SYMBOLS = {
     "arianna_set_state": (C.c_int32, [_H, C.c_void_p]),
     "arianna_init_synthetic": (C.c_int32, [_H, C.c_int64]),
     "arianna_get_state": (C.c_int32, [_H, C.c_void_p, C.c_void_p]),
+    "arianna_set_state_f32": (C.c_int32, [_H, C.c_void_p]),
+    "arianna_get_state_f32": (C.c_int32, [_H, C.c_void_p, C.c_void_p]),
     "arianna_get_state_async": (C.c_int32, [_H, C.c_void_p]),
     "arianna_copy_wait": (C.c_int32, [_H]),
     "arianna_host_alloc": (C.c_int32, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
@@ -125,7 +130,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library ever disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.arianna_abi_version() != 1:
+    if lib.arianna_abi_version() != 2:
         raise ImportError("libarianna_cuda.so ABI version mismatch")
     _lib = lib
     return lib

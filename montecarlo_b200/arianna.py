@@ -169,7 +169,8 @@ class ParticleEnsemble(AriannaSystem):
     or synthetically (x0 = 4u − 2 from the engine's counter-based stream, MC_harmonic_oscillator.jl:13)."""
 
     def __init__(self, x0=None, beta=1.0, *, n_chains: Optional[int] = None, potential: str = "harmonic",
-                 arith: str = "fast", rng: str = "philox", device: int = -1, init_seed: Optional[int] = None):
+                 arith: str = "fast", rng: str = "philox", device: int = -1, init_seed: Optional[int] = None,
+                 dtype: str = "f64"):
         if x0 is None and n_chains is None:
             raise ValueError("give x0 (host positions) or n_chains (synthetic initial condition)")
         if x0 is not None and not isinstance(x0, np.ndarray) and len(x0) and isinstance(x0[0], Particle):
@@ -189,6 +190,8 @@ class ParticleEnsemble(AriannaSystem):
             beta = float(self.betas[0])
         self.β = self.beta = float(beta)
         self.potential, self.arith, self.rng, self.device = potential, arith, rng, device
+        # element type of the chains: Particle{Float64} or Particle{Float32} (particle_1d.jl:9-16)
+        self.dtype = {"f64": "f64", "f32": "f32", "float64": "f64", "float32": "f32"}[str(np.dtype(dtype)) if not isinstance(dtype, str) else dtype]
         self.init_seed = init_seed
         dist = _dist()
         self.rank = dist.get_rank() if dist else 0
@@ -216,7 +219,8 @@ class ParticleEnsemble(AriannaSystem):
         self.pool = pool
         self.engine = CudaEnsemble(self.n_local, self.β, [m.parameters.σ for m in pool], [m.weight for m in pool],
                                    seed=seed, chain_offset=self.offset, n_chains_total=self.n_total,
-                                   potential=self.potential, rng=self.rng, arith=self.arith, device=self.device)
+                                   potential=self.potential, rng=self.rng, arith=self.arith, device=self.device,
+                                   **({"dtype": "f32"} if self.dtype == "f32" else {}))
         if self.x0 is not None:
             self.engine.set_state(self.x0[self.offset:self.offset + self.n_local])
         else:
@@ -261,7 +265,8 @@ class ParticleEnsemble(AriannaSystem):
             self.pending += n
 
     def _series_supported(self):
-        return self._lookahead is not None and self.rng == "philox" and hasattr(self.engine, "sweep_series")
+        return (self._lookahead is not None and self.rng == "philox" and self.dtype == "f64"
+                and hasattr(self.engine, "sweep_series"))
 
     def _run_series(self, Ks):
         """One arianna_sweep_series call for [pending, K_1, K_2, ...]; every record lands in the cache."""
@@ -313,9 +318,9 @@ class ParticleEnsemble(AriannaSystem):
 
     @property
     def x(self) -> np.ndarray:
-        """Local shard of positions (system.x)."""
+        """Local shard of positions (system.x), in the chains' element type."""
         self.flush()
-        return self.engine.get_state()
+        return self.engine.get_state_f32() if self.dtype == "f32" else self.engine.get_state()
 
     @property
     def e(self) -> np.ndarray:

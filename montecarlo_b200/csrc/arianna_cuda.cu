@@ -87,6 +87,10 @@ struct arianna_handle {
     int grid = 0;        // grid of the light streaming kernels: 8 CTAs per SM x SM count
 
     int64_t M = 0;
+    bool f32 = false;               // ARIANNA_F32: the state lives in d_xf (4 B per chain), d_x is not allocated
+    float *d_xf = nullptr;
+    float *d_betas_f = nullptr;
+    double lognorm_f32 = 0.0;       // log(2π·Float64(σ32·σ32))/2
     double *d_x = nullptr;
     uint32_t *d_acc = nullptr, *d_tot = nullptr;
     double *d_betas = nullptr;
@@ -320,6 +324,11 @@ int32_t arianna_create(const arianna_config *cfg, arianna_handle **out)
         return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: unknown rng_mode");
     if (cfg->arith_mode != ARIANNA_ARITH_EXACT && cfg->arith_mode != ARIANNA_ARITH_FAST)
         return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: unknown arith_mode");
+    if (cfg->dtype != ARIANNA_F64 && cfg->dtype != ARIANNA_F32)
+        return fail(nullptr, ARIANNA_ERR_INVALID, "arianna_create: unknown dtype");
+    if (cfg->dtype == ARIANNA_F32 && (cfg->n_moves != 1 || cfg->rng_mode != ARIANNA_RNG_PHILOX))
+        return fail(nullptr, ARIANNA_ERR_UNSUPPORTED,
+                    "arianna_create: Float32 ensembles support single-move pools with the native Philox stream (or replay)");
     double wsum = 0.0;
     for (int k = 0; k < cfg->n_moves; ++k) {
         if (!(cfg->sigma[k] > 0.0) || !std::isfinite(cfg->sigma[k]))
@@ -392,7 +401,15 @@ int32_t arianna_create(const arianna_config *cfg, arianna_handle **out)
         h->pool.inv2s2[k] = host_inv2s2(h->pool.sigma[k]);
     }
 
-    CU_CREATE(cudaMalloc(&h->d_x, sizeof(double) * h->M));
+    h->f32 = cfg->dtype == ARIANNA_F32;
+    if (h->f32) {
+        CU_CREATE(cudaMalloc(&h->d_xf, sizeof(float) * h->M));
+        CU_CREATE(cudaMemsetAsync(h->d_xf, 0, sizeof(float) * h->M, h->stream));
+        const float s32 = (float)h->pool.sigma[0], s2 = s32 * s32;
+        h->lognorm_f32 = std::log(6.283185307179586 * (double)s2) / 2.0;
+    } else {
+        CU_CREATE(cudaMalloc(&h->d_x, sizeof(double) * h->M));
+    }
     CU_CREATE(cudaMalloc(&h->d_acc, sizeof(uint32_t) * h->M * nm));
     CU_CREATE(cudaMemsetAsync(h->d_acc, 0, sizeof(uint32_t) * h->M * nm, h->stream));
     if (nm > 1) {
@@ -404,7 +421,7 @@ int32_t arianna_create(const arianna_config *cfg, arianna_handle **out)
         CU_CREATE(cudaMemcpyAsync(h->d_cat_table, table.data(), kCatBuckets, cudaMemcpyHostToDevice, h->stream));
         CU_CREATE(cudaStreamSynchronize(h->stream));
     }
-    CU_CREATE(cudaMemsetAsync(h->d_x, 0, sizeof(double) * h->M, h->stream));
+    if (!h->f32) CU_CREATE(cudaMemsetAsync(h->d_x, 0, sizeof(double) * h->M, h->stream));
     const int max_grid = h->sm_count * 8 * kMaxGridWaves;  // partials of the largest grid wave_grid() can return
     CU_CREATE(cudaMalloc(&h->d_partials, sizeof(double) * (size_t)max_grid * kMaxOut));
     CU_CREATE(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
@@ -448,6 +465,7 @@ int32_t arianna_destroy(arianna_handle *h)
     if (!h) return ARIANNA_OK;
     DeviceGuard guard(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_xf); cudaFree(h->d_betas_f);
     cudaFree(h->d_x); cudaFree(h->d_acc); cudaFree(h->d_tot); cudaFree(h->d_betas); cudaFree(h->d_rng);
     cudaFree(h->d_ki); cudaFree(h->d_wi); cudaFree(h->d_fi); cudaFree(h->d_partials); cudaFree(h->d_ticket);
     cudaFree(h->d_sums); cudaFree(h->d_gd); cudaFree(h->d_csum); cudaFree(h->d_scratch); cudaFree(h->d_tables);
@@ -478,6 +496,16 @@ int32_t arianna_set_state(arianna_handle *h, const double *x)
     if (!h) return ARIANNA_ERR_INVALID;
     REQUIRE(h, x != nullptr, "arianna_set_state: x is NULL");
     DeviceGuard guard(h->device);
+    if (h->f32) {        // Float64 view of a Float32 ensemble: upload, round to nearest
+        if (!ensure_scratch(h, sizeof(double) * h->M)) return fail(h, ARIANNA_ERR_NOMEM, "arianna_set_state: scratch allocation failed");
+        CU_TRY(h, cudaMemcpyAsync(h->d_scratch, x, sizeof(double) * h->M, cudaMemcpyHostToDevice, h->stream));
+        f32_from_f64_kernel<<<h->grid, kBlock, 0, h->stream>>>(h->d_xf, h->d_scratch, h->M);
+        CU_TRY(h, cudaGetLastError());
+        ++h->launches;
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        h->sums_valid = false;
+        return ARIANNA_OK;
+    }
     CU_TRY(h, cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->M, cudaMemcpyHostToDevice, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     h->sums_valid = false;
@@ -488,6 +516,9 @@ int32_t arianna_init_synthetic(arianna_handle *h, int64_t seed)
 {
     if (!h) return ARIANNA_ERR_INVALID;
     DeviceGuard guard(h->device);
+    if (h->f32)
+        init_kernel_f32<<<h->grid, kBlock, 0, h->stream>>>(h->d_xf, h->M, (uint64_t)(seed + h->cfg.chain_offset));
+    else
     init_kernel<<<h->grid, kBlock, 0, h->stream>>>(h->d_x, h->M, (uint64_t)(seed + h->cfg.chain_offset));
     CU_TRY(h, cudaGetLastError());
     ++h->launches;
@@ -499,6 +530,19 @@ int32_t arianna_get_state(arianna_handle *h, double *x, double *e)
 {
     if (!h) return ARIANNA_ERR_INVALID;
     DeviceGuard guard(h->device);
+    if (h->f32) {        // Float64 view of a Float32 ensemble: widen exactly on the device, then download
+        if (!ensure_scratch(h, sizeof(double) * h->M)) return fail(h, ARIANNA_ERR_NOMEM, "arianna_get_state: scratch allocation failed");
+        double *out[2] = {x, e};
+        for (int w = 0; w < 2; ++w) {
+            if (!out[w]) continue;
+            f64_from_f32_kernel<<<h->grid, kBlock, 0, h->stream>>>(h->d_scratch, h->d_xf, h->M, h->cfg.potential, w);
+            CU_TRY(h, cudaGetLastError());
+            ++h->launches;
+            CU_TRY(h, cudaMemcpyAsync(out[w], h->d_scratch, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        return ARIANNA_OK;
+    }
     if (x) CU_TRY(h, cudaMemcpyAsync(x, h->d_x, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->stream));
     if (e) {
         if (!ensure_scratch(h, sizeof(double) * h->M))
@@ -507,6 +551,35 @@ int32_t arianna_get_state(arianna_handle *h, double *x, double *e)
         CU_TRY(h, cudaGetLastError());
         ++h->launches;
         CU_TRY(h, cudaMemcpyAsync(e, h->d_scratch, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return ARIANNA_OK;
+}
+
+int32_t arianna_set_state_f32(arianna_handle *h, const float *x)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, x != nullptr, "arianna_set_state_f32: x is NULL");
+    if (!h->f32) return fail(h, ARIANNA_ERR_UNSUPPORTED, "arianna_set_state_f32: the handle was not created with ARIANNA_F32");
+    DeviceGuard guard(h->device);
+    CU_TRY(h, cudaMemcpyAsync(h->d_xf, x, sizeof(float) * h->M, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->sums_valid = false;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_get_state_f32(arianna_handle *h, float *x, float *e)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    if (!h->f32) return fail(h, ARIANNA_ERR_UNSUPPORTED, "arianna_get_state_f32: the handle was not created with ARIANNA_F32");
+    DeviceGuard guard(h->device);
+    if (x) CU_TRY(h, cudaMemcpyAsync(x, h->d_xf, sizeof(float) * h->M, cudaMemcpyDeviceToHost, h->stream));
+    if (e) {
+        if (!ensure_scratch(h, sizeof(float) * h->M)) return fail(h, ARIANNA_ERR_NOMEM, "arianna_get_state_f32: scratch allocation failed");
+        energy_kernel_f32<<<h->grid, kBlock, 0, h->stream>>>(h->d_xf, reinterpret_cast<float *>(h->d_scratch), h->M, h->cfg.potential);
+        CU_TRY(h, cudaGetLastError());
+        ++h->launches;
+        CU_TRY(h, cudaMemcpyAsync(e, h->d_scratch, sizeof(float) * h->M, cudaMemcpyDeviceToHost, h->stream));
     }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return ARIANNA_OK;
@@ -538,6 +611,7 @@ int32_t arianna_get_state_async(arianna_handle *h, double *x_pinned)
 {
     if (!h) return ARIANNA_ERR_INVALID;
     REQUIRE(h, x_pinned != nullptr, "arianna_get_state_async: destination is NULL");
+    if (h->f32) return fail(h, ARIANNA_ERR_UNSUPPORTED, "arianna_get_state_async: Float64 ensembles only (use arianna_get_state_f32)");
     DeviceGuard guard(h->device);
     int32_t rc = ensure_copy_stream(h);
     if (rc) return rc;
@@ -592,6 +666,7 @@ int32_t arianna_set_beta(arianna_handle *h, double beta)
     DeviceGuard guard(h->device);
     h->cfg.beta = beta;
     if (h->d_betas) { cudaStreamSynchronize(h->stream); cudaFree(h->d_betas); h->d_betas = nullptr; }
+    if (h->d_betas_f) { cudaStreamSynchronize(h->stream); cudaFree(h->d_betas_f); h->d_betas_f = nullptr; }
     return ARIANNA_OK;
 }
 
@@ -600,6 +675,16 @@ int32_t arianna_set_betas(arianna_handle *h, const double *betas)
     if (!h) return ARIANNA_ERR_INVALID;
     REQUIRE(h, betas != nullptr, "arianna_set_betas: betas is NULL");
     DeviceGuard guard(h->device);
+    if (h->f32) {        // Particle{Float32}.β is a Float32
+        if (!h->d_betas_f) CU_TRY(h, cudaMalloc(&h->d_betas_f, sizeof(float) * h->M));
+        if (!ensure_scratch(h, sizeof(double) * h->M)) return fail(h, ARIANNA_ERR_NOMEM, "arianna_set_betas: scratch allocation failed");
+        CU_TRY(h, cudaMemcpyAsync(h->d_scratch, betas, sizeof(double) * h->M, cudaMemcpyHostToDevice, h->stream));
+        f32_from_f64_kernel<<<h->grid, kBlock, 0, h->stream>>>(h->d_betas_f, h->d_scratch, h->M);
+        CU_TRY(h, cudaGetLastError());
+        ++h->launches;
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        return ARIANNA_OK;
+    }
     if (!h->d_betas) CU_TRY(h, cudaMalloc(&h->d_betas, sizeof(double) * h->M));
     CU_TRY(h, cudaMemcpyAsync(h->d_betas, betas, sizeof(double) * h->M, cudaMemcpyHostToDevice, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -617,6 +702,10 @@ int32_t arianna_set_params(arianna_handle *h, int32_t move_id, const double *the
     h->pool.sigma[move_id] = theta[0];
     h->pool.lognorm[move_id] = log_norm ? *log_norm : host_lognorm(theta[0]);
     h->pool.inv2s2[move_id] = host_inv2s2(theta[0]);
+    if (h->f32) {
+        const float s32 = (float)theta[0], s2 = s32 * s32;
+        h->lognorm_f32 = log_norm ? *log_norm : std::log(6.283185307179586 * (double)s2) / 2.0;
+    }
     return ARIANNA_OK;
 }
 
@@ -631,6 +720,14 @@ int32_t arianna_get_params(arianna_handle *h, int32_t move_id, double *theta, in
 
 static int32_t launch_callback_reduce(arianna_handle *h)
 {
+    if (h->f32) {
+        callback_reduce_f32_kernel<<<h->grid, kBlock, 0, h->stream>>>(h->d_xf, h->d_acc, h->M, h->steps_done, h->cfg.potential,
+                                                                      h->d_partials, h->d_ticket, h->d_sums);
+        CU_TRY(h, cudaGetLastError());
+        ++h->launches;
+        h->sums_valid = true;
+        return ARIANNA_OK;
+    }
     ReduceParams rp{h->d_x, h->d_acc, h->d_tot, h->M, h->steps_done, h->pool.n_moves, h->cfg.potential,
                     h->d_partials, h->d_ticket, h->d_sums};
     callback_reduce_kernel<<<h->grid, kBlock, 0, h->stream>>>(rp);
@@ -715,6 +812,31 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
     const bool exact = h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
     time_mark(h, 0, true);
 
+    if (h->f32) {
+        F32Params fp{};
+        fp.x = h->d_xf; fp.acc = h->d_acc; fp.betas = h->d_betas_f; fp.beta = (float)h->cfg.beta;
+        fp.M = h->M; fp.K = K; fp.t0 = h->steps_done;
+        fp.sid0 = (uint64_t)(h->cfg.seed + h->cfg.chain_offset);
+        fp.sigma = (float)h->pool.sigma[0]; fp.lognorm = h->lognorm_f32;
+        fp.reduce = want_reduce ? 1 : 0;
+        fp.partials = h->d_partials; fp.ticket = h->d_ticket; fp.sums = h->d_sums;
+        fp.tables = h->d_tables;
+        const int32_t rc = dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
+            constexpr int POT = decltype(pot)::value;
+            auto go = [&](auto kernel) -> int32_t {
+                kernel<<<wave_grid(h, kernel, 0, h->M), kBlock, 0, h->stream>>>(fp);
+                return ARIANNA_OK;
+            };
+            return exact ? go(sweep_f32_kernel<POT, ARITH_EXACT>) : go(sweep_f32_kernel<POT, ARITH_FAST>);
+        });
+        if (rc) return rc;
+        CU_TRY(h, cudaGetLastError());
+        ++h->launches;
+        h->steps_done += K;
+        h->sums_valid = want_reduce;
+        time_mark(h, 0, false);
+        return ARIANNA_OK;
+    }
     if (h->cfg.rng_mode == ARIANNA_RNG_PHILOX && multi) {
         // multi-move pools: the record (when asked for) is reduced inside the sweep, per move
         REQUIRE(h, K < (int64_t(1) << 31), "arianna_sweep: K must be < 2^31");
@@ -900,8 +1022,8 @@ static int32_t series_range(arianna_handle *h, int64_t off, int64_t m, int64_t t
 static int32_t series_prepare(arianna_handle *h, const char *who, int32_t n_stores, const int64_t *K, int64_t *total_out)
 {
     REQUIRE(h, n_stores >= 0 && (n_stores == 0 || K != nullptr), std::string(who) + ": bad arguments");
-    if (h->cfg.rng_mode != ARIANNA_RNG_PHILOX)
-        return fail(h, ARIANNA_ERR_UNSUPPORTED, std::string(who) + ": the native Philox stream only (use arianna_sweep)");
+    if (h->cfg.rng_mode != ARIANNA_RNG_PHILOX || h->f32)
+        return fail(h, ARIANNA_ERR_UNSUPPORTED, std::string(who) + ": Float64 ensembles with the native Philox stream only (use arianna_sweep)");
     int64_t total = 0;
     for (int32_t i = 0; i < n_stores; ++i) {
         REQUIRE(h, K[i] >= 0 && K[i] < (int64_t(1) << 31), std::string(who) + ": K[i] must be in [0, 2^31)");
@@ -1122,6 +1244,22 @@ int32_t arianna_sweep_replay(arianna_handle *h, int64_t K, const double *u_cat, 
     const size_t smem = multi ? sizeof(uint32_t) * 2 * h->pool.n_moves * kBlock : 0;
 
     auto launch = [&](int64_t k, const double *duc, const double *dz, const double *dua, uint8_t *ddec) -> int32_t {
+        if (h->f32) {       // Float32 ensemble: the same Float64 draws, z rounded to Float32 as randn(rng, Float32) does
+            F32Params fp{};
+            fp.x = h->d_xf; fp.acc = h->d_acc; fp.betas = h->d_betas_f; fp.beta = (float)h->cfg.beta;
+            fp.M = h->M; fp.K = k;
+            fp.sigma = (float)h->pool.sigma[0]; fp.lognorm = h->lognorm_f32;
+            fp.tables = h->d_tables;
+            fp.z = dz; fp.u_acc = dua; fp.decisions = ddec;
+            dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
+                constexpr int POT = decltype(pot)::value;
+                sweep_replay_f32_kernel<POT><<<wave_grid(h, sweep_replay_f32_kernel<POT>, 0, h->M), kBlock, 0, h->stream>>>(fp);
+                return ARIANNA_OK;
+            });
+            CU_TRY(h, cudaGetLastError());
+            ++h->launches;
+            return ARIANNA_OK;
+        }
         ReplayParams rp{};
         rp.x = h->d_x; rp.acc = h->d_acc; rp.tot = h->d_tot; rp.betas = h->d_betas; rp.beta = h->cfg.beta;
         rp.M = h->M; rp.K = k; rp.u_cat = multi ? duc : nullptr; rp.z = dz; rp.u_acc = dua; rp.decisions = ddec;
@@ -1455,6 +1593,7 @@ int32_t arianna_get_chain_counters(arianna_handle *h, uint32_t *accepted, uint32
 static int32_t pgmc_impl(arianna_handle *h, int32_t q_batch, const int32_t *learn_ids, int32_t n_learn,
                          const double *z, int32_t on_device, bool replay)
 {
+    if (h->f32) return fail(h, ARIANNA_ERR_UNSUPPORTED, "arianna_pgmc_estimate: Float64 ensembles only");
     REQUIRE(h, q_batch >= 1, "arianna_pgmc_estimate: q_batch must be >= 1");
     REQUIRE(h, n_learn >= 0 && n_learn <= kMaxMoves && (n_learn == 0 || learn_ids != nullptr),
             "arianna_pgmc_estimate: bad learn_ids");

@@ -1019,3 +1019,4 @@ __global__ void __launch_bounds__(kBlock) dfma_peak_kernel(double *out, int iter
 
 #include "kernels_multi.cuh"
 #include "kernels_replay.cuh"
+#include "kernels_f32.cuh"

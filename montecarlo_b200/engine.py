@@ -64,7 +64,7 @@ class CudaEnsemble:
 
     def __init__(self, n_chains: int, beta: float, sigma: Sequence[float], weight: Optional[Sequence[float]] = None,
                  *, seed: int = 1, chain_offset: int = 0, n_chains_total: int = 0, potential: str = "harmonic",
-                 rng: str = "philox", arith: str = "fast", device: int = -1, stream: int = 0):
+                 rng: str = "philox", arith: str = "fast", device: int = -1, stream: int = 0, dtype: str = "f64"):
         self._lib = L.load()
         sigma = [float(s) for s in np.atleast_1d(sigma)]
         weight = [1.0 / len(sigma)] * len(sigma) if weight is None else [float(w) for w in np.atleast_1d(weight)]
@@ -88,6 +88,8 @@ class CudaEnsemble:
         cfg.rng_mode = L.RNG_MODES[rng]
         cfg.arith_mode = L.ARITH_MODES[arith]
         cfg.stream = stream or None
+        cfg.dtype = L.DTYPES[dtype]
+        self.dtype = dtype
         self._h = C.c_void_p()
         L.check(None, self._lib.arianna_create(C.byref(cfg), C.byref(self._h)))
         self.n_chains = int(n_chains)
@@ -133,6 +135,19 @@ class CudaEnsemble:
         x = np.empty(self.n_chains, dtype=np.float64)
         e = np.empty(self.n_chains, dtype=np.float64) if with_energy else None
         self._ck(self._lib.arianna_get_state(self._h, _ptr(x), _ptr(e)))
+        return (x, e) if with_energy else x
+
+    def set_state_f32(self, x):
+        """Float32 ensembles: positions in their own element type (arianna_set_state_f32)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.shape != (self.n_chains,):
+            raise ValueError(f"x must have shape ({self.n_chains},)")
+        self._ck(self._lib.arianna_set_state_f32(self._h, _ptr(x)))
+
+    def get_state_f32(self, with_energy: bool = False):
+        x = np.empty(self.n_chains, dtype=np.float32)
+        e = np.empty(self.n_chains, dtype=np.float32) if with_energy else None
+        self._ck(self._lib.arianna_get_state_f32(self._h, _ptr(x), _ptr(e)))
         return (x, e) if with_energy else x
 
     def get_state_async(self, x_pinned_ptr: int):

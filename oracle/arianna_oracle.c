@@ -292,6 +292,112 @@ AO_API void ao_sweep_replay_betas(int64_t M, int64_t K, double *x, double *e, co
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Float32 ensembles: Particle{Float32}, Displacement{Float32}, ComponentArray(σ = 0.1f0)             */
+/* (example/particle_1d/particle_1d.jl:9-16,26-28: the system is generic in T<:AbstractFloat; mc_step!'s  */
+/* T is the PARAMETERS' element type, metropolis.jl:176).  Julia's promotion rules decide which        */
+/* operation runs in which precision [EXT Base/Distributions semantics, restated]:                    */
+/*   δ   = zero(δ) + σ*randn(rng, Float32)            Float32;  randn(rng, Float32) = Float32(randn(rng))  */
+/*   lq  = -(δ)^2 / (2σ^2)  -  log(2π*σ^2)/2          Float32 quotient  -  Float64 (2π is Float64)  => Float64 */
+/*   x  += δ;  e = x^2;  Δ = (-e)*β - (-e1)*β         Float32                                            */
+/*   α   = min(one(Float32), exp((Δ + lq_b) - lq_f))  Float64 (Float32 + Float64);  α > rand(rng) in Float64 */
+/* One IEEE operation per statement; compile with -ffp-contract=off (float expressions stay float:    */
+/* FLT_EVAL_METHOD == 0 on x86-64).                                                                   */
+/* ------------------------------------------------------------------------------------------------ */
+static inline float potential_f32(int pot, float x)
+{
+    switch (pot) {
+    default:
+    case AO_POT_HARMONIC: return x * x;
+    case AO_POT_QUARTIC: { float x2 = x * x; return x2 * x2; }
+    case AO_POT_DOUBLE_WELL: { float w = x * x - 1.0f; return w * w; }
+    }
+}
+
+/* log(2π·σ²)/2 for a Float32 σ: 2π*σ^2 = Float64(2π) * Float64(σ*σ)  (the Float32 square is promoted) */
+AO_API double ao_lognorm_f32(float sigma)
+{
+    float s2 = sigma * sigma;
+    return log(AO_TWO_PI * (double)s2) / 2.0;
+}
+
+static inline int mc_step_exact_f32(float *x, float *e, float beta, int pot, float sigma, double lognorm, double z64,
+                                    double u_acc, double *alpha_out)
+{
+    float z = (float)z64;                                  /* randn(rng, Float32) = Float32(randn(rng)) [EXT] */
+    float delta = 0.0f + (sigma * z);                      /* particle_1d.jl:57 */
+    float s2 = sigma * sigma;
+    float t1 = (-(delta * delta)) / (2.0f * s2);           /* :53, Float32 */
+    double lqf = (double)t1 - lognorm;                     /* Float32 - Float64 */
+    float e1 = *e;                                         /* :31 */
+    *x = *x + delta;                                       /* :32 */
+    *e = potential_f32(pot, *x);                           /* :33 */
+    float dlogp = ((-(*e)) * beta) - ((-e1) * beta);       /* metropolis.jl:98, Float32 */
+    delta = -delta;                                        /* particle_1d.jl:38 */
+    float t1b = (-(delta * delta)) / (2.0f * s2);
+    double lqb = (double)t1b - lognorm;                    /* metropolis.jl:182 */
+    double arg = ((double)dlogp + lqb) - lqf;              /* :183 */
+    double ex = exp(arg);
+    double alpha = (ex > 1.0) ? 1.0 : ex;                  /* min(one(Float32), ·) promotes to Float64 */
+    if (alpha_out) *alpha_out = alpha;
+    if (alpha > u_acc) return 1;                           /* :184 */
+    *x = *x + delta;                                       /* :187 */
+    *e = potential_f32(pot, *x);
+    return 0;
+}
+
+/* Replay sweep of a Float32 ensemble (single-move pool): draws are the SAME Float64 arrays as for Float64 ensembles
+ * (z is rounded to Float32 inside, as randn(rng, Float32) does). */
+AO_API void ao_sweep_replay_f32(int64_t M, int64_t K, float *x, float *e, float beta, const float *betas, int pot,
+                                float sigma, const double *z, const double *u_acc, int64_t *acc, uint8_t *decisions)
+{
+    double lognorm = ao_lognorm_f32(sigma);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < M; ++c) {
+        float xc = x[c], ec = e[c];
+        float b = betas ? betas[c] : beta;
+        for (int64_t s = 0; s < K; ++s) {
+            int d = mc_step_exact_f32(&xc, &ec, b, pot, sigma, lognorm, z[s * M + c], u_acc[s * M + c], NULL);
+            acc[c] += d;
+            if (decisions) decisions[s * M + c] = (uint8_t)d;
+        }
+        x[c] = xc;
+        e[c] = ec;
+    }
+}
+
+/* The engine's native Float32 stream (csrc/kernels_f32.cuh): tag 3, ONE block per pair of steps p = t >> 1, words
+ * (w0, w1, w2, w3): u1 = ((w0 >> 8) + 1/2) 2^-24, angle = w1 2^-32 turns, z(2p) = r cos, z(2p+1) = r sin with
+ * r = sqrt(-2 ln u1); accept uniforms w2 2^-32 and w3 2^-32.  The device evaluates the Box-Muller in FP32 on the MUFU
+ * pipe; here it is evaluated in Float64 libm and rounded: the two agree to ~1e-6 relative, so this only follows the
+ * device loosely (native-mode parity is statistical). */
+AO_API void ao_draws_philox_f32(int64_t seed, int64_t chain_offset, int64_t M, int64_t t0, int64_t K, double *z,
+                                double *u_acc)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < M; ++c) {
+        uint64_t sid = (uint64_t)(seed + chain_offset + c);
+        for (int64_t s = 0; s < K; ++s) {
+            uint64_t t = (uint64_t)(t0 + s), A, B;
+            philox_block(sid, t >> 1, 0, 3, &A, &B);
+            uint32_t w0 = (uint32_t)A, w1 = (uint32_t)(A >> 32), w2 = (uint32_t)B, w3 = (uint32_t)(B >> 32);
+            double u1 = ((double)(w0 >> 8) + 0.5) * 0x1.0p-24;
+            double r = sqrt(-2.0 * log(u1));
+            double a = AO_TWO_PI * ((double)w1 * 0x1.0p-32);
+            z[s * M + c] = (double)(float)((t & 1) ? r * sin(a) : r * cos(a));
+            u_acc[s * M + c] = (double)((t & 1) ? w3 : w2) * 0x1.0p-32;
+        }
+    }
+}
+
+/* callback_energy for Float32 chains: mean(system.e for system in chains) accumulates in Float32 [EXT Statistics]. */
+AO_API float ao_callback_energy_f32(int64_t M, const float *e)
+{
+    float s = 0.0f;
+    for (int64_t c = 0; c < M; ++c) s = s + e[c];
+    return s / (float)M;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Callbacks                                                                                         */
 /* ------------------------------------------------------------------------------------------------ */
 

@@ -45,6 +45,8 @@ def lib() -> C.CDLL:
         _lib.ao_xoshiro_rand.restype = C.c_double
         _lib.ao_xoshiro_randn.restype = C.c_double
         _lib.ao_num_threads.restype = C.c_int
+        _lib.ao_lognorm_f32.restype = C.c_double
+        _lib.ao_callback_energy_f32.restype = C.c_float
     return _lib
 
 
@@ -85,6 +87,15 @@ def draws_philox(seed, chain_offset, M, t0, K, with_cat=True):
     lib().ao_draws_philox(C.c_int64(seed), C.c_int64(chain_offset), C.c_int64(M), C.c_int64(t0), C.c_int64(K),
                           _p(uc, C.c_double), _p(z, C.c_double), _p(ua, C.c_double))
     return uc, z, ua
+
+
+def draws_philox_f32(seed, chain_offset, M, t0, K):
+    """The engine's native Float32 stream restated with libm (loose: the device uses MUFU Box-Muller): (z, u_acc)."""
+    z = np.empty((K, M), dtype=np.float64)
+    ua = np.empty((K, M), dtype=np.float64)
+    lib().ao_draws_philox_f32(C.c_int64(seed), C.c_int64(chain_offset), C.c_int64(M), C.c_int64(t0), C.c_int64(K),
+                              _p(z, C.c_double), _p(ua, C.c_double))
+    return z, ua
 
 
 def draws_pgmc_philox(seed, chain_offset, M, q0, n):
@@ -206,6 +217,42 @@ class Ensemble:
                               C.c_int(self.pot), _p(self.sigma, C.c_double), _p(ln, C.c_double),
                               _p(self.states, C.c_uint64), _p(gd, C.c_double))
         return gd
+
+
+class Ensemble32:
+    """M chains of Particle{Float32} with ONE Gaussian displacement move with Float32 parameters (σ = 0.1f0): the
+    Float32 instantiation of the reference's generic code (particle_1d.jl:9-16; promotion rules in arianna_oracle.c)."""
+
+    def __init__(self, x0, beta, sigma, potential=POT_HARMONIC):
+        self.x = np.ascontiguousarray(x0, dtype=np.float32).copy()
+        self.M = self.x.size
+        self.pot = int(potential)
+        x = self.x
+        self.e = (x * x if self.pot == POT_HARMONIC else (x * x) * (x * x) if self.pot == POT_QUARTIC
+                  else (x * x - np.float32(1)) * (x * x - np.float32(1))).astype(np.float32)
+        self.beta = np.float32(beta)
+        self.sigma = np.float32(sigma)
+        self.acc = np.zeros(self.M, dtype=np.int64)
+        self.tot = 0
+
+    def sweep_replay(self, z, u_acc, want_decisions=False, betas=None):
+        z, u_acc = _f64(z), _f64(u_acc)
+        K = z.shape[0]
+        assert z.shape == (K, self.M) and u_acc.shape == (K, self.M)
+        dec = np.empty((K, self.M), dtype=np.uint8) if want_decisions else None
+        b = None if betas is None else np.ascontiguousarray(betas, dtype=np.float32)
+        lib().ao_sweep_replay_f32(C.c_int64(self.M), C.c_int64(K), _p(self.x, C.c_float), _p(self.e, C.c_float),
+                                  C.c_float(self.beta), _p(b, C.c_float), C.c_int(self.pot), C.c_float(self.sigma),
+                                  _p(z, C.c_double), _p(u_acc, C.c_double), _p(self.acc, C.c_int64), _p(dec, C.c_uint8))
+        self.tot += K
+        return dec
+
+    def callback_energy(self):
+        return float(lib().ao_callback_energy_f32(C.c_int64(self.M), _p(self.e, C.c_float)))
+
+    def callback_acceptance(self):
+        with np.errstate(all="ignore"):
+            return float(np.sum(self.acc / np.float64(self.tot)) / self.M) if self.tot else float("nan")
 
 
 def learning_step(kind, p1, p2, gd_avg, theta):

@@ -2,7 +2,7 @@
 EXACT arithmetic, multi-move pools, replay (HBM-bound), the XOSHIRO device generator, the PGMC estimator (C4) and the
 trajectory write-back (C5).  Prints one JSON line per measurement; `scripts/gpu_paths.sh` stores them.  Every line
 carries the NVML clock / throttle-reason record sampled DURING its own timed region (bench.py's ClockSampler), CUDA
-events on the launching stream after warm-up, inputs larger than L2.  Optional argv: section names (native multi pgmc replay xoshiro c5)."""
+events on the launching stream after warm-up, inputs larger than L2.  Optional argv: section names (native f32 multi pgmc replay xoshiro c5)."""
 import json, os, sys, time
 import numpy as np
 import torch
@@ -58,6 +58,19 @@ def sec_native():
         eng.init_synthetic()
         ms = timed(eng, lambda: eng.sweep(10, reduce=True), reps=10)
         emit(path="K1 native EXACT single-move", M=M, K=10, ms=ms, chain_steps_per_s=M * 10 / (ms * 1e-3))
+
+
+def sec_f32():
+    # ---- Float32 ensembles (Particle{Float32}): FP32 Box-Muller on the MUFU pipe, x in 4 bytes ---------------------------
+    M = 1 << 27
+    for arith in ("fast", "exact"):
+        with mb.CudaEnsemble(M, 2.0, [0.1], seed=42, arith=arith, dtype="f32") as eng:
+            eng.init_synthetic()
+            for K in ((1, 10, 100) if arith == "fast" else (10,)):
+                ms = timed(eng, lambda: eng.sweep(K, reduce=True), reps=max(3, 100 // K))
+                emit(path=f"K1f native {arith.upper()} Float32 single-move", M=M, K=K, ms=ms,
+                     chain_steps_per_s=M * K / (ms * 1e-3), hbm_gbs=16 * M / (ms * 1e-3) / 1e9,
+                     hbm_frac=16 * M / (ms * 1e-3) / 1e9 / HBM)
 
 
 M4 = 1 << 24
@@ -153,7 +166,7 @@ def sec_c5():
         emit(path="C5 store interval without the write-back", M=M5, ms=ms0, chain_steps_per_s=M5 * 100 / (ms0 * 1e-3))
 
 
-SECTIONS = {"native": sec_native, "multi": sec_multi, "pgmc": sec_pgmc, "replay": sec_replay, "xoshiro": sec_xoshiro,
+SECTIONS = {"native": sec_native, "f32": sec_f32, "multi": sec_multi, "pgmc": sec_pgmc, "replay": sec_replay, "xoshiro": sec_xoshiro,
             "c5": sec_c5}
 
 

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/arianna_cuda.h but not exported"
     assert sorted(L.SYMBOLS) == names            # the ctypes table binds exactly the declared surface
-    assert L.load().arianna_abi_version() == 1
+    assert L.load().arianna_abi_version() == 2
 
 
 def test_library_is_sm100a_native():
