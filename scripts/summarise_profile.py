@@ -10,7 +10,9 @@ os.makedirs(out_dir, exist_ok=True)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
-keep = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+keep = ["Kernel Name", "gpu__time_duration.sum", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor", "sm__cycles_elapsed.max",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
@@ -63,11 +65,20 @@ def _val(name):
     i = hdr.index(name)
     v = float(data[0][i].replace(",", ""))
     return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[i]]
-series = int(sys.argv[2]) if len(sys.argv) > 2 else 16   # store intervals per launch of the profiled bench.py run
+series = int(sys.argv[2]) if len(sys.argv) > 2 else 11   # store intervals per launch of the profiled bench.py run
 inst = float(data[0][hdr.index("smsp__inst_executed.sum")].replace(",", ""))
+def _f(name):
+    return float(data[0][hdr.index(name)].replace(",", ""))
+# FP64 work the kernel really executes: thread-level DFMA (2 flop) + DMUL + DADD per elapsed cycle x elapsed cycles
+cycles = _f("sm__cycles_elapsed.max")
+flop = (2 * _f("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed") +
+        _f("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed") +
+        _f("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed")) * cycles
 json.dump({"chains": 1 << 27, "mc_steps": 10, "series": series,
            "warp_inst_per_warp_step": inst / ((1 << 27) / 32 * 10 * series),
            "issue_active_pct": float(data[0][hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")]),
+           "fp64_flop_per_chain_step": flop / ((1 << 27) * 10 * series),
+           "fp64_pipe_pct": _f("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
            "dram_bytes_per_launch": _val("dram__bytes_read.sum") + _val("dram__bytes_write.sum"),
            "source": f"profiles/{tag}_sweep_ncu_summary.md (ncu --set full, bench.py default shape)"},
           open(os.path.join(out_dir, "traffic.json"), "w"))
