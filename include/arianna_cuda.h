@@ -233,6 +233,27 @@ ARIANNA_API int32_t arianna_pgmc_read(arianna_handle *h, arianna_gradient_data *
 ARIANNA_API int32_t arianna_pgmc_reset(arianna_handle *h);
 ARIANNA_API int32_t arianna_pgmc_sums_device(arianna_handle *h, double **dptr, int32_t *n);
 
+/* PolicyGradientUpdate ON THE DEVICE (update.jl:50-57 + learning_step!, learning.jl:32-164): averages the accumulated
+ * GradientData of every learnable move (all-reduced over the communicator first when there is one), applies the move's
+ * optimiser, stores the new σ in a device-resident parameter block that every following sweep / estimator launch of
+ * this handle reads, and zeroes the accumulators -- no host round trip per update (asynchronous).  The host copy of θ
+ * is refreshed by arianna_params_sync / arianna_get_params, which also report (ARIANNA_ERR_INVALID) a step that left
+ * σ outside (0, ∞), as Normal(0, σ) would throw in the reference.  p1 = η (VPG, BLPG, NPG) or δ (BLAPG, ANPG,
+ * BLANPG); p2 = ϵid.  Float64 ensembles with the native Philox stream. */
+enum arianna_optimiser_kind {
+    ARIANNA_OPT_STATIC = 0, ARIANNA_OPT_VPG = 1, ARIANNA_OPT_BLPG = 2, ARIANNA_OPT_BLAPG = 3, ARIANNA_OPT_NPG = 4,
+    ARIANNA_OPT_ANPG = 5, ARIANNA_OPT_BLANPG = 6
+};
+typedef struct arianna_optimiser {
+    int32_t kind;                /* enum arianna_optimiser_kind                                            */
+    int32_t reserved;
+    double p1;
+    double p2;
+} arianna_optimiser;
+ARIANNA_API int32_t arianna_pgmc_update_device(arianna_handle *h, const int32_t *learn_ids, const arianna_optimiser *opts,
+                                               int32_t n_learn);
+ARIANNA_API int32_t arianna_params_sync(arianna_handle *h);
+
 /* Page-locked host memory for hosts without a CUDA binding of their own: what arianna_run_host_job and
  * arianna_get_state_async need for their copies to be asynchronous.  write_combined != 0: memory the host only WRITES
  * and the GPU reads (x_in) -- not snooped, faster over PCIe, very slow to read back on the CPU. */

@@ -47,6 +47,13 @@ class GradientData(C.Structure):
                 ("n", C.c_double)]
 
 
+class Optimiser(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("p1", C.c_double), ("p2", C.c_double)]
+
+
+OPT_KINDS = {"Static": 0, "VPG": 1, "BLPG": 2, "BLAPG": 3, "NPG": 4, "ANPG": 5, "BLANPG": 6}
+
+
 class AriannaError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libarianna_cuda error {code}: {msg}")
@@ -95,6 +102,8 @@ SYMBOLS = {
     "arianna_pgmc_estimate_replay": (C.c_int32, [_H, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_int32]),
     "arianna_pgmc_read": (C.c_int32, [_H, C.POINTER(GradientData), C.c_int32]),
     "arianna_pgmc_reset": (C.c_int32, [_H]),
+    "arianna_pgmc_update_device": (C.c_int32, [_H, C.POINTER(C.c_int32), C.POINTER(Optimiser), C.c_int32]),
+    "arianna_params_sync": (C.c_int32, [_H]),
     "arianna_pgmc_sums_device": (C.c_int32, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "arianna_get_stream": (C.c_int32, [_H, C.POINTER(C.c_void_p)]),
     "arianna_synchronize": (C.c_int32, [_H]),

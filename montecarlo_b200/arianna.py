@@ -238,9 +238,17 @@ class ParticleEnsemble(AriannaSystem):
             self.engine.set_rng_state(st)
 
     def _push_params(self):
+        if getattr(self, "_params_on_device", False):
+            return                       # the on-device optimiser owns σ: the host copies are refreshed by pull_params
         for k, m in enumerate(self.pool):
             if self.engine.get_params(k) != m.parameters.σ:
                 self.engine.set_params(k, m.parameters.σ)
+
+    def pull_params(self):
+        """Refresh the host Moves' σ from the device (only needed after PolicyGradientUpdate(on_device=True))."""
+        if getattr(self, "_params_on_device", False):
+            for k, m in enumerate(self.pool):
+                m.parameters.σ = self.engine.get_params(k)      # (the first call synchronises and pulls the whole block)
 
     def flush(self, reduce: bool = False):
         """Run the pending Metropolis steps as one fused launch."""
@@ -643,6 +651,7 @@ class StoreParameters(AriannaAlgorithm):
             self.make_step(simulation)
 
     def make_step(self, simulation):
+        simulation.chains.pull_params()                          # no-op unless the optimiser runs on the device
         for f, p in zip(self.files, self.parameters_list):
             f.write(f"{simulation.t} {_jl(list(p.data))}\n")
             f.flush()
@@ -784,6 +793,7 @@ def run(simulation: Simulation):
                     counters[k] = ck + 1
         sim.chains.flush()
         sim.chains.engine.synchronize()
+        sim.chains.pull_params()
         sim.sim_time = time.perf_counter() - t0
         if sim.chains.rank == 0:
             with open(os.path.join(sim.path, "summary.log"), "a") as f:

@@ -122,6 +122,9 @@ struct arianna_handle {
     double *d_coll = nullptr;       // [kMaxMoves * 5] staging of the tiny all-reduces
 
     PoolParams pool{};
+    DevTheta *d_theta = nullptr;    // device-resident θ block (on-device optimiser); mirrors `pool` when active
+    bool theta_active = false;      // the kernels read θ from d_theta
+    bool theta_dirty = false;       // the device copy is ahead of `pool` (arianna_params_sync pulls it)
     int64_t steps_done = 0;         // MC steps done per chain == draw index base == total_calls (single move)
     int64_t pgmc_samples = 0;       // estimator samples drawn per chain
     int64_t launches = 0;
@@ -170,6 +173,52 @@ double host_inv2s2(double sigma)
 {
     const double d = 2.0 * (sigma * sigma);
     return (d >= 0x1p-300 && d <= 0x1p300) ? 1.0 / d : 0.0;
+}
+
+// host pool -> device θ block (whole block; tiny)
+int32_t push_theta(arianna_handle *h)
+{
+    DevTheta t{};
+    for (int k = 0; k < kMaxMoves; ++k) {
+        t.sigma[k] = h->pool.sigma[k];
+        t.lognorm[k] = h->pool.lognorm[k];
+        t.inv2s2[k] = h->pool.inv2s2[k];
+    }
+    if (!h->d_theta && cudaMalloc(&h->d_theta, sizeof(DevTheta)) != cudaSuccess) {
+        cudaGetLastError();
+        h->err = "device parameter block allocation failed";
+        return ARIANNA_ERR_NOMEM;
+    }
+    // (synchronous on purpose: `t` lives on this stack frame)
+    if (cudaMemcpyAsync(h->d_theta, &t, sizeof t, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        h->err = std::string("device parameter upload: ") + cudaGetErrorString(cudaGetLastError());
+        return ARIANNA_ERR_CUDA;
+    }
+    return ARIANNA_OK;
+}
+
+// device θ block -> host pool (synchronises); reports an optimiser step that left (0, ∞)
+int32_t pull_theta(arianna_handle *h)
+{
+    if (!h->theta_active || !h->theta_dirty) return ARIANNA_OK;
+    DevTheta t{};
+    if (cudaMemcpyAsync(&t, h->d_theta, sizeof t, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        h->err = std::string("device parameter download: ") + cudaGetErrorString(cudaGetLastError());
+        return ARIANNA_ERR_CUDA;
+    }
+    for (int k = 0; k < h->pool.n_moves; ++k) {
+        h->pool.sigma[k] = t.sigma[k];
+        h->pool.lognorm[k] = t.lognorm[k];
+        h->pool.inv2s2[k] = t.inv2s2[k];
+    }
+    h->theta_dirty = false;
+    if (t.bad) {
+        h->err = "arianna_pgmc_update_device: an optimiser step left sigma outside (0, inf) (Normal(0, sigma) throws in the reference)";
+        return ARIANNA_ERR_INVALID;
+    }
+    return ARIANNA_OK;
 }
 
 int grid_for(const arianna_handle *h, int64_t M, int ctas_per_sm)
@@ -470,7 +519,7 @@ int32_t arianna_destroy(arianna_handle *h)
     cudaFree(h->d_ki); cudaFree(h->d_wi); cudaFree(h->d_fi); cudaFree(h->d_partials); cudaFree(h->d_ticket);
     cudaFree(h->d_sums); cudaFree(h->d_gd); cudaFree(h->d_csum); cudaFree(h->d_scratch); cudaFree(h->d_tables);
     cudaFree(h->d_series); cudaFree(h->d_series_partials); cudaFree(h->d_cat_table);
-    cudaFree(h->d_pgmc_partials); cudaFree(h->d_pgmc_ticket);
+    cudaFree(h->d_pgmc_partials); cudaFree(h->d_pgmc_ticket); cudaFree(h->d_theta);
     if (h->coll_stream) cudaStreamSynchronize(h->coll_stream);
     if (h->comm) { nccl::g_api.CommDestroy(h->comm); h->comm = nullptr; }
     cudaFree(h->d_coll);
@@ -702,6 +751,15 @@ int32_t arianna_set_params(arianna_handle *h, int32_t move_id, const double *the
     h->pool.sigma[move_id] = theta[0];
     h->pool.lognorm[move_id] = log_norm ? *log_norm : host_lognorm(theta[0]);
     h->pool.inv2s2[move_id] = host_inv2s2(theta[0]);
+    if (h->theta_active) {          // keep the device-resident block coherent (pull first: other moves may be ahead there)
+        DeviceGuard guard(h->device);
+        const double s0 = h->pool.sigma[move_id], l0 = h->pool.lognorm[move_id], i0 = h->pool.inv2s2[move_id];
+        int32_t rc = pull_theta(h);
+        if (rc) return rc;
+        h->pool.sigma[move_id] = s0; h->pool.lognorm[move_id] = l0; h->pool.inv2s2[move_id] = i0;
+        rc = push_theta(h);
+        if (rc) return rc;
+    }
     if (h->f32) {
         const float s32 = (float)theta[0], s2 = s32 * s32;
         h->lognorm_f32 = log_norm ? *log_norm : std::log(6.283185307179586 * (double)s2) / 2.0;
@@ -714,6 +772,11 @@ int32_t arianna_get_params(arianna_handle *h, int32_t move_id, double *theta, in
     if (!h) return ARIANNA_ERR_INVALID;
     REQUIRE(h, move_id >= 0 && move_id < h->pool.n_moves, "arianna_get_params: move_id out of range");
     REQUIRE(h, theta != nullptr && P == 1, "arianna_get_params: StandardGaussian has exactly one parameter (σ)");
+    {
+        DeviceGuard guard(h->device);
+        const int32_t rc = pull_theta(h);       // the on-device optimiser may be ahead of the host copy
+        if (rc) return rc;
+    }
     theta[0] = h->pool.sigma[move_id];
     return ARIANNA_OK;
 }
@@ -756,6 +819,7 @@ static int32_t launch_multi(arianna_handle *h, int64_t off, int64_t m, int64_t t
     for (int j = 0; j < kMaxMoves; ++j) mp.cat_thr[j] = h->cat_thr[j];
     mp.cat_n = h->cat_n;
     mp.pool = h->pool;
+    mp.theta = h->theta_active ? h->d_theta : nullptr;
     mp.n_int = n_int; mp.record = out ? 1 : 0;
     bool even = (t0 & 1) == 0;
     for (int i = 0; i < n_int; ++i) {
@@ -808,6 +872,10 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
     const bool multi = h->pool.n_moves > 1;
     const bool want_reduce = (flags & ARIANNA_SWEEP_REDUCE) != 0;
     if (K == 0) return want_reduce ? launch_callback_reduce(h) : ARIANNA_OK;
+    if (h->f32 || h->cfg.rng_mode != ARIANNA_RNG_PHILOX) {           // (these paths pass θ by value)
+        const int32_t rcp = pull_theta(h);
+        if (rcp) return rcp;
+    }
     const size_t smem = multi ? sizeof(uint32_t) * 2 * h->pool.n_moves * kBlock : 0;
     const bool exact = h->cfg.arith_mode == ARIANNA_ARITH_EXACT;
     time_mark(h, 0, true);
@@ -857,6 +925,7 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
         sp.partials = h->d_partials; sp.ticket = h->d_ticket; sp.sums = h->d_sums;
         sp.tables = h->d_tables;
         sp.pool = h->pool;
+        sp.theta = h->theta_active ? h->d_theta : nullptr;
         // the Philox sweep keeps its math tables in dynamic shared memory (one pinned base register, kernels.cuh)
         const size_t psmem = sizeof(m64::MathTables);
         auto launch = [&](auto kernel) -> int32_t {
@@ -867,11 +936,12 @@ int32_t arianna_sweep(arianna_handle *h, int64_t K, uint32_t flags)
         };
         const int32_t rc = dispatch_pot(h->cfg.potential, [&](auto pot) -> int32_t {
             constexpr int POT = decltype(pot)::value;
+            const bool generic = h->d_betas || h->theta_active;     // per-chain β and / or σ read from the device
             if (exact) {
-                if (h->d_betas) return launch(sweep_philox_kernel<POT, ARITH_EXACT>);
+                if (generic) return launch(sweep_philox_kernel<POT, ARITH_EXACT>);
                 return launch(sweep_philox_kernel<POT, ARITH_EXACT, false, false>);
             }
-            if (h->d_betas) return launch(sweep_philox_kernel<POT, ARITH_FAST>);
+            if (generic) return launch(sweep_philox_kernel<POT, ARITH_FAST>);
             return launch(sweep_philox_kernel<POT, ARITH_FAST, false, false>);
         });
         if (rc) return rc;
@@ -977,6 +1047,7 @@ static int32_t series_range(arianna_handle *h, int64_t off, int64_t m, int64_t t
         sp.sid0 = (uint64_t)(h->cfg.seed + h->cfg.chain_offset + off);
         sp.tables = h->d_tables;
         sp.pool = h->pool;
+        sp.theta = h->theta_active ? h->d_theta : nullptr;
         sp.n_series = ns;
         SeriesK sk{};
         int64_t k_launch = 0;
@@ -1002,7 +1073,7 @@ static int32_t series_range(arianna_handle *h, int64_t off, int64_t m, int64_t t
                 kernel<<<grid, kBlock, smem, h->stream>>>(sp);
                 return ARIANNA_OK;
             };
-            if (h->d_betas)
+            if (h->d_betas || h->theta_active)
                 return exact ? go(sweep_philox_kernel<POT, ARITH_EXACT, true, true>)
                              : go(sweep_philox_kernel<POT, ARITH_FAST, true, true>);
             return exact ? go(sweep_philox_kernel<POT, ARITH_EXACT, true, false>)
@@ -1241,6 +1312,7 @@ int32_t arianna_sweep_replay(arianna_handle *h, int64_t K, const double *u_cat, 
     REQUIRE(h, !multi || u_cat != nullptr, "arianna_sweep_replay: u_cat is required for multi-move pools");
     REQUIRE(h, h->steps_done + K <= 0xFFFFFFFFll, "arianna_sweep_replay: per-chain counters are 32-bit");
     DeviceGuard guard(h->device);
+    { const int32_t rcp = pull_theta(h); if (rcp) return rcp; }      // (this path passes θ by value)
     const size_t smem = multi ? sizeof(uint32_t) * 2 * h->pool.n_moves * kBlock : 0;
 
     auto launch = [&](int64_t k, const double *duc, const double *dz, const double *dua, uint8_t *ddec) -> int32_t {
@@ -1622,7 +1694,9 @@ static int32_t pgmc_impl(arianna_handle *h, int32_t q_batch, const int32_t *lear
         for (int l = 0; l < n_learn; ++l) {
             pp.sigma[l] = h->pool.sigma[learn_ids[l]];
             pp.lognorm[l] = h->pool.lognorm[learn_ids[l]];
+            pp.learn_id[l] = learn_ids[l];
         }
+        pp.theta = h->theta_active ? h->d_theta : nullptr;
         pp.z = replay ? dz : nullptr;
         pp.gd = h->d_gd;
         pp.tables = h->d_tables;
@@ -1694,6 +1768,44 @@ int32_t arianna_pgmc_reset(arianna_handle *h)
     DeviceGuard guard(h->device);
     CU_TRY(h, cudaMemsetAsync(h->d_gd, 0, sizeof(double) * kMaxMoves * 5, h->stream));
     return ARIANNA_OK;
+}
+
+int32_t arianna_pgmc_update_device(arianna_handle *h, const int32_t *learn_ids, const arianna_optimiser *opts, int32_t n_learn)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    REQUIRE(h, n_learn >= 0 && n_learn <= kMaxMoves && (n_learn == 0 || (learn_ids && opts)),
+            "arianna_pgmc_update_device: bad arguments");
+    if (h->f32) return fail(h, ARIANNA_ERR_UNSUPPORTED, "arianna_pgmc_update_device: Float64 ensembles only");
+    if (n_learn == 0) return ARIANNA_OK;
+    UpdateParams u{};
+    u.n_learn = n_learn;
+    for (int l = 0; l < n_learn; ++l) {
+        REQUIRE(h, learn_ids[l] >= 0 && learn_ids[l] < h->pool.n_moves, "arianna_pgmc_update_device: learn id out of range");
+        REQUIRE(h, opts[l].kind >= ARIANNA_OPT_STATIC && opts[l].kind <= ARIANNA_OPT_BLANPG,
+                "arianna_pgmc_update_device: unknown optimiser");
+        u.learn_id[l] = learn_ids[l]; u.kind[l] = opts[l].kind; u.p1[l] = opts[l].p1; u.p2[l] = opts[l].p2;
+    }
+    DeviceGuard guard(h->device);
+    if (!h->theta_active) {
+        const int32_t rc = push_theta(h);
+        if (rc) return rc;
+        h->theta_active = true;
+    }
+    // gradients_data summed over all ranks, in place (every rank then applies the same step to its own θ block)
+    if (h->comm)
+        NCCL_TRY(h, nccl::g_api.AllReduce(h->d_gd, h->d_gd, (size_t)5 * n_learn, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->comm, h->stream));
+    pgmc_update_kernel<<<1, 32, 0, h->stream>>>(h->d_theta, h->d_gd, u);
+    CU_TRY(h, cudaGetLastError());
+    ++h->launches;
+    h->theta_dirty = true;
+    return ARIANNA_OK;
+}
+
+int32_t arianna_params_sync(arianna_handle *h)
+{
+    if (!h) return ARIANNA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    return pull_theta(h);
 }
 
 int32_t arianna_pgmc_sums_device(arianna_handle *h, double **dptr, int32_t *n)

@@ -58,6 +58,16 @@ struct PoolParams {
     double inv2s2[kMaxMoves];   // RN(1 / (2·(σ·σ))), host-computed, or 0 when σ is outside the range exact_div covers
 };
 
+// Device-resident policy parameters θ = (σ) of every move + the per-move constants derived from them: written by
+// pgmc_update_kernel (on-device optimiser), read by the sweep / estimator kernels instead of the by-value PoolParams
+// when a handle runs its PolicyGradientUpdate on the device (no host round trip per update).
+struct DevTheta {
+    double sigma[kMaxMoves];
+    double lognorm[kMaxMoves];
+    double inv2s2[kMaxMoves];
+    int bad;                    // set when an update left σ outside (0, ∞) (Normal(0, σ) would throw in the reference)
+};
+
 struct SweepParams {
     double *x;
     uint32_t *acc;
@@ -74,6 +84,7 @@ struct SweepParams {
     double *sums;           // [2 + n_moves]
     const m64::MathTables *tables;  // exp/log tables in global memory (copied to shared by every CTA)
     PoolParams pool;
+    const DevTheta *theta;          // non-null: σ lives on the device (read by the BETAS = true instantiations only)
     // series mode (sweep_philox_kernel<..., SERIES = true>): n_series store intervals fused into ONE launch
     int n_series;
     int series_even;                // every interval is a positive even number of steps starting on an even step
@@ -333,7 +344,11 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
     double sum_e = 0.0;
     unsigned long long sum_acc = 0ull;   // Σ accepted_calls: exact in integers; every chain shares tot = tend
     uint32_t cnt = 0;
-    const double sigma0 = p.pool.sigma[0], lognorm0 = p.pool.lognorm[0], inv0 = p.pool.inv2s2[0];
+    // (the BETAS = false instantiation -- the headline kernel -- keeps σ as a constant-bank operand; a handle whose
+    // optimiser runs on the device is routed to the BETAS = true one)
+    const bool dev = BETAS && p.theta != nullptr;
+    const double sigma0 = dev ? p.theta->sigma[0] : p.pool.sigma[0], lognorm0 = dev ? p.theta->lognorm[0] : p.pool.lognorm[0],
+                 inv0 = dev ? p.theta->inv2s2[0] : p.pool.inv2s2[0];
     // Steps are consumed in Box-Muller pairs (pair index = step >> 1).  A run of steps [ta, tb) that starts on an odd
     // step uses only the sine half of its first pair and one that ends on an even step only the cosine half of its
     // last, so the result does not depend on how the steps are chunked into launches or store intervals.
@@ -839,6 +854,8 @@ struct PgmcParams {
     uint64_t sid0;
     double sigma[kMaxMoves];     // of the learnable moves, in order
     double lognorm[kMaxMoves];
+    int learn_id[kMaxMoves];     // pool index of each learnable move
+    const DevTheta *theta;       // non-null: σ lives on the device
     const double *z;      // replay only
     double *partials;     // [n_learn][gridDim.x][5]
     unsigned int *ticket; // [n_learn]
@@ -894,7 +911,8 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_PGMC_MINB) pgmc_kernel(const P
     const m64::Tab tb = shared_tab(&s_T);
 #pragma unroll 1
     for (int l = 0; l < p.n_learn; ++l) {
-        const double sigma = p.sigma[l], lognorm = p.lognorm[l];
+        const double sigma = p.theta ? p.theta->sigma[p.learn_id[l]] : p.sigma[l];
+        const double lognorm = p.theta ? p.theta->lognorm[p.learn_id[l]] : p.lognorm[l];
         const int64_t q0 = p.q0 + (int64_t)l * p.q_batch, qend = q0 + p.q_batch;
         double sj = 0.0, sdj = 0.0, sgf = 0.0, sg = 0.0, sn = 0.0;
         for (int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x; c < p.M; c += (int64_t)gridDim.x * kBlock) {
@@ -936,6 +954,67 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_PGMC_MINB) pgmc_kernel(const P
         __syncthreads();                       // the reduction's shared scratch is reused from move to move
         block_reduce_and_finish<5>(vals, 5, p.partials + (size_t)l * gridDim.x * 5, p.ticket + l, p.gd + 5 * l, true);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PolicyGradientUpdate on the device (update.jl:50-57 + learning.jl): thread l averages the accumulated GradientData of
+// learnable move l (gradients.jl:83-85), applies its optimiser's learning_step! -- the six rules restated operation by
+// operation as oracle/arianna_oracle.c:ao_learning_step, IEEE sqrt / division, nothing contracted -- writes σ and the
+// constants derived from it to the device-resident parameter block, and zeroes the accumulator (update.jl:55).
+// ---------------------------------------------------------------------------------------------------------
+enum { OPT_STATIC = 0, OPT_VPG = 1, OPT_BLPG = 2, OPT_BLAPG = 3, OPT_NPG = 4, OPT_ANPG = 5, OPT_BLANPG = 6 };
+struct UpdateParams {
+    int n_learn;
+    int learn_id[kMaxMoves];
+    int kind[kMaxMoves];
+    double p1[kMaxMoves];   // η (VPG, BLPG, NPG) or δ (BLAPG, ANPG, BLANPG)
+    double p2[kMaxMoves];   // ϵid
+};
+
+__global__ void pgmc_update_kernel(DevTheta *th, double *gd, const UpdateParams u)
+{
+    const int l = threadIdx.x;
+    if (l >= u.n_learn) return;
+    const int k = u.learn_id[l];
+    const double n = gd[5 * l + 4];
+    const double j = __ddiv_rn(gd[5 * l], n), dj = __ddiv_rn(gd[5 * l + 1], n), glq = __ddiv_rn(gd[5 * l + 2], n),
+                 g = __ddiv_rn(gd[5 * l + 3], n);
+    const double theta = th->sigma[k], p1 = u.p1[l], p2 = u.p2[l];
+    double out = theta;
+    switch (u.kind[l]) {
+    case OPT_VPG: out = __dadd_rn(theta, __dmul_rn(p1, dj)); break;                                        // learning.jl:32-34
+    case OPT_BLPG: out = __dadd_rn(theta, __dmul_rn(p1, __dsub_rn(dj, __dmul_rn(j, glq)))); break;         // :50-52
+    case OPT_BLAPG: {                                                                                      // :76-79
+        const double eta = __dsqrt_rn(__ddiv_rn(__dmul_rn(2.0, p1), __dadd_rn(__dmul_rn(dj, dj), p2)));
+        out = __dadd_rn(theta, __dmul_rn(eta, __dsub_rn(dj, __dmul_rn(j, glq))));
+        break;
+    }
+    case OPT_NPG: {                                                                                        // :103-105
+        const double Finv = __ddiv_rn(1.0, __dadd_rn(g, __dmul_rn(p2, 1.0)));
+        out = __dadd_rn(theta, __dmul_rn(__dmul_rn(p1, Finv), dj));
+        break;
+    }
+    case OPT_ANPG: {                                                                                       // :130-134
+        const double Finv = __ddiv_rn(1.0, __dadd_rn(g, __dmul_rn(p2, 1.0)));
+        const double eta = __dsqrt_rn(__ddiv_rn(__dmul_rn(2.0, p1), __dmul_rn(dj, __dmul_rn(Finv, dj))));
+        out = __dadd_rn(theta, __dmul_rn(__dmul_rn(eta, Finv), dj));
+        break;
+    }
+    case OPT_BLANPG: {                                                                                     // :159-164
+        const double Finv = __ddiv_rn(1.0, __dadd_rn(g, __dmul_rn(p2, 1.0)));
+        const double bj = __dsub_rn(dj, __dmul_rn(j, glq));
+        const double eta = __dsqrt_rn(__ddiv_rn(__dmul_rn(2.0, p1), __dmul_rn(bj, __dmul_rn(Finv, bj))));
+        out = __dadd_rn(theta, __dmul_rn(__dmul_rn(eta, Finv), bj));
+        break;
+    }
+    default: break;                                                                                        // Static
+    }
+    th->sigma[k] = out;
+    const double s2 = __dmul_rn(out, out), d = __dmul_rn(2.0, s2);
+    th->lognorm[k] = __ddiv_rn(log(__dmul_rn(6.283185307179586, s2)), 2.0);      // particle_1d.jl:53
+    th->inv2s2[k] = (d >= 0x1p-300 && d <= 0x1p300) ? __ddiv_rn(1.0, d) : 0.0;
+    if (!(out > 0.0) || isinf(out)) atomicOr(&th->bad, 1);
+    for (int i = 0; i < 5; ++i) gd[5 * l + i] = 0.0;
 }
 
 // K5: synthetic initial condition x0 = 4u − 2 (MC_harmonic_oscillator.jl:13) from stream tag 0.

@@ -44,6 +44,7 @@ struct MultiParams {
     uint32_t cat_thr[kMaxMoves];            // T_j = min(ceil(cp_j 2^32), 2^32 - 1), j < n_moves - 1
     int cat_n;                              // thresholds below 2^32 (the others can never be reached by a 32-bit word)
     PoolParams pool;
+    const DevTheta *theta;          // non-null: σ (and the constants derived from it) live on the device
     int n_int;                      // intervals of this launch (>= 1)
     int record;                     // 1: a callback record after every interval
     int even;                       // every interval is a positive even number of steps starting on an even step
@@ -100,9 +101,10 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MULTI_MINB) sweep_multi_kernel
         uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + kOffCat);
         for (int i = threadIdx.x; i < kCatBuckets / 16; i += kBlock) dst[i] = src[i];
         if (threadIdx.x < kMaxMoves) {
-            reinterpret_cast<double *>(smem_raw + kOffSigma)[threadIdx.x] = p.pool.sigma[threadIdx.x];
-            reinterpret_cast<double *>(smem_raw + kOffLognorm)[threadIdx.x] = p.pool.lognorm[threadIdx.x];
-            reinterpret_cast<double *>(smem_raw + kOffInv)[threadIdx.x] = p.pool.inv2s2[threadIdx.x];
+            const int i = threadIdx.x;
+            reinterpret_cast<double *>(smem_raw + kOffSigma)[i] = p.theta ? p.theta->sigma[i] : p.pool.sigma[i];
+            reinterpret_cast<double *>(smem_raw + kOffLognorm)[i] = p.theta ? p.theta->lognorm[i] : p.pool.lognorm[i];
+            reinterpret_cast<double *>(smem_raw + kOffInv)[i] = p.theta ? p.theta->inv2s2[i] : p.pool.inv2s2[i];
             reinterpret_cast<uint32_t *>(smem_raw + kOffThr)[threadIdx.x] = p.cat_thr[threadIdx.x];
         }
         if (p.record)

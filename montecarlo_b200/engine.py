@@ -350,6 +350,20 @@ class CudaEnsemble:
     def pgmc_reset(self):
         self._ck(self._lib.arianna_pgmc_reset(self._h))
 
+    def pgmc_update_device(self, learn_ids: Sequence[int], optimisers):
+        """PolicyGradientUpdate on the device (arianna_pgmc_update_device): `optimisers` = one (kind, p1, p2) per
+        learnable move, kind a name of learning.jl ("VPG", "BLPG", "BLAPG", "NPG", "ANPG", "BLANPG", "Static").
+        Asynchronous; get_params / params_sync refresh the host copy."""
+        n = len(learn_ids)
+        ids = (C.c_int32 * n)(*[int(i) for i in learn_ids])
+        opts = (L.Optimiser * n)()
+        for o, (kind, p1, p2) in zip(opts, optimisers):
+            o.kind, o.p1, o.p2 = L.OPT_KINDS[kind], float(p1), float(p2)
+        self._ck(self._lib.arianna_pgmc_update_device(self._h, ids, opts, n))
+
+    def params_sync(self):
+        self._ck(self._lib.arianna_params_sync(self._h))
+
     def pgmc_sums_tensor(self):
         import torch
         p = C.c_void_p()

@@ -188,10 +188,27 @@ class PolicyGradientEstimator(AriannaAlgorithm):
         io.write(f"\t\tQ batch size: {self.q_batch_size}\n\t\tAD backend: analytic (CUDA)\n\t\tSeed: {self.seed}\n")
 
 
-class PolicyGradientUpdate(AriannaAlgorithm):
-    """PolicyGradientUpdate(chains; dependencies=(PolicyGradientEstimator,)) (update.jl:14-67)."""
+def _opt_tuple(opt: PolicyGradient):
+    """(kind, p1, p2) of an optimiser for arianna_pgmc_update_device."""
+    if isinstance(opt, (VPG, BLPG)):
+        return type(opt).__name__, opt.η, 0.0
+    if isinstance(opt, NPG):
+        return "NPG", opt.η, opt.ϵid
+    if isinstance(opt, (BLAPG, ANPG, BLANPG)):
+        return type(opt).__name__, opt.δ, opt.ϵid
+    return "Static", 0.0, 0.0
 
-    def __init__(self, chains, *, dependencies=None, **extras):
+
+class PolicyGradientUpdate(AriannaAlgorithm):
+    """PolicyGradientUpdate(chains; dependencies=(PolicyGradientEstimator,)) (update.jl:14-67).
+
+    on_device=True (extension): the averaging, the learning_step! of every learnable move and the reset of the
+    accumulators run in ONE tiny kernel on the device (arianna_pgmc_update_device), the sweeps read σ from a
+    device-resident block, and the host only pulls σ when something asks for it (StoreParameters, the end of the run):
+    no all-reduce read-back and no host synchronisation per update."""
+
+    def __init__(self, chains, *, dependencies=None, on_device: bool = False, **extras):
+        self.on_device = bool(on_device)
         assert dependencies is not None and len(dependencies) == 1        # update.jl:43-44
         assert isinstance(dependencies[0], PolicyGradientEstimator)
         self.pge = dependencies[0]
@@ -201,6 +218,18 @@ class PolicyGradientUpdate(AriannaAlgorithm):
 
     def make_step(self, simulation):                                      # update.jl:50-57
         ch = simulation.chains
+        if self.on_device and hasattr(ch.engine, "pgmc_update_device"):
+            dist = _dist()
+            if dist is not None and dist.get_world_size() > 1:
+                # gradients_data summed over the ranks IN PLACE on the device, then the same update everywhere
+                import torch
+                with torch.cuda.stream(ch.engine.torch_stream()):
+                    dist.all_reduce(ch.engine.pgmc_sums_tensor())
+            ch._push_params()
+            ch.engine.pgmc_update_device(self.learn_ids, [_opt_tuple(self.optimisers[k]) for k in self.learn_ids])
+            ch._params_on_device = True
+            self.pge.steps_since_update = 0
+            return
         gds = self.pge.gradients_data()
         for k, lid in enumerate(self.learn_ids):
             gd = average(gds[k])

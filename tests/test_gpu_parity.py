@@ -672,6 +672,60 @@ def test_pgmc_learns_sigma_through_the_driver(tmp_path):
     assert all(abs(s - 1.2) < 0.2 for s in sig[1:]), sig
 
 
+def test_on_device_optimiser_matches_host_updates(tmp_path):
+    """PolicyGradientUpdate(on_device=True): averaging + learning_step! + reset in one device kernel, σ kept in a
+    device-resident block read by the sweeps and the estimator -- against the host path (read-back, Python
+    learning_step, set_params) on the same seeds: identical chains, identical counters, σ histories equal to the last
+    bit (the six rules are restated operation by operation, IEEE sqrt / division), and each rule equal to the oracle's
+    ao_learning_step on the same averaged record."""
+    M, steps, burn = 1 << 14, 120, 20
+    optimisers = (PG.Static(), PG.VPG(0.05), PG.BLPG(0.05), PG.BLAPG(2e-3, 1e-6), PG.NPG(0.5, 1e-6),
+                  PG.ANPG(2e-3, 1e-6), PG.BLANPG(2e-3, 1e-6))
+
+    def run(path, on_device):
+        chains = mb.ParticleEnsemble(n_chains=M, beta=2.0)
+        mk = lambda w: mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=0.2), w)
+        pool = (mk(0.4), mk(0.1), mk(0.1), mk(0.1), mk(0.1), mk(0.1), mk(0.1))
+        sim = mb.Simulation(chains, (
+            dict(algorithm=mb.Metropolis, pool=pool, seed=42),
+            dict(algorithm=PG.PolicyGradientEstimator, dependencies=(mb.Metropolis,), optimisers=optimisers, q_batch_size=10),
+            dict(algorithm=PG.PolicyGradientUpdate, dependencies=(PG.PolicyGradientEstimator,),
+                 scheduler=mb.build_schedule(steps, burn, 2), on_device=on_device),
+            dict(algorithm=mb.StoreParameters, dependencies=(mb.Metropolis,), scheduler=mb.build_schedule(steps, burn, 10)),
+        ), steps, path=str(path))
+        mb.run(sim)
+        hist = [open(path / "parameters" / str(k + 1) / "parameters.dat").read() for k in range(7)]
+        return chains.x, chains.engine.chain_counters(), [m.parameters.σ for m in pool], hist, chains.engine.launch_count
+
+    xh, ch, sh, hh, _ = run(tmp_path / "host", False)
+    xd, cd, sd, hd, _ = run(tmp_path / "dev", True)
+    assert sh[0] == sd[0] == 0.2 and all(s != 0.2 for s in sd[1:])
+    assert sd == sh                                               # final σ, bit for bit
+    assert hd == hh                                               # every stored σ along the way, byte for byte
+    assert np.array_equal(xd, xh)
+    for u, v in zip(cd, ch):
+        assert np.array_equal(u, v)
+    # every rule against the oracle on one hand-made record (sums over n = 1000 samples)
+    rec = np.array([[310.5, 44.25, -120.75, 5120.0, 1000.0]])
+    for name, kind, p1, p2 in [("VPG", O.OPT_VPG, 0.05, 0.0), ("BLPG", O.OPT_BLPG, 0.05, 0.0), ("BLAPG", O.OPT_BLAPG, 2e-3, 1e-6),
+                               ("NPG", O.OPT_NPG, 0.5, 1e-6), ("ANPG", O.OPT_ANPG, 2e-3, 1e-6), ("BLANPG", O.OPT_BLANPG, 2e-3, 1e-6)]:
+        with mb.CudaEnsemble(256, 2.0, [0.3, 0.7], [0.5, 0.5], seed=1) as eng:
+            import torch
+            with torch.cuda.stream(eng.torch_stream()):
+                eng.pgmc_sums_tensor()[:5].copy_(torch.from_numpy(rec[0]))
+            eng.pgmc_update_device([1], [(name, p1, p2)])
+            want = O.learning_step(kind, p1, p2, rec[0, :4] / rec[0, 4], 0.7)
+            assert eng.get_params(1) == want and eng.get_params(0) == 0.3, name
+            assert np.all(eng.pgmc_read(1) == 0)                  # accumulators zeroed (update.jl:55)
+    # an update that drives σ out of (0, ∞) is reported when the parameters are pulled (Normal(0, σ) throws in the reference)
+    with mb.CudaEnsemble(256, 2.0, [0.3, 0.7], [0.5, 0.5], seed=1) as eng:
+        with torch.cuda.stream(eng.torch_stream()):
+            eng.pgmc_sums_tensor()[:5].copy_(torch.tensor([1.0, -1e6, 0.0, 1.0, 1.0], dtype=torch.float64))
+        eng.pgmc_update_device([1], [("VPG", 1.0, 0.0)])
+        with pytest.raises(mb.AriannaError):
+            eng.get_params(1)
+
+
 def test_driver_matches_oracle_on_gpu(tmp_path):
     """Simulation / run! through the real engine == the stepwise oracle (same check as the CPU test double)."""
     M, steps, burn, seed = 2048, 300, 100, 42
