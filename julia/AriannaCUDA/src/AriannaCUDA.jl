@@ -17,7 +17,8 @@ using ComponentArrays
 using Libdl
 using Random
 
-export CudaEnsemble, callback_acceptance_cuda, flush!, device_positions, nccl_unique_id, comm_init!, plan!, run_host_job!
+export CudaEnsemble, callback_acceptance_cuda, flush!, device_positions, nccl_unique_id, comm_init!, plan!, run_host_job!,
+       device_update!
 
 const MAX_MOVES = 16
 const libarianna = Ref{String}(get(ENV, "ARIANNA_CUDA_LIB", "libarianna_cuda.so"))
@@ -40,6 +41,13 @@ struct AriannaConfig
     stream::Ptr{Cvoid}
     dtype::Int32                  # 0 = Float64, 1 = Float32 (Particle{Float32}, σ = 0.1f0)
     reserved::Int32
+end
+
+struct OptimiserSpec             # arianna_optimiser
+    kind::Int32
+    reserved::Int32
+    p1::Float64
+    p2::Float64
 end
 
 struct GradientRecord            # arianna_gradient_data
@@ -334,6 +342,35 @@ function Arianna.make_step!(simulation::Simulation{<:CudaEnsemble}, algorithm::P
                                                fill(r.g, 1, 1), Int(r.n))
         algorithm.gradients_data[k] = algorithm.gradients_data[k] + gd             # estimator.jl:130
         algorithm.objectives[k] = algorithm.gradients_data[k].j / algorithm.gradients_data[k].n
+    end
+    return nothing
+end
+
+# PolicyGradientUpdate on the device (arianna_pgmc_update_device): the averaging, learning_step! of every learnable move
+# and the reset of the accumulators run in one kernel; σ stays in a device-resident block that the sweeps read.  Opt-in:
+# call `device_update!(simulation, update_algorithm)` from a `make_step!` overload, or use it directly; it needs the
+# estimator sums to be ACCUMULATED on the device, i.e. an estimator step that does not reset them (accumulate = true).
+optimiser_spec(o::Arianna.PolicyGuided.VPG) = OptimiserSpec(Int32(1), Int32(0), o.η, 0.0)
+optimiser_spec(o::Arianna.PolicyGuided.BLPG) = OptimiserSpec(Int32(2), Int32(0), o.η, 0.0)
+optimiser_spec(o::Arianna.PolicyGuided.BLAPG) = OptimiserSpec(Int32(3), Int32(0), o.δ, o.ϵid)
+optimiser_spec(o::Arianna.PolicyGuided.NPG) = OptimiserSpec(Int32(4), Int32(0), o.η, o.ϵid)
+optimiser_spec(o::Arianna.PolicyGuided.ANPG) = OptimiserSpec(Int32(5), Int32(0), o.δ, o.ϵid)
+optimiser_spec(o::Arianna.PolicyGuided.BLANPG) = OptimiserSpec(Int32(6), Int32(0), o.δ, o.ϵid)
+optimiser_spec(::Any) = OptimiserSpec(Int32(0), Int32(0), 0.0, 0.0)           # Static
+
+function device_update!(simulation::Simulation, algorithm::PolicyGradientUpdate)
+    ens = simulation.chains[1]
+    ids = Int32.(algorithm.learn_ids .- 1)
+    specs = [optimiser_spec(algorithm.optimisers[k]) for k in algorithm.learn_ids]
+    check(ens.handle, ccall((:arianna_pgmc_update_device, libarianna[]), Int32,
+                            (Ptr{Cvoid}, Ptr{Int32}, Ptr{OptimiserSpec}, Int32), ens.handle, ids, specs, length(ids)))
+    # refresh the host Moves (one small synchronising read; StoreParameters prints move.parameters)
+    check(ens.handle, ccall((:arianna_params_sync, libarianna[]), Int32, (Ptr{Cvoid},), ens.handle))
+    θ = Ref{Float64}(0.0)
+    for k in algorithm.learn_ids
+        check(ens.handle, ccall((:arianna_get_params, libarianna[]), Int32, (Ptr{Cvoid}, Int32, Ref{Float64}, Int32),
+                                ens.handle, k - 1, θ, 1))
+        ens.pool[k].parameters.σ = θ[]
     end
     return nothing
 end

@@ -52,7 +52,7 @@ JL2C = {
     "Ptr{Int32}": {"int32_t*"}, "Ref{Int32}": {"int32_t*"},
     "Ptr{UInt8}": {"void*", "uint8_t*"}, "Ptr{UInt32}": {"uint32_t*"}, "Ptr{UInt64}": {"uint64_t*"},
     "Ref{AriannaConfig}": {"arianna_config*"}, "Ref{Ptr{Cvoid}}": {"arianna_handle**", "void**", "double**"},
-    "Ptr{GradientRecord}": {"arianna_gradient_data*"},
+    "Ptr{GradientRecord}": {"arianna_gradient_data*"}, "Ptr{OptimiserSpec}": {"arianna_optimiser*"},
 }
 
 
@@ -168,3 +168,8 @@ def test_struct_layouts_match():
     goffs, gsize = _c_layout(g)
     assert [f for f, _, _ in g] == [f for f, _ in L.GradientData._fields_] and gsize == C.sizeof(L.GradientData) == 40
     assert int(re.search(r"const MAX_MOVES = (\d+)", open(SHIM).read()).group(1)) == L.MAX_MOVES
+    o = _julia_struct("OptimiserSpec")
+    ooffs, osize = _c_layout(o)
+    assert [f for f, _, _ in o] == [f for f, _ in L.Optimiser._fields_] and osize == C.sizeof(L.Optimiser) == 24
+    for f, _ in L.Optimiser._fields_:
+        assert ooffs[f] == getattr(L.Optimiser, f).offset
