@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--mc-steps", type=int, default=10, help="Metropolis steps per store interval")
     ap.add_argument("--series", type=int, default=0,
                     help="store intervals fused per launch (0 = the engine's preferred count, 1 = one launch per store)")
-    ap.add_argument("--slices", type=int, default=4, help="regular chain slices of the pipelined end-to-end job")
+    ap.add_argument("--slices", type=int, default=8, help="regular chain slices of the pipelined end-to-end job")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -409,15 +409,23 @@ def run_ours(args):
                     eng.set_params(0, 0.1)
                     r = eng.run_host_job([S] * K, x_in=x_in.data_ptr(), x_out=x_out.data_ptr() if download else None,
                                          n_slices=args.slices, read=(world == 1))
+                    t_job = time.perf_counter() - t0
                     if world > 1:
                         r = eng.series_global(K)                       # in-library NCCL all-reduce + D2H of the K records
                     ev = float(r[-1, 0] / r[-1, 2])
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
+                detail = None
+                if main["g_max"] > 1:
+                    detail = dict(eng.job_timing(), job_ms=1e3 * t_job, sweep_ms=eng.timing()[0], total_ms=1e3 * dt)
+                    if world > 1:                                      # every rank's view (the slowest one sets the time)
+                        rows = [None] * world
+                        dist.all_gather_object(rows, detail)
+                        detail = {"per_rank": rows}
                 tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
                 if world > 1:
                     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                return float(tt.item()), ev, (eng.job_timing() if main["g_max"] > 1 else None)
+                return float(tt.item()), ev, detail
 
             dt, evals, pcie = timed_job(False)
             dt_dl, _, pcie_dl = timed_job(True)
@@ -425,7 +433,7 @@ def run_ours(args):
         e2e = {"value": total_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(8 * m_local / K + 8), "d2h_bytes_per_step": 24,
                "seconds": dt, "collective": "in-library NCCL (arianna_series_global)" if world > 1 else None,
-               "pcie_rank0": pcie,
+               "pcie": pcie,
                "note": ("timed: ONE arianna_run_host_job call = pinned-host x0 -> HBM, K store intervals, the K callback "
                         f"records -> host, pipelined over ramped slices of chains ({args.slices} regular ones); the chains "
                         "stay resident in HBM like the shim's CudaEnsemble (C3 has no StoreLastFrames)"
@@ -434,7 +442,7 @@ def run_ours(args):
                         "amortised over the K steps"),
                "with_final_state_download": {
                    "value": total_steps / dt_dl, "seconds": dt_dl, "d2h_bytes_per_step": int(8 * m_local / K + 24),
-                   "pcie_rank0": pcie_dl,
+                   "pcie": pcie_dl,
                    "note": "the same job + the final chains -> pinned host (StoreLastFrames), uploads and downloads on "
                            "separate streams"},
                "energy": evals}

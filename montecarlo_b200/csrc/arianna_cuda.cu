@@ -1113,6 +1113,19 @@ static int32_t series_prepare(arianna_handle *h, const char *who, int32_t n_stor
         CU_TRY(h, cudaMalloc(&h->d_series, sizeof(double) * record_stride(h) * cap));
         h->series_cap = cap;
     }
+    // The per-CTA partials for the LARGEST grid any launch of this call can use, allocated NOW: growing the buffer in the
+    // middle of a pipelined host job means cudaFree, i.e. a device-wide synchronisation that waits for every queued
+    // upload (measured: the regular slices of a job started only after the whole ensemble had been uploaded).
+    {
+        static const int env_waves = getenv("ARIANNA_GRID_WAVES") ? atoi(getenv("ARIANNA_GRID_WAVES")) : 0;
+        int waves = env_waves > 0 ? env_waves : kGridWaves;
+        if (waves > kMaxGridWaves) waves = kMaxGridWaves;
+        const size_t max_grid = (size_t)h->sm_count * 8 * waves;
+        const int per_launch = series_per_launch(h);
+        const size_t per_cta = h->pool.n_moves > 1 ? (size_t)per_launch * (1 + h->pool.n_moves) : (size_t)(per_launch + 1) * 2;
+        const int32_t rc = ensure_series_partials(h, max_grid * per_cta);
+        if (rc) return rc;
+    }
     return ARIANNA_OK;
 }
 

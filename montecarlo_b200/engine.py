@@ -201,7 +201,7 @@ class CudaEnsemble:
                                                 _ptr(rec)))
         return rec
 
-    def run_host_job(self, Ks: Sequence[int], x_in=None, x_out=None, n_slices: int = 4, read: bool = True):
+    def run_host_job(self, Ks: Sequence[int], x_in=None, x_out=None, n_slices: int = 8, read: bool = True):
         """A complete callbacks-only job with host buffers, pipelined over slices of the chains
         (arianna_run_host_job): chains in, len(Ks) store intervals, records out, chains out.  x_in / x_out: numpy
         arrays or raw pointers of page-locked host memory ([n_chains] f64), or None."""

@@ -40,7 +40,7 @@ def test_bench_line_contract(series):
     assert 0 < w["value"] <= 1.3 * d["value"] and w["d2h_bytes_per_step"] >= 8 * (1 << 22) // 25
     assert abs(d["mean_energy"] - e["energy"]) < 0.02          # both runs sample the same ensemble a little later
     if series == "0":
-        assert e["pcie_rank0"]["h2d_gbs"] > 1 and w["pcie_rank0"]["d2h_gbs"] > 1
+        assert e["pcie"]["h2d_gbs"] > 1 and w["pcie"]["d2h_gbs"] > 1 and e["pcie"]["sweep_ms"] > 0
     assert d["strong"]["chains_total"] == 1 << 22 and d["strong"]["value"] == d["value"]
     p = d["parity"]
     assert p["ok"] is True and p["accepted_sums_equal_oracle"] is True and p["energy_sum_max_rel_err_vs_oracle"] <= 1e-12
