@@ -20,7 +20,7 @@ NVCC_FLAGS = [
 
 
 def _sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".inc"))] + [
         os.path.join(INCLUDE, "arianna_cuda.h")]
 
 

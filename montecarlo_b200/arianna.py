@@ -229,7 +229,7 @@ class ParticleEnsemble(AriannaSystem):
             self.engine.set_betas(self.betas[self.offset:self.offset + self.n_local])
         if self.rng == "xoshiro" and hasattr(self.engine, "set_rng_state"):
             # rngs = [Xoshiro(seed + c - 1) for c in 1:M] (metropolis.jl:262-263): Julia 1.7-1.10's own seeding, hashed on
-            # the host in chunks and uploaded (julia_rng.py; [EXT], unverified without a Julia toolchain)
+            # the host in chunks and uploaded (julia_rng.py; [EXT], pinned by the Julia manual's known answers)
             from .julia_rng import xoshiro_states
             st = np.empty((self.n_local, 4), dtype=np.uint64)
             for a in range(0, self.n_local, 1 << 20):

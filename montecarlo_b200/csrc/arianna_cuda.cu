@@ -248,25 +248,17 @@ size_t ensure_scratch(arianna_handle *h, size_t bytes)
     return bytes;
 }
 
-// Ziggurat tables of the "Julia-like" randn (generated exactly as oracle/arianna_oracle.c:zig_init does, which
-// restates randmtzig's create_ziggurat_tables [EXT]); the host may override them (arianna_set_ziggurat_tables).
+// Ziggurat tables of Julia's randn [EXT: stdlib Random, normal.jl]: Julia's literal constants, i.e. the randmtzig
+// recursion evaluated exactly and rounded once (scripts/make_zig_tables.py) -- randmtzig.c's own double-precision recipe
+// is 3e-12..3e-10 away from them.  With these defaults and Xoshiro(seed + c - 1) states (julia_rng.py, uploaded through
+// arianna_set_rng_state) the XOSHIRO mode draws the very normals Julia draws (known answers of the Julia manual: tests/test_host.py, tests/test_oracle.py); the host may
+// still override the tables (arianna_set_ziggurat_tables), e.g. for a Julia whose tables ever change.
+#include "zig_tables_julia.inc"
 void make_zig_tables(uint64_t *ki, double *wi, double *fi)
 {
-    const double R = 3.6541528853610088, AREA = 0.00492867323399, NM = 2251799813685248.0;
-    double x1 = R, xx;
-    wi[255] = x1 / NM;
-    fi[255] = std::exp(-0.5 * x1 * x1);
-    ki[0] = (uint64_t)(x1 * fi[255] / AREA * NM);
-    wi[0] = AREA / fi[255] / NM;
-    fi[0] = 1.0;
-    for (int i = 254; i > 0; --i) {
-        xx = std::sqrt(-2.0 * std::log(AREA / x1 + fi[i + 1]));
-        ki[i + 1] = (uint64_t)(xx / x1 * NM);
-        wi[i] = xx / NM;
-        fi[i] = std::exp(-0.5 * xx * xx);
-        x1 = xx;
-    }
-    ki[1] = 0;
+    std::memcpy(ki, kZigKiJulia, sizeof kZigKiJulia);
+    std::memcpy(wi, kZigWiJulia, sizeof kZigWiJulia);
+    std::memcpy(fi, kZigFiJulia, sizeof kZigFiJulia);
 }
 
 // Doubles per callback record: [Σe, Σ_c acc/tot per move, count]

@@ -7,9 +7,12 @@ The reference builds one generator per chain, `rngs = [Xoshiro(seed + c - 1) for
     seed!(rng, v::Vector{UInt32}):  s0, s1, s2, s3 = reinterpret(UInt64, sha256(reinterpret(UInt8, v)))
 
 i.e. the state is the SHA-256 digest of the seed's little-endian limbs, read as four little-endian 64-bit words
-(Julia 1.11 changed the scheme).  **Unverified here: no Julia toolchain exists in the build environment**; SHA-256 itself
-is pinned by the FIPS 180-4 vectors and by hashlib (tests/test_host.py), the four-line recipe above is restated from
-the Julia sources.  A user with Julia confirms it with `julia/tools/record_replay.jl`, which prints `Xoshiro(42)`'s state.
+(Julia 1.11 changed the scheme).  No Julia toolchain exists in the build environment, but the recipe is **pinned by
+the known answers printed in the Julia manual**: `rng = Xoshiro(1234); rand(rng, 2)` = [0.32597672886359486,
+0.5490511363155669] (Xoshiro docstring) and `rng = Xoshiro(123); randn(rng, ComplexF64)` = -0.45660053706486897 -
+1.0346749725929225im (randn docstring) are reproduced bit for bit from these states (tests/test_oracle.py::
+test_julia_rng_known_answers on the host, tests/test_gpu_parity.py::test_xoshiro_device_draws_the_julia_manual_normals on
+the device generator with the engine's default ziggurat tables = Julia's literal ki / wi / fi).
 
 The hash is vectorised over chains with numpy (one 64-byte block per seed), so 2^24 chains seed in seconds.
 """

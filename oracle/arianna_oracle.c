@@ -10,7 +10,10 @@
  * test/distribution_test.jl:36-37, test/pgmc_test.jl:45,50, test/ad_backends_test.jl:31-32).  This oracle
  * is a line-by-line restatement of the reference sources cited at each function; the statistical
  * assertions of the reference tests and the public known-answer vectors of the RNG building blocks
- * (Philox4x32-10, xoshiro256++) are what pin it.
+ * are what pin it: Philox4x32-10 (Random123 kat_vectors), xoshiro256++, and -- for the third-party stream
+ * the reference actually draws from, Julia's Random stdlib [EXT] -- the known answers printed in the Julia
+ * manual (Xoshiro(1234) -> rand; Xoshiro(123) -> fourteen consecutive randn), which pin the SHA-256
+ * seeding, the generator, rand(Float64) and the ziggurat's literal tables + fast path bit for bit.
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared (see oracle/Makefile).  -ffp-contract=off is
  * REQUIRED: every arithmetic statement below is one IEEE-754 binary64 operation in the reference's order.
@@ -506,11 +509,13 @@ AO_API double ao_learning_step(int kind, double p1, double p2, const double *gd,
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-/* "Julia-like" RNG front-end [EXT, restated from public descriptions; NOT verifiable here, never part */
-/* of the parity contract -- it only manufactures replay streams and drives the CPU baseline].        */
+/* Julia's RNG front-end [EXT: stdlib Random, Julia 1.7 - 1.10], restated from its published algorithm */
+/* and PINNED by the known answers printed in the Julia manual (Xoshiro(1234) -> rand, Xoshiro(123) -> */
+/* randn; tests/test_oracle.py::test_julia_rng_known_answers): SHA-256 seeding, xoshiro256++, rand,    */
+/* the ziggurat's tables and fast path.  The wedge / tail slow paths (1 %) are restated, not pinned.   */
 /* xoshiro256++ (Blackman & Vigna); self-check: state (1,2,3,4) -> first output 41943041.             */
 /* rand(Float64) = (next >> 11) * 2^-53;  randn = 256-layer ziggurat (Marsaglia-Tsang / Doornik ZIGNOR */
-/* as in Julia's Random/normal.jl, tables generated as in randmtzig.c).                               */
+/* as in Julia's Random/normal.jl, with Julia's literal tables (zig_tables_julia.h).                   */
 /* ------------------------------------------------------------------------------------------------ */
 static inline uint64_t rotl64(uint64_t v, int k) { return (v << k) | (v >> (64 - k)); }
 
@@ -541,7 +546,7 @@ AO_API void ao_xoshiro_seed(uint64_t seed, uint64_t s[4])
     }
 }
 
-/* Julia's own seeding of `Xoshiro(n::Integer)` [EXT Random stdlib, Julia 1.7 - 1.10; UNVERIFIED here -- no Julia]:
+/* Julia's own seeding of `Xoshiro(n::Integer)` [EXT Random stdlib, Julia 1.7 - 1.10; PINNED by the Julia manual's known answers]:
  *   seed!(rng, n) = seed!(rng, make_seed(n));  make_seed(n) = the 32-bit limbs of n, least significant first;
  *   seed!(rng, v::Vector{UInt32}): s0..s3 = reinterpret(UInt64, sha256(reinterpret(UInt8, v)))
  * i.e. the SHA-256 digest of the limbs' little-endian bytes read as four little-endian 64-bit words.  This is what
@@ -618,33 +623,17 @@ AO_API void ao_xoshiro_seed_chains_julia(int64_t seed, int64_t chain_offset, int
     for (int64_t c = 0; c < M; ++c) ao_xoshiro_seed_julia((uint64_t)(seed + chain_offset + c), states + 4 * c);
 }
 
-#define ZIG_R 3.6541528853610088
-#define ZIG_INV_R 0.27366123732975828
-#define ZIG_AREA 0.00492867323399
-#define ZIG_NMANT 2251799813685248.0 /* 2^51 */
-static uint64_t zig_ki[256];
-static double zig_wi[256], zig_fi[256];
-static int zig_ready = 0;
-
-static void zig_init(void)
-{
-    if (zig_ready) return;
-    double x1 = ZIG_R, xx;
-    zig_wi[255] = x1 / ZIG_NMANT;
-    zig_fi[255] = exp(-0.5 * x1 * x1);
-    zig_ki[0] = (uint64_t)(x1 * zig_fi[255] / ZIG_AREA * ZIG_NMANT);
-    zig_wi[0] = ZIG_AREA / zig_fi[255] / ZIG_NMANT;
-    zig_fi[0] = 1.0;
-    for (int i = 254; i > 0; --i) {
-        xx = sqrt(-2.0 * log(ZIG_AREA / x1 + zig_fi[i + 1]));
-        zig_ki[i + 1] = (uint64_t)(xx / x1 * ZIG_NMANT);
-        zig_wi[i] = xx / ZIG_NMANT;
-        zig_fi[i] = exp(-0.5 * xx * xx);
-        x1 = xx;
-    }
-    zig_ki[1] = 0;
-    zig_ready = 1;
-}
+#define ZIG_R 3.6541528853610088       /* ziggurat_nor_r (normal.jl) rounded to binary64 */
+#define ZIG_INV_R 0.27366123732975828 /* inv(ziggurat_nor_r) in binary64 */
+/* Julia's literal tables ki / wi / fi (normal.jl [EXT]): the randmtzig recursion evaluated exactly and rounded   */
+/* once (scripts/make_zig_tables.py), NOT randmtzig.c's double-precision recipe (that one is 3e-12..3e-10 off and  */
+/* moves every draw in its 12th digit).  Pinned by the Julia manual's known answers: Xoshiro(123);                */
+/* randn(rng, ComplexF64) = -0.45660053706486897 - 1.0346749725929225im (tests/test_oracle.py).                   */
+#include "zig_tables_julia.h"
+#define zig_ki kZigKiJulia
+#define zig_wi kZigWiJulia
+#define zig_fi kZigFiJulia
+static void zig_init(void) {}
 
 /* Expose the tables so the CUDA engine's XOSHIRO mode can be handed the *identical* binary64 tables. */
 AO_API void ao_ziggurat_tables(uint64_t *ki, double *wi, double *fi)

@@ -3,7 +3,9 @@
 TEST INFRASTRUCTURE ONLY -- importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs.  The product package (montecarlo_b200/) must never import this module.
 
-PARITY UNPINNED (see the header of arianna_oracle.c): the reference is pure Julia and cannot run here.
+PARITY UNPINNED for the reference's own arithmetic (see the header of arianna_oracle.c): the reference is pure Julia
+and cannot run here.  Its third-party random stream (Julia's Random stdlib: Xoshiro seeding, rand, randn) IS pinned, by
+the known answers printed in the Julia manual (tests/test_oracle.py::test_julia_rng_known_answers).
 """
 from __future__ import annotations
 
@@ -22,8 +24,8 @@ OPT_STATIC, OPT_VPG, OPT_BLPG, OPT_BLAPG, OPT_NPG, OPT_ANPG, OPT_BLANPG = range(
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the recipe in oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp)."""
-    src = os.path.join(_HERE, "arianna_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("arianna_oracle.c", "zig_tables_julia.h", "Makefile")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
     return _SO
 
@@ -188,7 +190,7 @@ class Ensemble:
     # --- "Julia-like" generator front-end (CPU baseline / replay-stream manufacture) ---------------------
     def seed_xoshiro(self, seed, chain_offset=0, julia=False):
         """Per-chain generator states for seeds seed + c - 1 (metropolis.jl:262-263).  julia=True: Julia 1.7-1.10's
-        own SHA-256 seeding of Xoshiro(n) [EXT, unverified]; default: a splitmix64 stand-in."""
+        own SHA-256 seeding of Xoshiro(n) [EXT, pinned by the Julia manual's known answers]; default: a splitmix64 stand-in."""
         self.states = np.zeros((self.M, 4), dtype=np.uint64)
         fn = lib().ao_xoshiro_seed_chains_julia if julia else lib().ao_xoshiro_seed_chains
         fn(C.c_int64(seed), C.c_int64(chain_offset), C.c_int64(self.M), _p(self.states, C.c_uint64))

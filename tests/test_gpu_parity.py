@@ -570,8 +570,7 @@ def test_xoshiro_mode_matches_oracle(sigma, weight):
     ref.sweep_xoshiro(K)
     with mb.CudaEnsemble(M, 2.0, sigma, weight, seed=seed, rng="xoshiro", arith="exact") as eng:
         eng.set_state(x0)
-        eng.set_rng_state(states0)
-        eng.set_ziggurat_tables(*O.ziggurat_tables())
+        eng.set_rng_state(states0)                                    # (the engine's own default ziggurat tables)
         eng.sweep(K)
         x = eng.get_state()
         acc, tot = eng.chain_counters()
@@ -581,6 +580,39 @@ def test_xoshiro_mode_matches_oracle(sigma, weight):
     # fast-path normals are bit-identical; ziggurat tail/wedge samples go through log/exp (≤ 1 ulp apart)
     assert np.max(np.abs(x - ref.x)) < 1e-12
     assert np.mean(x == ref.x) > 0.9
+
+
+def _xoshiro_unstep(s):
+    """The state BEFORE one xoshiro256++ draw (the engine is linear and invertible)."""
+    m64 = (1 << 64) - 1
+    s0, s1, s2, s3 = (int(v) for v in s)
+    e = ((s3 >> 45) | (s3 << 19)) & m64                # d ^ b
+    a = s0 ^ e
+    m = (s1 ^ a) ^ (s2 ^ a)                            # b ^ (b << 17)
+    b = (m ^ (m << 17) ^ (m << 34) ^ (m << 51)) & m64
+    return np.array([a, b, (s1 ^ a) ^ b, e ^ b], dtype=np.uint64)
+
+
+def test_xoshiro_device_draws_the_julia_manual_normals():
+    """The device generator through the C ABI against the known answers printed in the Julia manual (randn docstring:
+    `rng = Xoshiro(123); randn(rng, ComplexF64)` = -0.45660053706486897 - 1.0346749725929225im, tests/test_oracle.py).
+    One EXACT step with beta = 0 (always accepted), sigma = 1, x0 = 0 leaves x = 0 + (0 + 1 z) = z, the step's normal
+    draw; a step consumes rand (u_cat), randn, rand (u_acc) in the reference's order (metropolis.jl:206, particle_1d.jl:57,
+    metropolis.jl:184).  Chain 0 starts one draw BEFORE Xoshiro(123), so its normal is the manual's first one; chain 1
+    starts AT Xoshiro(123) (u_cat uses up the draw the first normal took), so its normal is the manual's second."""
+    from montecarlo_b200 import julia_rng as J
+    s123 = J.xoshiro_state(123)
+    r, nxt = O.xoshiro_next(_xoshiro_unstep(s123))
+    assert np.array_equal(nxt, s123)                   # the inverse step is right
+    states = np.stack([_xoshiro_unstep(s123), s123])
+    with mb.CudaEnsemble(2, 0.0, [1.0], seed=0, rng="xoshiro", arith="exact") as eng:
+        eng.set_state(np.zeros(2))
+        eng.set_rng_state(states)                      # default tables = Julia's literal ki / wi / fi
+        eng.sweep(1)
+        z = eng.get_state()
+        acc, _ = eng.chain_counters()
+    assert list(acc[0]) == [1, 1]
+    assert [float(0.7071067811865476 * v) for v in z] == [-0.45660053706486897, -1.0346749725929225]
 
 
 # ---------------------------------------------------------------------------------------------------------

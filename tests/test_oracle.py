@@ -309,7 +309,7 @@ def test_build_schedule_restatement():
 
 
 def test_sha256_and_julia_xoshiro_seeding():
-    """Xoshiro(n) of Julia 1.7-1.10 [EXT, unverified without Julia]: SHA-256 of n's 32-bit little-endian limbs, digest
+    """Xoshiro(n) of Julia 1.7-1.10 [EXT; pinned by test_julia_rng_known_answers]: SHA-256 of n's 32-bit little-endian limbs, digest
     read as four little-endian UInt64 (metropolis.jl:262-263 builds Xoshiro(seed + c - 1) per chain).  The oracle's C
     SHA-256, hashlib and the product's vectorised numpy hash (montecarlo_b200/julia_rng.py) agree; SHA-256 itself is
     pinned by the FIPS 180-4 known answers."""
@@ -340,3 +340,65 @@ def test_sha256_and_julia_xoshiro_seeding():
     assert np.array_equal(ens.states, J.xoshiro_states(np.arange(49, 149)))
     with pytest.raises(ValueError):
         J.make_seed(-1)
+
+
+# ---- Julia's Random stdlib [EXT]: known answers printed in the Julia manual --------------------------------------
+# The reference draws EVERYTHING from it (rngs = [Xoshiro(seed + c - 1) ...] src/metropolis.jl:262-263; rand at
+# :184/:206 via Distributions.Categorical, randn at example/particle_1d/particle_1d.jl:57 via Distributions.Normal).
+# The docstrings of `Xoshiro` and `randn` (Julia 1.7 - 1.10 manual, Random chapter) print:
+#     julia> rng = Xoshiro(1234);  julia> x1 = rand(rng, 2)      ->  0.32597672886359486, 0.5490511363155669
+#     julia> rng = Xoshiro(123);   julia> randn(rng, ComplexF64) ->  -0.45660053706486897 - 1.0346749725929225im
+#     julia> randn(rng, ComplexF32, (2, 3))  ->  -1.14806-0.153912im  0.056538+1.0954im   0.419454-0.543347im
+#                                                 0.34807+0.693657im  -0.948661+0.291442im  -0.0538589-0.463085im
+# (randn(rng, Complex{T}) = Complex(SQRT_HALF randn(rng, T), SQRT_HALF randn(rng, T)); arrays fill column-major;
+#  randn(rng, Float32) = Float32(randn(rng)) in those versions.)
+JULIA_RAND_1234 = [0.32597672886359486, 0.5490511363155669]
+JULIA_RANDN_123_C64 = [-0.45660053706486897, -1.0346749725929225]
+JULIA_RANDN_123_C32 = [-1.14806, -0.153912, 0.34807, 0.693657, 0.056538, 1.0954, -0.948661, 0.291442,
+                       0.419454, -0.543347, -0.0538589, -0.463085]
+# leading entries of the literal tables in normal.jl (1-based ki[1], ki[3], wi[1..3], fi[2])
+JULIA_KI = {0: 0x0007799ec012f7b2, 1: 0, 2: 0x0006045f4c7de363}
+JULIA_WI = {0: 1.7367254121602630e-15, 1: 9.5586603514556339e-17, 2: 1.2708704834810623e-16}
+JULIA_FI = {0: 1.0, 1: 9.7710170126767082e-01}
+
+
+def _julia_sig(v, digits=6):
+    """a number the way Julia's 6-significant-digit array display prints it, as a float"""
+    return float("%.*g" % (digits, v))
+
+
+def test_julia_rng_known_answers():
+    """Pins the oracle's restatement of Julia's generator bit for bit: SHA-256 seeding, xoshiro256++, rand(Float64) =
+    (next >>> 11) 2^-53, and randn's ziggurat (literal tables + fast path) reproduce the manual's printed values."""
+    from montecarlo_b200 import julia_rng as J
+    st = O.xoshiro_seed_julia(1234)
+    assert np.array_equal(st, J.xoshiro_state(1234))
+    got = []
+    for _ in range(2):
+        r, st = O.xoshiro_next(st)
+        got.append((r >> 11) * 2.0 ** -53)
+    assert got == JULIA_RAND_1234
+    z = O.xoshiro_randn_stream(O.xoshiro_seed_julia(123), 14)
+    sqrt_half = 0.7071067811865476                      # Float64(SQRT_HALF)
+    assert [float(sqrt_half * v) for v in z[:2]] == JULIA_RANDN_123_C64
+    c32 = np.float32(0.70710677) * z[2:].astype(np.float32)
+    assert [_julia_sig(v) for v in c32] == JULIA_RANDN_123_C32
+    ki, wi, fi = O.ziggurat_tables()
+    assert all(int(ki[i]) == v for i, v in JULIA_KI.items())
+    assert all(float(wi[i]) == v for i, v in JULIA_WI.items())
+    assert all(float(fi[i]) == v for i, v in JULIA_FI.items())
+
+
+def test_ziggurat_tables_are_the_generated_ones():
+    """oracle/zig_tables_julia.h and the product's csrc/zig_tables_julia.inc are the same generated data; when mpmath is
+    importable the exact-arithmetic recursion is re-run and must give the committed files byte for byte."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a = open(os.path.join(root, "oracle", "zig_tables_julia.h")).read()
+    b = open(os.path.join(root, "montecarlo_b200", "csrc", "zig_tables_julia.inc")).read()
+    assert a == b and a.count("0x") == 3 * 256
+    pytest.importorskip("mpmath")
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "make_zig_tables.py"), "--check"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
