@@ -173,3 +173,77 @@ def test_struct_layouts_match():
     assert [f for f, _, _ in o] == [f for f, _ in L.Optimiser._fields_] and osize == C.sizeof(L.Optimiser) == 24
     for f, _ in L.Optimiser._fields_:
         assert ooffs[f] == getattr(L.Optimiser, f).offset
+
+
+# ---- block structure -------------------------------------------------------------------------------------
+_IDENT = re.compile("[A-Za-z_\\u00a0-\\uffff][\\w!\\u00a0-\\uffff]*")
+_CHAR = re.compile(r"'(\\.|[^\\'])'")
+
+
+def _julia_tokens(src):
+    """Code tokens of a Julia source with comments, strings and character literals removed: yields (token, depth) with
+    depth = nesting in (), [] and {} (where `for` / `if` are comprehension clauses and `end` is an index)."""
+    i, n, depth = 0, len(src), 0
+    while i < n:
+        ch = src[i]
+        if src.startswith("#=", i):
+            j = src.find("=#", i + 2)
+            assert j >= 0, "unterminated #= comment"
+            i = j + 2
+        elif ch == "#":
+            j = src.find("\n", i)
+            i = n if j < 0 else j
+        elif src.startswith('"""', i):
+            j = src.find('"""', i + 3)
+            assert j >= 0, "unterminated triple-quoted string"
+            i = j + 3
+        elif ch == '"':
+            j = i + 1
+            while j < n and src[j] != '"':
+                j += 2 if src[j] == "\\" else 1
+            assert j < n, "unterminated string"
+            i = j + 1
+        elif ch == "'" and _CHAR.match(src, i):
+            i = _CHAR.match(src, i).end()
+        elif ch in "([{":
+            depth += 1
+            yield ch, depth
+            i += 1
+        elif ch in ")]}":
+            yield ch, depth
+            depth -= 1
+            assert depth >= 0, "unbalanced closing bracket"
+            i += 1
+        else:
+            m = _IDENT.match(src, i)
+            if m:
+                prev = src[i - 1] if i else " "
+                if prev not in ".:":                       # not a field (x.end) or a symbol (:end)
+                    yield m.group(0), depth
+                i = m.end()
+            else:
+                i += 1
+    assert depth == 0, "unbalanced opening bracket"
+
+
+def test_julia_sources_are_block_balanced():
+    """Every block opener of the shim and the record tool has its `end` (and every bracket its partner): the grossest
+    class of error a never-executed Julia file can carry, checked without a Julia parser."""
+    openers = {"function", "if", "for", "while", "let", "begin", "struct", "try", "do", "quote", "module", "macro"}
+    for path in [SHIM] + TOOLS:
+        stack = []
+        for tok, _ in _julia_tokens(open(path).read()):
+            if tok in ("(", "[", "{"):
+                stack.append(tok)
+            elif tok in (")", "]", "}"):
+                assert stack and stack.pop() == {")": "(", "]": "[", "}": "{"}[tok], f"{path}: mismatched {tok}"
+            elif tok in openers:
+                if stack and stack[-1] in ("(", "[", "{") and tok in ("for", "if"):
+                    continue                                # comprehension / generator clause: no `end`
+                stack.append(tok)
+            elif tok == "end":
+                if stack and stack[-1] == "[":
+                    continue                                # a[end]
+                assert stack and stack[-1] in openers, f"{path}: `end` without an open block"
+                stack.pop()
+        assert not stack, f"{path}: unclosed {stack}"
