@@ -21,6 +21,14 @@ echo "== paths"
 timeout 1500 python scripts/bench_paths.py 2>&1 | tee gpurun_out/paths.jsonl | cut -c1-170
 echo "== ncu"
 bash scripts/gpu_profile.sh
+if [ "${SKIP_MULTI:-0}" = "0" ]; then      # (gpurun brings back at most 64 MiB: four .ncu-rep files are too many)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:sweep_multi -s 1 -c 1 -f -o gpurun_out/prof_multi_final \
     python scripts/prof_multi.py > gpurun_out/ncu_multi_final.log 2>&1
 tail -2 gpurun_out/ncu_multi_final.log
+fi
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:pgmc_kernel -s 1 -c 1 -f -o gpurun_out/prof_pgmc \
+    python scripts/prof_pgmc.py > gpurun_out/ncu_pgmc.log 2>&1
+tail -2 gpurun_out/ncu_pgmc.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sweep_f32 -s 1 -c 1 -f -o gpurun_out/prof_f32 \
+    python scripts/prof_f32.py > gpurun_out/ncu_f32.log 2>&1
+tail -2 gpurun_out/ncu_f32.log
