@@ -191,7 +191,7 @@ def run_reference(args):
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -204,6 +204,21 @@ def workload_config(args, world):
         "l2_policy": "inputs larger than L2 (x + counters = %.0f MiB per GPU vs 126 MB L2)" % (m_local * 12 / 2 ** 20),
         "parallelism": f"chains sharded x{world}, all-reduce of 3 doubles per store",
     }
+
+
+def _finite(o):
+    """JSON has no NaN / Infinity: non-finite floats become null (strict parsers reject Python's `NaN` literal)."""
+    if isinstance(o, float):
+        return o if math.isfinite(o) else None
+    if isinstance(o, dict):
+        return {k: _finite(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_finite(v) for v in o]
+    return o
+
+
+def emit(line):
+    print(json.dumps(_finite(line), allow_nan=False), flush=True)
 
 
 def _profile():
@@ -525,7 +540,7 @@ def run_ours(args):
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"2^{lg} chains x {done} store intervals of {S} MC steps in {dt:.1f} s "
                           "(oracle: C restatement of mc_sweep! with xoshiro256++/ziggurat, OpenMP over chains)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -14,7 +14,9 @@ def _run(*extra):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--log2-chains", "22", "--steps", "25",
                           "--warmup", "3", "--ref-log2-chains", "12", "--cpu-seconds", "1", *extra], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
-    return json.loads(out.stdout.strip().splitlines()[-1])
+    def strict(name):                    # Python's json would accept NaN / Infinity; a strict parser does not
+        raise AssertionError(f"bench.py printed the non-JSON constant {name}")
+    return json.loads(out.stdout.strip().splitlines()[-1], parse_constant=strict)
 
 
 @pytest.mark.parametrize("series", ["0", "1"])
