@@ -1130,7 +1130,12 @@ int32_t arianna_sweep_series(arianna_handle *h, int32_t n_stores, const int64_t 
     if (rc || n_stores == 0) return rc;
     time_mark(h, 0, true);
     rc = series_range(h, 0, h->M, h->steps_done, n_stores, K, 0);
-    if (rc) return rc;
+    if (rc) {   // a launch failed after earlier ones were queued: drain them; the chains are part-way through the stretch
+        cudaStreamSynchronize(h->stream);
+        h->sums_valid = false;
+        h->err += " (arianna_sweep_series was partly executed: chain state is undefined, steps_done was not advanced)";
+        return rc;
+    }
     time_mark(h, 0, false);
     h->steps_done += total;
     h->series_n = n_stores;

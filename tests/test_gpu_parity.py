@@ -466,11 +466,11 @@ def test_device_timers():
         assert 0.05 < s100 < 50.0
         eng.sweep(1000)
         s1000, p = eng.timing()
-        assert 5 * s100 < s1000 < 15 * s100 and math.isnan(p)       # device time scales with the fused steps
+        assert 4 * s100 < s1000 < 25 * s100 and math.isnan(p)       # device time scales with the fused steps
         eng.sweep_series([10] * 30)                                 # (first call: lazy module load + buffer allocation)
         eng.sweep_series([10] * 30)
         s300, _ = eng.timing()
-        assert 1.5 * s100 < s300 < 6 * s100
+        assert 1.2 * s100 < s300 < 10 * s100                        # (wide margins: a timing assert must never flake)
         eng.pgmc_estimate(10, [0])
         _, p = eng.timing()
         assert 0.01 < p < 50.0
