@@ -197,8 +197,11 @@ ARIANNA_API int32_t arianna_job_timing(arianna_handle *h, double *h2d_ms, double
 ARIANNA_API int32_t arianna_sweep_replay(arianna_handle *h, int64_t K, const double *u_cat, const double *z,
                              const double *u_acc, uint8_t *decisions_out, int32_t on_device);
 
-/* XOSHIRO mode: per-chain generator states [n_chains][4] uint64 (Xoshiro.s0..s3 [EXT]); tables: the
- * 256-entry ziggurat tables ki/wi/fi of the host's randn [EXT] (NULL = engine-generated). */
+/* XOSHIRO mode: per-chain generator states [n_chains][4] uint64 -- the fields s0..s3 of the reference's
+ * `Xoshiro(seed + c - 1)` (metropolis.jl:262-263; Random stdlib [EXT]).  The engine's default ziggurat tables are
+ * Julia's literal ki / wi / fi (normal.jl [EXT]), so with those states the device draws the uniforms and normals Julia
+ * draws (pinned by the known answers printed in the Julia manual).
+ * arianna_set_ziggurat_tables overrides the three 256-entry tables (a host whose randn uses other tables). */
 ARIANNA_API int32_t arianna_set_rng_state(arianna_handle *h, const uint64_t *states);
 ARIANNA_API int32_t arianna_get_rng_state(arianna_handle *h, uint64_t *states);
 ARIANNA_API int32_t arianna_set_ziggurat_tables(arianna_handle *h, const uint64_t *ki, const double *wi, const double *fi);
