@@ -1053,6 +1053,47 @@ def test_config1_verbatim(tmp_path):
     assert acc[0] == "0 [NaN]" and abs(float(acc[-2].split("[")[1][:-1]) - ref.callback_acceptance()[0]) < 1e-12
 
 
+def test_config1_julia_mode_matches_the_prediction(tmp_path, golden_dir):
+    """BASELINE config 1 run the way Julia runs it: the initial condition from Xoshiro(42), the chains on the DEVICE
+    generator (XOSHIRO mode: Julia's own Xoshiro(seed + c - 1) states, Julia's ziggurat tables) in EXACT arithmetic,
+    through the mirror's Simulation / run.  It must land on tests/golden/julia_prediction_config1.json, the oracle's
+    prediction of what the real reference writes for its example script: the same number of raw draws consumed by
+    every chain (final generator states), the same accept counts, energies to 1e-12."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_julia_prediction", os.path.join(golden_dir, "make_julia_prediction.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = json.load(open(os.path.join(golden_dir, "julia_prediction_config1.json")))
+    x0, ens_ref, energy_ref, accept_ref = mod.predict()                     # the full predicted files (2 s of oracle)
+    assert energy_ref[:20] == gold["energy_head"] and accept_ref[-5:] == gold["acceptance_tail"]
+    seed, beta, steps, burn = gold["seed"], gold["beta"], gold["steps"], gold["burn"]
+    chains = mb.ParticleEnsemble(x0, beta, rng="xoshiro", arith="exact")
+    pool = (mb.Move(mb.Displacement(0.0), mb.StandardGaussian(), mb.ComponentArray(σ=gold["sigma"]), 1.0),)
+    sampletimes = mb.build_schedule(steps, burn, [0, 10])
+    algorithm_list = (
+        dict(algorithm=mb.Metropolis, pool=pool, seed=seed, parallel=False),
+        dict(algorithm=mb.StoreCallbacks, callbacks=(mb.callback_energy, mb.callback_acceptance), scheduler=sampletimes),
+    )
+    simulation = mb.Simulation(chains, algorithm_list, steps, path=str(tmp_path), verbose=False)
+    mb.run(simulation)
+    eng = chains.engine
+    assert np.array_equal(eng.get_rng_state(), np.array(gold["rng_states_final"], dtype=np.uint64))
+    acc, _ = eng.chain_counters()
+    assert list(acc[0]) == gold["accepted_calls"]
+    x_ref = np.array([float.fromhex(h) for h in gold["x_final_hex"]])
+    assert np.max(np.abs(eng.get_state() - x_ref)) < 1e-12
+    got = open(tmp_path / "energy.dat").read().split("\n")[:-1]
+    assert len(got) == gold["records"] and [ln.split()[0] for ln in got] == [ln.split()[0] for ln in energy_ref]
+    e_got = np.array([float(ln.split()[1]) for ln in got])
+    e_ref = np.array([float(ln.split()[1]) for ln in energy_ref])
+    np.testing.assert_allclose(e_got, e_ref, rtol=1e-12)
+    a_got = open(tmp_path / "acceptance.dat").read().split("\n")[:-1]
+    assert a_got[0] == "0 [NaN]"
+    np.testing.assert_allclose([float(ln.split("[")[1][:-1]) for ln in a_got[1:]],
+                               [float(ln.split("[")[1][:-1]) for ln in accept_ref[1:]], rtol=1e-12)
+
+
 _LIBNCCL_WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})

@@ -11,7 +11,7 @@ import re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "arianna_cuda.h")
 SHIM = os.path.join(ROOT, "julia", "AriannaCUDA", "src", "AriannaCUDA.jl")
-TOOLS = [os.path.join(ROOT, "julia", "tools", "record_replay.jl")]
+TOOLS = [os.path.join(ROOT, "julia", "tools", f) for f in ("record_replay.jl", "check_prediction.jl")]
 
 
 def _strip_comments(src):

@@ -402,3 +402,19 @@ def test_ziggurat_tables_are_the_generated_ones():
     res = subprocess.run([sys.executable, os.path.join(root, "scripts", "make_zig_tables.py"), "--check"],
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
+
+
+def test_julia_prediction_fixture_is_current(golden_dir):
+    """tests/golden/julia_prediction_config1.json -- the falsifiable prediction of the reference's own output for its
+    example script (config 1) under Julia 1.7 - 1.10 -- is what the oracle computes today (make_julia_prediction.py)."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_julia_prediction", os.path.join(golden_dir, "make_julia_prediction.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(golden_dir, "julia_prediction_config1.json")))
+    got = json.loads(json.dumps(mod.record(*mod.predict())))
+    assert got == want
+    # the initial condition is 4 rand(Xoshiro(42)) - 2, ten consecutive draws of ONE generator (MC_harmonic_oscillator.jl:10-13)
+    assert want["x0"][0] == "0.5173804925704357" and len(want["x0"]) == 10
+    assert want["records"] == 9902 and want["energy_head"][0].startswith("0 ") and want["acceptance_head"][0] == "0 [NaN]"
