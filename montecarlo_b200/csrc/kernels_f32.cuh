@@ -91,10 +91,9 @@ template <int PBITS>
 __device__ __forceinline__ bool exp_accept_prefix_f32(float a, uint32_t f, uint32_t w, m64::Tab tb)
 {
     const float Es = m64::ex2_approx(fmaf(a, 1.44269504f, (float)PBITS));
-    const int ilo = __float2int_rd(Es * 0.9998779296875f);
-    const int ihi = __float2int_rd(Es * 1.0001220703125f);
-    bool acc = (a >= 0.0f) || (ilo > (int)f);
-    const bool rej = ihi < (int)f;
+    const float v = m64::fma_floor_offset(Es, f);               // floor(Es(1 − 2^-13)) − f − 1.5·2^23 (math64.cuh)
+    bool acc = (a >= 0.0f) || (v > -m64::kFloorMagic);
+    const bool rej = v < -(m64::kFloorMagic + 1.0f);
     if (!(acc || rej)) {
         const double x = (double)a;
         const uint32_t t = (uint32_t)__double2hiint(x) - 0x7ff00000u;

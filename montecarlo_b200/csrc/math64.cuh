@@ -5,7 +5,7 @@
 // their arguments straight from the Philox INTEGER words (no int->fp64 conversion instructions):
 //
 //   exp_core / exp_accept / exp_nonpos   exp for the accept test / PGMC α      11 FP64, 1 table load, integer range checks
-//   exp_accept_prefix<P> the accept test against a P-bit prefix of u          FP32 + MUFU.EX2 + 2 F2I; FP64 only when ambiguous
+//   exp_accept_prefix<P> the accept test against a P-bit prefix of u          FP32 + MUFU.EX2 + one FFMA.RM; FP64 only when ambiguous
 //   neg2log_k52(k)       −2·ln(k·2^-52), k ∈ [1, 2^52)  (Box-Muller radius²)   10 FP64 (incl. the exact int->fp64 DADD), 3 table loads
 //   neg2log_u53(n)       −2·ln(n·2^-53), n ∈ [1, 2^53)  (reference form, clz)   9 FP64, 3 table loads
 //   sqrt_pos(w)          √w, w > 0 normal                                       6 FP64 + 1 MUFU.RSQ64H
@@ -324,36 +324,47 @@ AM_FN bool exp_accept(double x, float ulo, float uhi, ExactU exact_u, Tab tb)
     return acc;
 }
 
-// The same decision for the native stream, where u is known through its 11-bit PREFIX f (u ∈ [f, f+1)·2^-11): the
-// comparison is done in the integer domain, so no float cell has to be assembled from f (5 ALU instructions per step)
-// and the error bound is a constant (no per-step FFMA):
-//   Es ≈ 2^11·exp(x) from MUFU.EX2(a·log2e + 11);  floor(Es(1−ε)) ≥ f+1 accepts,  floor(Es(1+ε)) < f rejects,
-//   ε = 2^-13.  Valid for −127 ≤ a < 0: |Es/(2^11 e^x) − 1| ≤ 2^-24|a| (a = RN32(x)) + 2^-25|a| (log2e) + 2^-17·ln2
-//   (rounding of the fma at |y'| < 256) + 2^-22 (EX2) + 2^-24 (the ε multiply) < 2^-15.6, a 6x margin.  a < −127:
-//   Es = 0 (the EX2 argument is below −172, flushed), which rejects every f ≥ 1 — correct because
-//   exp(x) < 2^-183 < 2^-11 ≤ u — and sends f = 0 to the exact path.  a ≥ 0 (incl. −0, +inf) accepts: α = 1 > u.
-//   NaN: every float comparison is false and the float->int conversion gives 0: f ≥ 1 rejects here, f = 0 rejects in
-//   the exact path -- min(1, NaN) > u is false in the reference too.
-// The two F2I run on the XU pipe, which idles beside the issue-bound sweep (17 % busy).
-AM_FN int float2int_floor(float v)
+// The same decision for the native stream, where u is known through its P-bit PREFIX f (u ∈ [f, f+1)·2^-P): the
+// comparison needs no float cell assembled from f (5 ALU instructions per step) and its error bound is a constant:
+//   Es ≈ 2^P·exp(x) from MUFU.EX2(a·log2e + P), a = RN32(x).  Valid for −127 ≤ a < 0:
+//   |Es/(2^P e^x) − 1| ≤ 2^-24|a| (a = RN32(x)) + 2^-25|a| (log2e) + 2^-17·ln2 (rounding of the fma at |y'| < 256)
+//   + 2^-22 (EX2) =: δ < 2^-15.6.
+// ONE fused multiply-add rounded toward −∞ does the scaling by c = 1 − 2^-13, the subtraction of f AND the floor:
+//   v = fma_rd(Es, c, −(1.5·2^23 + f)) = floor(Es·c) − f − 1.5·2^23   exactly
+// because the exact value lies in (−2^24, −2^23), where binary32 has ulp 1, and the addend is an integer; the addend
+// is assembled by bit arithmetic (bits(−1.5·2^23) + f: the mantissa of a float of that binade counts in units of 1).
+// With g = floor(Es·c) − f (an integer, read off v):
+//   g ≥  1  accepts:  Es·c ≥ f+1  ⇒  2^P e^x ≥ Es(1−δ) ≥ (f+1)(1−δ)/(1−2^-13) > f+1  ⇒  exp(x) > (f+1)2^-P > u;
+//   g ≤ −2  rejects:  Es·c < f−1  ⇒  2^P e^x ≤ Es(1+δ) < (f−1)(1+δ)/(1−2^-13) < f−1 + 2^P·1.17·2^-13 ≤ f−0.41 (P ≤ 12)
+//                     ⇒  exp(x) < f 2^-P ≤ u;
+//   g ∈ {−1, 0} is decided by the FP64 exp against the exact uniform (lazy refinement).
+// a < −127: Es = 0 (the EX2 argument is below −172, flushed), g = −f rejects every f ≥ 2 — correct because
+// exp(x) < 2^-183 < 2^-P ≤ u — and sends f ≤ 1 to the exact path.  a ≥ 0 (incl. −0, +inf) accepts: α = 1 > u.
+// NaN: v is NaN, both comparisons are false, the exact path rejects -- min(1, NaN) > u is false in the reference too.
+// Three instructions (FFMA.RM + two FSETP) replace two FMUL, two F2I and two ISETP of the two-sided integer form.
+constexpr float kFloorMagic = 12582912.0f;                  // 1.5·2^23
+AM_FN float fma_floor_offset(float Es, uint32_t f)
 {
+    const float m = uint_as_float(0xCB400000u + f);         // −(1.5·2^23 + f), f < 2^12
 #if AM_DEV
-    return __float2int_rd(v);
+    return __fmaf_rd(Es, 0.9998779296875f, m);              // c = 1 − 2^-13
 #else
-    return (v != v) ? 0 : (int)floorf(v);
+    if (Es != Es) return Es;
+    if (Es > 3.0e38f) return Es;                            // +inf stays +inf
+    return (float)(floor((double)Es * (double)0.9998779296875f) + (double)m);     // exact: integer-valued, |·| < 2^24
 #endif
 }
 // PBITS = length of the prefix (11 for the odd step of a pair, 12 for the even one: DESIGN.md "RNG stream layout");
-// the bound above is for 11 + log2e·127 < 256, unchanged for 12.
+// the bound above is for PBITS + log2e·127 < 256 and 2^PBITS·1.17·2^-13 < 1, i.e. PBITS ≤ 12.
 template <int PBITS, class ExactU>
 AM_FN bool exp_accept_prefix(double x, uint32_t f, ExactU exact_u, Tab tb)
 {
+    static_assert(PBITS <= 12, "the one-sided floor form needs 2^PBITS * 1.17 * 2^-13 < 1");
     const float a = (float)x;
     const float Es = ex2_approx(fmaf(a, 1.44269504f, (float)PBITS));
-    const int ilo = float2int_floor(Es * 0.9998779296875f);    // 1 − 2^-13
-    const int ihi = float2int_floor(Es * 1.0001220703125f);    // 1 + 2^-13
-    bool acc = (a >= 0.0f) || (ilo > (int)f);
-    const bool rej = ihi < (int)f;
+    const float v = fma_floor_offset(Es, f);
+    bool acc = (a >= 0.0f) || (v > -kFloorMagic);            // g ≥ 1
+    const bool rej = v < -(kFloorMagic + 1.0f);              // g ≤ −2
     if (!(acc || rej)) {
         const uint32_t t = double2hi(x) - 0x7ff00000u;
         const bool core = (t - 0x00100000u) < (0x40962000u - 0x00100000u);  // x ∈ [−708, −0]
