@@ -1894,7 +1894,7 @@ int32_t arianna_debug_math(arianna_handle *h, int32_t kind, const double *a, con
                            double *out, int64_t n)
 {
     if (!h) return ARIANNA_ERR_INVALID;
-    REQUIRE(h, kind >= 0 && kind <= 9 && out != nullptr && n >= 0, "arianna_debug_math: bad arguments");
+    REQUIRE(h, kind >= 0 && kind <= 11 && out != nullptr && n >= 0, "arianna_debug_math: bad arguments");
     if (n == 0) return ARIANNA_OK;
     DeviceGuard guard(h->device);
     const int64_t nout = (kind == 6 || kind == 7) ? 4 * n : (kind == 9 || kind < 3) ? n : 2 * n;

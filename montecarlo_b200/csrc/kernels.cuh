@@ -188,12 +188,27 @@ __device__ __forceinline__ int mc_step_exact(double &x, double &e, double beta, 
 // producing the exact 53-bit u on demand (see m64::exp_accept).
 template <int PBITS>
 struct CellP { uint32_t f; };     // PBITS-bit prefix of the accept uniform: u ∈ [f, f+1)·2^-PBITS
+template <int PBITS>
+struct CellM { uint32_t fm; };    // the same prefix as the filter's pre-assembled addend bits (m64::exp_prefix_bits);
+                                  // the FAST step of a CellM caller must be given β·log2(e) for β (m64::exp_accept_prefix)
 struct CellF { float ulo, cell; };
 
 template <int PBITS, class ExactU>
 __device__ __forceinline__ bool accept_in_cell(double arg, CellP<PBITS> c, ExactU exact_u, m64::Tab tb)
 {
     return m64::exp_accept_prefix<PBITS>(arg, c.f, exact_u, tb);
+}
+template <int PBITS, class ExactU>
+__device__ __forceinline__ bool accept_in_cell(double arg, CellM<PBITS> c, ExactU exact_u, m64::Tab tb)
+{
+    return m64::exp_accept_prefix<PBITS, true>(arg, c.fm, exact_u, tb);
+}
+// kFloorMagicBits in a register the compiler cannot fold back into an immediate
+__device__ __forceinline__ uint32_t floor_magic_reg()
+{
+    uint32_t m;
+    asm volatile("mov.u32 %0, 0xCB400000;" : "=r"(m));
+    return m;
 }
 template <class ExactU>
 __device__ __forceinline__ bool accept_in_cell(double arg, CellF c, ExactU exact_u, m64::Tab tb)
@@ -353,6 +368,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
     // step uses only the sine half of its first pair and one that ends on an even step only the cosine half of its
     // last, so the result does not depend on how the steps are chunked into launches or store intervals.
 
+    const uint32_t magic = floor_magic_reg();
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     int64_t c = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     // the next chain's state is fetched while the current chain runs its K serial steps (hides the HBM latency
@@ -378,7 +394,9 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         }
         double e = potential<POT, ARITH>(x);
         // BETAS = false: β is a kernel-parameter constant (a constant-bank operand, no registers)
-        const double beta = BETAS ? (p.betas ? p.betas[c] : p.beta) : p.beta;
+        const double beta_nat = BETAS ? (p.betas ? p.betas[c] : p.beta) : p.beta;
+        // FAST: the accept argument is formed in binary-log units (CellM), β·log2e·(e − e')
+        const double beta = ARITH == ARITH_FAST ? beta_nat * 1.4426950408889634 : beta_nat;
         const uint64_t sid = p.sid0 + (uint64_t)c;
 
         // chain-only halves of the first three Philox rounds (rng.cuh); the rare refinement block is generated unhoisted
@@ -389,15 +407,15 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
         // uniform come from sub-block 1 of the pair and are only generated when the FP32 filter cannot decide (lazy refinement).
         struct PairDraws {
             double z0, z1;
-            uint32_t f0, f1;   // 12-bit / 11-bit prefixes of u_acc(2p), u_acc(2p+1)
+            uint32_t f0, f1;   // 12-bit / 11-bit prefixes of u_acc(2p), u_acc(2p+1), OR-ed into the filter's magic bits
             uint64_t pr;
         };
         auto gen_pair = [&](uint64_t pr) {
             PairDraws d;
             const U64Pair b0 = ph.block((uint32_t)pr);
             m64::box_muller_u64(u64_of(b0.a_lo, b0.a_hi), u64_of(b0.b_lo, b0.b_hi), tb, d.z0, d.z1);
-            d.f0 = b0.a_lo & 0xfffu;   // 12 bits: the radius uniform takes A >> 12
-            d.f1 = b0.b_lo & 0x7ffu;
+            d.f0 = m64::exp_prefix_bits<12>(b0.a_lo, magic);   // 12 bits: the radius uniform takes A >> 12
+            d.f1 = m64::exp_prefix_bits<11>(b0.b_lo, magic);   // (as the accept filter's addend bits: magic | prefix)
             d.pr = pr;
             return d;
         };
@@ -406,18 +424,18 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
             if constexpr (decltype(do0)::value) {
                 auto exact_u = [&]() {
                     const U64Pair r = philox_block<kTagMetropolis>(sid, d.pr, 1);
-                    return m64::u53_prefix_refine<12>(d.f0, r.a_lo, r.a_hi);
+                    return m64::u53_prefix_refine<12>(d.f0 & 0xfffu, r.a_lo, r.a_hi);
                 };
-                const CellP<12> ulo{d.f0};
+                const CellM<12> ulo{d.f0};
                 const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, inv0, d.z0, ulo, exact_u, tb);
                 count_if(acc, a);
             }
             if constexpr (decltype(do1)::value) {
                 auto exact_u = [&]() {
                     const U64Pair r = philox_block<kTagMetropolis>(sid, d.pr, 1);
-                    return m64::u53_prefix_refine<11>(d.f1, r.b_lo, r.b_hi);
+                    return m64::u53_prefix_refine<11>(d.f1 & 0x7ffu, r.b_lo, r.b_hi);
                 };
-                const CellP<11> ulo{d.f1};
+                const CellM<11> ulo{d.f1};
                 const uint32_t a = mc_step<POT, ARITH>(x, e, beta, sigma0, lognorm0, inv0, d.z1, ulo, exact_u, tb);
                 count_if(acc, a);
             }
@@ -1041,6 +1059,7 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const double *x, double 
 // 2 sqrt_pos(x) | 3 sincos_turn53(k) -> out[2i], out[2i+1] | 4 box_muller_u64(a, b) -> out[2i], out[2i+1] |
 // 5 accept test (x = a, prefix word = b, refinement word = c) -> out[2i] = filtered, out[2i+1] = reference decision |
 // 6 / 7 Philox block of (sid = b, p = c[, sub = a]) through PhiloxChain / philox_block -> out[4i .. 4i+3] = the 4 words
+// 10 / 11 accept test of the headline sweep (a = x·log2e, 11- / 12-bit prefix as addend bits) -> like 5 / 8
 __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const double *a, const uint64_t *b,
                                                             const uint64_t *cc, double *out, int64_t n,
                                                             const m64::MathTables *tables)
@@ -1063,6 +1082,23 @@ __global__ void __launch_bounds__(kBlock) debug_math_kernel(int kind, const doub
             else r = philox_block<kTagMetropolis>(b[i], cc[i], (uint32_t)a[i]);
             out[4 * i] = (double)r.a_lo; out[4 * i + 1] = (double)r.a_hi;
             out[4 * i + 2] = (double)r.b_lo; out[4 * i + 3] = (double)r.b_hi;
+        } else if (kind == 10 || kind == 11) {
+            // the headline sweep's form of the accept test: argument in binary-log units (a = y = x·log2e), prefix as
+            // the filter's pre-assembled addend bits; reference = the FP64 decision on x = RN(y·ln2)
+            const uint64_t r = cc[i];
+            const uint32_t magic = floor_magic_reg();
+            const double xr = a[i] * 0x1.62e42fefa39efp-1;
+            if (kind == 10) {
+                const uint32_t fm = m64::exp_prefix_bits<11>((uint32_t)b[i], magic);
+                auto exact_u = [&]() { return m64::u53_prefix_refine<11>(fm & 0x7ffu, (uint32_t)r, (uint32_t)(r >> 32)); };
+                out[2 * i] = m64::exp_accept_prefix<11, true>(a[i], fm, exact_u, tb) ? 1.0 : 0.0;
+                out[2 * i + 1] = m64::exp_accept_ref(xr, exact_u(), tb) ? 1.0 : 0.0;
+            } else {
+                const uint32_t fm = m64::exp_prefix_bits<12>((uint32_t)b[i], magic);
+                auto exact_u = [&]() { return m64::u53_prefix_refine<12>(fm & 0xfffu, (uint32_t)r, (uint32_t)(r >> 32)); };
+                out[2 * i] = m64::exp_accept_prefix<12, true>(a[i], fm, exact_u, tb) ? 1.0 : 0.0;
+                out[2 * i + 1] = m64::exp_accept_ref(xr, exact_u(), tb) ? 1.0 : 0.0;
+            }
         } else {
             const uint64_t r = cc[i];
             if (kind == 5) {

@@ -124,12 +124,11 @@ AM_CONST double kExpK[8] = {
 AM_CONST double kLogK[4] = {-2.0 / 7.0, 1.0 / 3.0, -0.4, -2.0 / 3.0};  // −2·log1p(r) = r(−2 + r(1 + k3 r + ½r² + k2 r³ + k1 r⁴ + k0 r⁵))
 // High-order coefficients whose terms are below 5·10^-11 of the result only need 20 mantissa bits: as doubles with a
 // zero low word they are encoded as 32-bit IMMEDIATES of DFMA/DMUL (no constant load, no register pair).  Truncation
-// errors: k2 r⁴·3.6e-7 < 2·10^-17, 1/120·φ⁴·6e-8 < 10^-19, 1/24·φ⁴·2.4e-7 < 10^-18 (|r| ≤ 2^-8, |φ| ≤ π/1024).
-constexpr double kLogK0t = -0x1.24924p-2;   // −2/7
-constexpr double kLogK1t = 0x1.55555p-2;    // 1/3
+// errors: k2 r⁴·3.6e-7 < 2·10^-17, 1/120·φ⁴·6e-8 < 10^-19, 1/12·φ⁴/2·2.4e-7 < 10^-18 (|r| ≤ 2^-8, |φ| ≤ π/1024).
+constexpr double kLogK10t = 0x1.3cf3cp-1;   // 1/3 + 2/7 = 13/21: k0 r + k1 = k0 (m rc) + (k1 − k0), with k0 rc from the table
 constexpr double kLogK2t = -0x1.99999p-2;   // −2/5
 constexpr double kTrig120t = 0x1.11111p-7;  // 1/120
-constexpr double kTrig24t = 0x1.55555p-5;   // 1/24
+constexpr double kTrigM12t = -0x1.55555p-4;  // −1/12
 AM_CONST double kSinK[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
                             -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};
 AM_CONST double kCosK[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
@@ -147,8 +146,12 @@ constexpr uint32_t kHxBase = 0x3fe6a09eu;  // high word of √½ (fdlibm's log r
 
 struct alignas(16) MathTables {
     double sincos[kTrigTab][2]; // (sin, cos)(2π·i/1024), correctly rounded; exact 0 / ±1 on the axes
-    double log_rc[kLogTab];    // 1 / c_i (c_i: centre of mantissa interval i; exactly 1.0 for the interval holding 1)
-    double log_m2lc[kLogTab];  // −2·ln(c_i) == +2·ln(rc_i), computed from the ROUNDED rc_i
+    // one 32-byte record per mantissa interval i, so that ONE index serves an LDS.128 and an LDS.64:
+    //   [0] rc_i = 1 / c_i (c_i: centre of the interval; exactly 1.0 for the interval holding 1)
+    //   [1] k0·rc_i, k0 = −2/7: the first Horner step k0 r + k1 of the log1p polynomial becomes ONE fma on m with a
+    //       single immediate, fma(m, k0 rc, k1 − k0) (two constants in one DFMA cost two MOVs per pair of steps)
+    //   [2] −2·ln(c_i) == +2·ln(rc_i), computed from the ROUNDED rc_i        [3] unused
+    double log_rec[kLogTab][4];
     double e_m2ln2[kETab];     // −2·E·ln2, index −E
     double exp2_j[kExpTab];    // 2^(j/32)
 };
@@ -165,8 +168,10 @@ static inline void build_math_tables(MathTables &T)
         double c = 0.5 * (a + b);
         if (a <= 1.0 && 1.0 < b) c = 1.0;
         const double rc = (double)(1.0L / (long double)c);
-        T.log_rc[i] = rc;
-        T.log_m2lc[i] = (c == 1.0) ? 0.0 : (double)(2.0L * __builtin_logl((long double)rc));
+        T.log_rec[i][0] = rc;
+        T.log_rec[i][1] = (double)((long double)rc * (-2.0L / 7.0L));
+        T.log_rec[i][2] = (c == 1.0) ? 0.0 : (double)(2.0L * __builtin_logl((long double)rc));
+        T.log_rec[i][3] = 0.0;
     }
     const long double two_pi = 6.283185307179586476925286766559005768L;
     for (int j = 0; j < kTrigTab / 4; ++j) {
@@ -215,8 +220,7 @@ AM_FN void tab_ld2(Tab t, uint32_t byte_off, double &a, double &b)
 }
 #endif
 constexpr uint32_t kOffSinCos = (uint32_t)offsetof(MathTables, sincos);
-constexpr uint32_t kOffLogRc = (uint32_t)offsetof(MathTables, log_rc);
-constexpr uint32_t kOffLogM2lc = (uint32_t)offsetof(MathTables, log_m2lc);
+constexpr uint32_t kOffLogRec = (uint32_t)offsetof(MathTables, log_rec);
 constexpr uint32_t kOffEM2ln2 = (uint32_t)offsetof(MathTables, e_m2ln2);
 constexpr uint32_t kOffExp2 = (uint32_t)offsetof(MathTables, exp2_j);
 
@@ -356,22 +360,53 @@ AM_FN float fma_floor_offset(float Es, uint32_t f)
 }
 // PBITS = length of the prefix (11 for the odd step of a pair, 12 for the even one: DESIGN.md "RNG stream layout");
 // the bound above is for PBITS + log2e·127 < 256 and 2^PBITS·1.17·2^-13 < 1, i.e. PBITS ≤ 12.
-template <int PBITS, class ExactU>
-AM_FN bool exp_accept_prefix(double x, uint32_t f, ExactU exact_u, Tab tb)
+// MAGIC = false: `fm` = f and `x` = the argument of exp.
+// MAGIC = true (the headline sweep): `fm` = the pre-assembled bits 0xCB400000 | f of the addend (built by the one LOP3
+// that extracts the prefix, exp_prefix_bits below) and `x` = the argument ALREADY IN BINARY-LOG UNITS, y = x·log2(e)
+// (the caller multiplies by β·log2e instead of β): the scaling FFMA becomes an FADD and its constant leaves the loop.
+// The bound above holds a fortiori (a = RN32(y): 2^-24|y|·ln2 = 2^-24|x|; no log2e rounding term); the exact path
+// recovers x = y·ln2 (one more rounding of the argument, 2^-53 relative: the FP64 decision is as sharp as before).
+constexpr uint32_t kFloorMagicBits = 0xCB400000u;           // bits(−1.5·2^23)
+template <int PBITS, bool MAGIC = false, class ExactU>
+AM_FN bool exp_accept_prefix(double x, uint32_t fm, ExactU exact_u, Tab tb)
 {
     static_assert(PBITS <= 12, "the one-sided floor form needs 2^PBITS * 1.17 * 2^-13 < 1");
     const float a = (float)x;
-    const float Es = ex2_approx(fmaf(a, 1.44269504f, (float)PBITS));
-    const float v = fma_floor_offset(Es, f);
+    const float Es = MAGIC ? ex2_approx(a + (float)PBITS) : ex2_approx(fmaf(a, 1.44269504f, (float)PBITS));
+    float v;
+    if constexpr (MAGIC) {
+#if AM_DEV
+        v = __fmaf_rd(Es, 0.9998779296875f, uint_as_float(fm));
+#else
+        v = fma_floor_offset(Es, fm & 0xfffu);
+#endif
+    } else {
+        v = fma_floor_offset(Es, fm);
+    }
     bool acc = (a >= 0.0f) || (v > -kFloorMagic);            // g ≥ 1
     const bool rej = v < -(kFloorMagic + 1.0f);              // g ≤ −2
     if (!(acc || rej)) {
+        if constexpr (MAGIC) x = x * 0x1.62e42fefa39efp-1;   // y·ln2: only this rare exact path needs the argument itself
         const uint32_t t = double2hi(x) - 0x7ff00000u;
         const bool core = (t - 0x00100000u) < (0x40962000u - 0x00100000u);  // x ∈ [−708, −0]
         const bool tiny_pos = t >= 0x80100000u;                             // 0 ≤ x, finite
         acc = tiny_pos || (core && (exp_core(x, tb) > exact_u()));
     }
     return acc;
+}
+
+// (w & (2^PBITS − 1)) | magic in ONE LOP3: `magic` must be a REGISTER holding kFloorMagicBits (an immediate would make
+// it two instructions: a LOP3 has one immediate slot).
+template <int PBITS>
+AM_FN uint32_t exp_prefix_bits(uint32_t w, uint32_t magic)
+{
+#if AM_DEV
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(w), "n"((1u << PBITS) - 1u), "r"(magic));   // (a & b) | c
+    return r;
+#else
+    return (w & ((1u << PBITS) - 1u)) | magic;
+#endif
 }
 
 // Filter cell from the top 23 bits of a raw 64-bit word whose u is (w >> 11)·2^-53 (XOSHIRO mode).
@@ -442,17 +477,18 @@ AM_FN double exact_div(double n, double d, double y)
 AM_FN double neg2log_core(uint32_t hx_folded, uint32_t lx, int negE, Tab tb)
 {
     const double m = hilo2double(hx_folded, lx);
-    const uint32_t i8 = ((hx_folded - kHxBase) >> 13) * 8u;   // byte offset of mantissa interval i
-    const double rc = tab_ld(tb, kOffLogRc + i8);
+    const uint32_t i32 = ((hx_folded - kHxBase) >> 13) * 32u;   // byte offset of the record of mantissa interval i
+    double rc, rck0;
+    tab_ld2(tb, kOffLogRec + i32, rc, rck0);
     const double r = fma64(m, rc, -1.0);    // |r| ≤ 2^-8
     // −2·log1p(r) = r·(−2 + r·(1 − (2/3)r + (1/2)r² − (2/5)r³ + (1/3)r⁴ − (2/7)r⁵))
-    double q = fma64(r, kLogK0t, kLogK1t);
+    double q = fma64(m, rck0, kLogK10t);    // = k0 r + k1
     q = fma64(q, r, kLogK2t);
     q = fma64(q, r, 0.5);
     q = fma64(q, r, kLogK[3]);
     q = fma64(q, r, 1.0);
     const double t = r * fma64(q, r, -2.0);
-    return (tab_ld(tb, kOffEM2ln2 + 8u * (uint32_t)negE) + tab_ld(tb, kOffLogM2lc + i8)) + t;
+    return (tab_ld(tb, kOffEM2ln2 + 8u * (uint32_t)negE) + tab_ld(tb, kOffLogRec + 16u + i32)) + t;
 }
 
 // From the integer n ∈ [1, 2^53) (clz normalisation; reference formulation used by the accuracy tests).
@@ -560,7 +596,8 @@ AM_FN void sincos_turn53_tab(uint32_t k_hi, uint32_t k_lo, Tab tb, double &sn, d
     const double z = phi * phi;
     const double ps = fma64(z, kTrig120t, kTrigK[1]);      // 1/120, −1/6
     const double sphi = fma64(z * phi, ps, phi);
-    const double cm1 = fma64(z, kTrig24t, -0.5) * z;       // 1/24
+    const double hz = z * -0.5;
+    const double cm1 = fma64(hz, z * kTrigM12t, hz);       // cos φ − 1 = −z/2·(1 − z/12): one immediate per instruction
     double S, C;
     tab_ld2(tb, kOffSinCos + 16u * i, S, C);
     sn = fma64(C, sphi, fma64(S, cm1, S));

@@ -36,12 +36,29 @@ void m64_accept(const double *x, const uint64_t *w, const uint64_t *r, int mode,
             filt[i] = exp_accept_prefix<11>(x[i], f, [&] { return u; }, Tab{&T});
             ref[i] = exp_accept_ref(x[i], u, Tab{&T});
             u_out[i] = u;
-        } else {
+        } else if (mode == 3) {
             const uint32_t f = lo & 0xfffu;
             const double u = u53_prefix_refine<12>(f, (uint32_t)r[i], (uint32_t)(r[i] >> 32));
             filt[i] = exp_accept_prefix<12>(x[i], f, [&] { return u; }, Tab{&T});
             ref[i] = exp_accept_ref(x[i], u, Tab{&T});
             u_out[i] = u;
+        } else {
+            // modes 4 / 5: the headline sweep's form -- x[i] is the argument in binary-log units (y = x log2e), the prefix
+            // arrives as the filter's addend bits; reference = the FP64 decision on RN(y ln2)
+            const double xr = x[i] * 0x1.62e42fefa39efp-1;
+            if (mode == 4) {
+                const uint32_t fm = exp_prefix_bits<11>(lo, kFloorMagicBits);
+                const double u = u53_prefix_refine<11>(fm & 0x7ffu, (uint32_t)r[i], (uint32_t)(r[i] >> 32));
+                filt[i] = exp_accept_prefix<11, true>(x[i], fm, [&] { return u; }, Tab{&T});
+                ref[i] = exp_accept_ref(xr, u, Tab{&T});
+                u_out[i] = u;
+            } else {
+                const uint32_t fm = exp_prefix_bits<12>(lo, kFloorMagicBits);
+                const double u = u53_prefix_refine<12>(fm & 0xfffu, (uint32_t)r[i], (uint32_t)(r[i] >> 32));
+                filt[i] = exp_accept_prefix<12, true>(x[i], fm, [&] { return u; }, Tab{&T});
+                ref[i] = exp_accept_ref(xr, u, Tab{&T});
+                u_out[i] = u;
+            }
         }
     }
 }

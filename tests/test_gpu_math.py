@@ -87,10 +87,11 @@ def test_device_philox_kat(eng):
     assert np.array_equal(got.astype(np.uint64), want)
 
 
-@pytest.mark.parametrize("pbits,kind", [(11, 5), (12, 8)])
+@pytest.mark.parametrize("pbits,kind", [(11, 5), (12, 8), (11, 10), (12, 11)])
 def test_device_fp32_filter_never_changes_a_decision(eng, pbits, kind):
-    """Integer-domain prefix filter (11-bit prefix: odd step of a pair, 12-bit: even step) on the DEVICE (MUFU.EX2,
-    F2I) against the plain FP64 decision, half of the cases adversarial near-ties."""
+    """Prefix filter (11-bit prefix: odd step of a pair, 12-bit: even step) on the DEVICE (MUFU.EX2, FFMA.RM) against
+    the plain FP64 decision, half of the cases adversarial near-ties.  Kinds 10 / 11: the headline sweep's form (argument
+    in binary-log units, prefix as the filter's addend bits)."""
     rng = np.random.default_rng(7 + pbits)
     n = 4_000_000
     x = -rng.random(n) * rng.choice([0.01, 1.0, 3.0, 30.0, 300.0], size=n)
@@ -102,7 +103,8 @@ def test_device_fp32_filter_never_changes_a_decision(eng, pbits, kind):
     rb = 53 - pbits
     w[:h] = (w[:h] & ~np.uint64(2 ** pbits - 1)) | (k >> np.uint64(rb))
     r[:h] = (k & np.uint64(2 ** rb - 1)) << np.uint64(64 - rb)
-    d = eng.debug_math(kind, a=x, b=w, c=r).reshape(-1, 2)
+    xin = x * 1.4426950408889634 if kind >= 10 else x
+    d = eng.debug_math(kind, a=xin, b=w, c=r).reshape(-1, 2)
     assert np.array_equal(d[:, 0], d[:, 1])
     u = np.concatenate([k.astype(np.float64) * 2.0 ** -53])
     with np.errstate(all="ignore"):

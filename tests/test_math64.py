@@ -116,11 +116,12 @@ def test_box_muller_matches_oracle_definition(lib):
     assert abs(zz.mean()) < 4 / np.sqrt(zz.size) and abs(zz.std() - 1) < 4 / np.sqrt(2 * zz.size)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 def test_fp32_filter_never_changes_a_decision(lib, mode):
     """mode 0: 23-bit cell of a 53-bit word (XOSHIRO path); mode 1 / 3: 11- / 12-bit prefix + lazy 42- / 41-bit
     refinement (native, odd / even step of a pair); mode 2: directed-rounding float cell of an arbitrary double u
-    (replay / EXACT paths)."""
+    (replay / EXACT paths); mode 4 / 5: the headline sweep's form of 1 / 3 (argument in binary-log units, prefix as the
+    filter's addend bits)."""
     rng = np.random.default_rng(6 + mode)
     n = 2_000_000
     x = -rng.random(n) * rng.choice([0.01, 1.0, 3.0, 30.0, 300.0], size=n)
@@ -132,7 +133,7 @@ def test_fp32_filter_never_changes_a_decision(lib, mode):
     k = np.clip(tie * 2.0 ** 53, 0, 2 ** 53 - 1).astype(np.uint64)
     if mode in (0, 2):
         w[:h] = (k << np.uint64(11)) | (w[:h] & np.uint64(0x7ff))
-    elif mode == 1:
+    elif mode in (1, 4):
         w[:h] = (w[:h] & ~np.uint64(0x7ff)) | (k >> np.uint64(42))
         r[:h] = (k & np.uint64(2 ** 42 - 1)) << np.uint64(22)
     else:
@@ -142,7 +143,12 @@ def test_fp32_filter_never_changes_a_decision(lib, mode):
     w = np.concatenate([w, rng.integers(0, 2 ** 64, size=11, dtype=np.uint64)])
     r = np.concatenate([r, rng.integers(0, 2 ** 64, size=11, dtype=np.uint64)])
     f, ref, u = np.empty(x.size, np.uint8), np.empty(x.size, np.uint8), np.empty(x.size)
-    lib.m64_accept(P(x), P(w), P(r), C.c_int(mode), P(f), P(ref), P(u), C.c_long(x.size))
+    xin = x
+    if mode >= 4:
+        with np.errstate(all="ignore"):
+            xin = x * 1.4426950408889634                # the sweep multiplies by β·log2e instead of β
+            x = xin * 0.6931471805599453                 # what the exact path evaluates: RN(y·ln2)
+    lib.m64_accept(P(xin), P(w), P(r), C.c_int(mode), P(f), P(ref), P(u), C.c_long(x.size))
     assert np.array_equal(f, ref)
     assert np.array_equal(u[:h], k.astype(np.float64) * 2.0 ** -53)             # bit-assembled uniform is exact
     with np.errstate(all="ignore"):
