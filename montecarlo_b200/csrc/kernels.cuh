@@ -478,17 +478,21 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MINB) sweep_philox_kernel(cons
                 // whole pairs only: ONE flat loop over the pairs of all intervals; a countdown marks the store points
                 // (a nested interval/pair loop makes the compiler rebuild the per-chain Philox constants in every
                 // interval's preheader: measured 6 % slower than this form)
+                // Loop control is ONE add, compare and branch per pair: the pair index is compared with the index of the
+                // next store point, and the end of the launch (always a store point) is tested inside that rare block
+                // (a countdown + the loop's own counter cost seven instructions per pair in an issue-bound loop)
                 int s = 0;
-                int left = p.series_K[0] >> 1;
-                const uint32_t pr1 = (uint32_t)(tend >> 1);
+                uint32_t pr = ta >> 1;
+                uint32_t next = pr + ((uint32_t)p.series_K[0] >> 1);
 #pragma unroll 1
-                for (uint32_t pr = ta >> 1; pr < pr1; ++pr) {
+                for (;;) {
                     do_steps(gen_pair((uint64_t)pr), T_{}, T_{});
-                    if (--left == 0) {
+                    if (++pr == next) {
                         sts_f64(a_se + 8u * kBlock * s, lds_f64(a_se + 8u * kBlock * s) + potential<POT, ARITH>(x));
                         sts_u32(a_da + 4u * kBlock * s, lds_u32(a_da + 4u * kBlock * s) + (acc - acc_prev));
                         acc_prev = acc;
-                        left = p.series_K[++s] >> 1;
+                        if (++s == p.n_series) break;
+                        next += (uint32_t)p.series_K[s] >> 1;
                     }
                 }
             } else

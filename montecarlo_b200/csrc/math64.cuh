@@ -152,7 +152,8 @@ struct alignas(16) MathTables {
     //       single immediate, fma(m, k0 rc, k1 − k0) (two constants in one DFMA cost two MOVs per pair of steps)
     //   [2] −2·ln(c_i) == +2·ln(rc_i), computed from the ROUNDED rc_i        [3] unused
     double log_rec[kLogTab][4];
-    double e_m2ln2[kETab];     // −2·E·ln2, index −E
+    double e_m2ln2[kETab];     // −2·E·ln2 at index n = 53 + E (E = −53 … 0): rising with the exponent field, so the
+                               // byte offset is (high word >> 17) & 0x7ff8 plus a constant -- no negation (IADD3) per pair
     double exp2_j[kExpTab];    // 2^(j/32)
 };
 
@@ -184,7 +185,7 @@ static inline void build_math_tables(MathTables &T)
         T.sincos[j + 2 * q][0] = -sj; T.sincos[j + 2 * q][1] = -cj;
         T.sincos[j + 3 * q][0] = -cj; T.sincos[j + 3 * q][1] = sj;
     }
-    for (int e = 0; e < kETab; ++e) T.e_m2ln2[e] = (double)(2.0L * e * 0.693147180559945309417232121458176568L);
+    for (int n = 0; n < kETab; ++n) T.e_m2ln2[n] = n <= 53 ? (double)(2.0L * (53 - n) * 0.693147180559945309417232121458176568L) : 0.0;
     for (int j = 0; j < kExpTab; ++j) T.exp2_j[j] = (double)__builtin_exp2l((long double)j / 32.0L);
 }
 
@@ -474,7 +475,7 @@ AM_FN double exact_div(double n, double d, double y)
 
 // ---- −2·ln(n·2^-53) --------------------------------------------------------------------------------------
 // Core: u = m·2^E with m ∈ [√½, √2) given by its words (hx, lx) after fdlibm's fold; i = mantissa interval.
-AM_FN double neg2log_core(uint32_t hx_folded, uint32_t lx, int negE, Tab tb)
+AM_FN double neg2log_core(uint32_t hx_folded, uint32_t lx, uint32_t n8, Tab tb)     // n8 = 8·(53 + E)
 {
     const double m = hilo2double(hx_folded, lx);
     const uint32_t i32 = ((hx_folded - kHxBase) >> 13) * 32u;   // byte offset of the record of mantissa interval i
@@ -488,7 +489,7 @@ AM_FN double neg2log_core(uint32_t hx_folded, uint32_t lx, int negE, Tab tb)
     q = fma64(q, r, kLogK[3]);
     q = fma64(q, r, 1.0);
     const double t = r * fma64(q, r, -2.0);
-    return (tab_ld(tb, kOffEM2ln2 + 8u * (uint32_t)negE) + tab_ld(tb, kOffLogRec + 16u + i32)) + t;
+    return (tab_ld(tb, kOffEM2ln2 + n8) + tab_ld(tb, kOffLogRec + 16u + i32)) + t;
 }
 
 // From the integer n ∈ [1, 2^53) (clz normalisation; reference formulation used by the accuracy tests).
@@ -502,7 +503,7 @@ AM_FN double neg2log_u53(uint64_t n, Tab tb)
     hx += 0x3ff00000u - kHxBase;            // fdlibm: fold the mantissa's top bit into the exponent
     E += (int)(hx >> 20) - 0x3ff;
     hx = (hx & 0x000fffffu) + kHxBase;
-    return neg2log_core(hx, lx, -E, tb);
+    return neg2log_core(hx, lx, 8u * (uint32_t)(53 + E), tb);
 }
 
 // Same value, from the two 32-bit halves of k = n (k_hi: top 21 bits, k_lo: low 32 bits): u = k·2^-53 is first
@@ -514,8 +515,8 @@ AM_FN double neg2log_words(uint32_t k_hi, uint32_t k_lo, Tab tb)
     const double dl = hilo2double(0x3FE00000u, k_lo);   // 2^-1 + k_lo·2^-53
     const double u = (dh - 2147483648.5) + dl;          // exact
     const uint32_t hx = double2hi(u) + (0x3ff00000u - kHxBase);
-    const int negE = 0x3ff - (int)(hx >> 20);           // −E ∈ [0, 53]
-    return neg2log_core((hx & 0x000fffffu) + kHxBase, double2lo(u), negE, tb);
+    const uint32_t n8 = ((hx >> 17) & 0x7ff8u) - 8u * 0x3cau;    // 8·(53 + E), E = (hx >> 20) − 0x3ff ∈ [−53, 0]
+    return neg2log_core((hx & 0x000fffffu) + kHxBase, double2lo(u), n8, tb);
 }
 
 // −2·ln(k·2^-52) for a 52-bit k given as (k_hi: top 20 bits, k_lo: low 32 bits), k ≥ 1: the Box-Muller radius of the
@@ -526,8 +527,8 @@ AM_FN double neg2log_k52(uint32_t k_hi, uint32_t k_lo, Tab tb)
 {
     const double kd = hilo2double(0x43300000u | k_hi, k_lo) - 4503599627370496.0;   // exact
     const uint32_t hx = double2hi(kd) + (0x3ff00000u - kHxBase);
-    const int negE = (0x3ff + 52) - (int)(hx >> 20);    // −E ∈ [0, 52]
-    return neg2log_core((hx & 0x000fffffu) + kHxBase, double2lo(kd), negE, tb);
+    const uint32_t n8 = ((hx >> 17) & 0x7ff8u) - 8u * 0x3feu;    // 8·(53 + E), E = (hx >> 20) − (0x3ff + 52) ∈ [−52, 0]
+    return neg2log_core((hx & 0x000fffffu) + kHxBase, double2lo(kd), n8, tb);
 }
 
 // ---- √w, w > 0 normal ---------------------------------------------------------------------------------------
