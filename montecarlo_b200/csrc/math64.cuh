@@ -384,7 +384,9 @@ AM_FN bool exp_accept_prefix(double x, uint32_t fm, ExactU exact_u, Tab tb)
     } else {
         v = fma_floor_offset(Es, fm);
     }
-    bool acc = (a >= 0.0f) || (v > -kFloorMagic);            // g ≥ 1
+    // MAGIC: no test of a ≥ 0 (one FSETP per step).  For y ≥ 0, Es ≥ 2^P(1 − 2^-22) gives floor(Es·c) ≥ 2^P − 1 ≥ f,
+    // i.e. g ≥ 0: accepted here unless f = 2^P − 1, which the exact path accepts (x ≥ 0: tiny_pos, or exp(−0) = 1 > u).
+    bool acc = MAGIC ? (v > -kFloorMagic) : ((a >= 0.0f) || (v > -kFloorMagic));            // g ≥ 1
     const bool rej = v < -(kFloorMagic + 1.0f);              // g ≤ −2
     if (!(acc || rej)) {
         if constexpr (MAGIC) x = x * 0x1.62e42fefa39efp-1;   // y·ln2: only this rare exact path needs the argument itself
