@@ -5,7 +5,7 @@ set -u
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_n$N.txt 2>&1
-if [ "$N" = "2" ]; then
+if [ "$N" = "2" ] && [ "${SKIP_TESTS:-0}" = "0" ]; then
   echo "== pytest two_gpu"
   timeout 900 python -m pytest tests -m gpu -q -x -k "two_gpu" 2>&1 | tail -3 | tee gpurun_out/pytest_2gpu.log
 fi
