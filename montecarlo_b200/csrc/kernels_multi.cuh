@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MULTI_MINB) sweep_multi_kernel
     const uint32_t a_rec = tb.s + off_rec + 8u * (uint32_t)(warp * p.n_int * V);
     const uint32_t buf_flip = p.dbuf ? cnt_bytes : 0u;
     const size_t pitch_b = (size_t)p.pitch * 4;
+    const uint32_t magic = floor_magic_reg();
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     uint32_t steps_launch = 0;                            // (hoisted by hand: the compiler re-summed K[] per chain)
     for (int i = 0; i < p.n_int; ++i) steps_launch += (uint32_t)p.K[i];
@@ -155,7 +156,9 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MULTI_MINB) sweep_multi_kernel
             cp_async_wait_all();
         }
         double e = potential<POT, ARITH>(x);
-        const double beta = BETAS ? ((p.betas && live) ? p.betas[c] : p.beta) : p.beta;
+        const double beta_nat = BETAS ? ((p.betas && live) ? p.betas[c] : p.beta) : p.beta;
+        // FAST: the accept argument is formed in binary-log units (CellM, kernels.cuh), β·log2e·(e − e')
+        const double beta = ARITH == ARITH_FAST ? beta_nat * 1.4426950408889634 : beta_nat;
         const uint64_t sid = p.sid0 + (uint64_t)c;
         const PhiloxChain<kTagMetropolis, 0> ph(sid);
         const PhiloxChain<kTagMetropolis, 2> ph_cat(sid);
@@ -197,20 +200,20 @@ __global__ void __launch_bounds__(kBlock, ARIANNA_MULTI_MINB) sweep_multi_kernel
             }
             const bool hi = (pr & 1u) != 0;              // steps 4q+2, 4q+3 take the B words
             if constexpr (decltype(do0)::value) {
-                const uint32_t f0 = b0.a_lo & 0xfffu;
+                const uint32_t f0 = m64::exp_prefix_bits<12>(b0.a_lo, magic);     // prefix | the filter's magic bits
                 auto exact_u = [&]() {
                     const U64Pair r = philox_block<kTagMetropolis>(sid, (uint64_t)pr, 1);
-                    return m64::u53_prefix_refine<12>(f0, r.a_lo, r.a_hi);
+                    return m64::u53_prefix_refine<12>(f0 & 0xfffu, r.a_lo, r.a_hi);
                 };
-                one_step(hi ? cat.b_lo : cat.a_lo, z0, CellP<12>{f0}, exact_u);
+                one_step(hi ? cat.b_lo : cat.a_lo, z0, CellM<12>{f0}, exact_u);
             }
             if constexpr (decltype(do1)::value) {
-                const uint32_t f1 = b0.b_lo & 0x7ffu;
+                const uint32_t f1 = m64::exp_prefix_bits<11>(b0.b_lo, magic);
                 auto exact_u = [&]() {
                     const U64Pair r = philox_block<kTagMetropolis>(sid, (uint64_t)pr, 1);
-                    return m64::u53_prefix_refine<11>(f1, r.b_lo, r.b_hi);
+                    return m64::u53_prefix_refine<11>(f1 & 0x7ffu, r.b_lo, r.b_hi);
                 };
-                one_step(hi ? cat.b_hi : cat.a_hi, z1, CellP<11>{f1}, exact_u);
+                one_step(hi ? cat.b_hi : cat.a_hi, z1, CellM<11>{f1}, exact_u);
             }
         };
         using T_ = std::true_type;
