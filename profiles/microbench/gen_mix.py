@@ -17,6 +17,18 @@ MIX = collections.OrderedDict([     # SASS opcode -> count per pair (r02 capture
 ])
 assert sum(MIX.values()) + 1 == 141          # + the loop's own backward branch
 
+# The same loop at the END of round 2 (125 instructions per pair: one-FFMA accept filter, table-folded Horner step,
+# single-compare loop control; opcode counts from cuobjdump of the shipped kernel's flat series loop, hot path only).
+# FADD and FFMA.RM are modelled as FFMA, LEA.HI / BSSY / BSYNC / not-taken BRA as integer adds.   --final selects it.
+MIX_FINAL = collections.OrderedDict([
+    ("LOP3", 26), ("DFMA", 23), ("IMAD.WIDE", 16), ("DMUL", 13), ("VIADD", 6 + 2 + 2 + 2 + 2),
+    ("MOV", 2), ("FFMA", 2 + 2), ("FSEL", 4), ("DADD", 3), ("SHF", 3 + 2), ("LDS64", 2), ("LDS128", 2),
+    ("ISETP", 1), ("FSETP", 4), ("F2F", 2), ("EX2", 2), ("RSQ64H", 1),
+])
+assert sum(MIX_FINAL.values()) + 1 == 125
+if "--final" in sys.argv:
+    MIX = MIX_FINAL
+
 # Every result must be CONSUMED (ptxas deletes dead instructions whatever `volatile` says): instructions whose result
 # the sweep uses elsewhere ("sinks": conversions, loads, shifts, moves, MUFU) hand their value to an instruction of the
 # mix that exists anyway -- 32-bit integers to a LOP3 source, doubles to a DFMA addend, floats to an FMUL operand,
