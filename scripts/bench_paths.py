@@ -1,6 +1,6 @@
 """Secondary measurements of the other §8 paths on one B200 (all through the C ABI): K sweep of the native kernel,
 EXACT arithmetic, multi-move pools, replay (HBM-bound), the XOSHIRO device generator, the PGMC estimator (C4) and the
-trajectory write-back (C5).  Prints one JSON line per measurement; `scripts/gpu_paths.sh` stores them.  Every line
+trajectory write-back (C5).  Prints one JSON line per measurement; `scripts/gpu_evidence.sh` stores them.  Every line
 carries the NVML clock / throttle-reason record sampled DURING its own timed region (bench.py's ClockSampler), CUDA
 events on the launching stream after warm-up, inputs larger than L2.  Optional argv: section names (native f32 multi pgmc replay xoshiro c5)."""
 import json, os, sys, time

@@ -1,6 +1,6 @@
 #!/bin/bash
 # multi-GPU evidence: both arms at N GPUs with the driver's flags (+ the 2-GPU NCCL tests at N = 2).
-# Usage: gpurun --gpus N -- bash scripts/gpu_r02_n.sh N
+# Usage: gpurun --gpus N -- bash scripts/gpu_evidence_n.sh N
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
