@@ -500,6 +500,21 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
+def test_bench_emits_strict_json(capsys):
+    """bench.py's line must be JSON a strict parser accepts: non-finite floats (the PCIe breakdown of a direction a job
+    did not use is NaN) become null at any nesting depth; Python's own json would print the non-standard `NaN`."""
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    bench.emit({"a": float("nan"), "b": [1.5, float("inf"), {"c": float("-inf"), "d": np.float64("nan")}], "e": 3, "f": "x"})
+    out = capsys.readouterr().out.strip()
+
+    def strict(name):
+        raise AssertionError(name)
+    assert json.loads(out, parse_constant=strict) == {"a": None, "b": [1.5, None, {"c": None, "d": None}], "e": 3, "f": "x"}
+
+
 def test_bench_refuses_to_run_without_a_gpu():
     import subprocess
     import sys
